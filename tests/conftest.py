@@ -1,0 +1,53 @@
+import json
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+for p in (ROOT, os.path.join(ROOT, "oracle")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run with -m gpu on the B200 box)")
+
+
+def load_golden(name):
+    with open(os.path.join(GOLDEN, name)) as f:
+        return json.load(f)
+
+
+@pytest.fixture(scope="session")
+def golden_scores():
+    return load_golden("tree_scores.json")
+
+
+@pytest.fixture(scope="session")
+def golden_vectors():
+    return load_golden("vectors.json")
+
+
+@pytest.fixture(scope="session")
+def golden_canon():
+    return load_golden("canon.json")
+
+
+@pytest.fixture(scope="session")
+def golden_constants():
+    return load_golden("constants.json")
+
+
+@pytest.fixture(scope="session")
+def golden_search():
+    return load_golden("search.json")
+
+
+def has_cuda():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False

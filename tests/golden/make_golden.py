@@ -1,0 +1,237 @@
+"""Generates tests/golden/*.json by calling the UNMODIFIED reference functions
+(imported from /root/reference through oracle/ref_shim.py).  Run in the build
+container only (the GPU box has no /root/reference):
+
+    python tests/golden/make_golden.py
+
+Everything is seeded; re-running reproduces the committed files bit for bit
+(up to json float repr, which round-trips fp64 exactly).
+"""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import ref_shim  # noqa: E402
+
+ref = ref_shim.load()
+cl = ref.clustering
+tt = ref.tree_tools
+
+
+def dump(name, obj):
+    with open(os.path.join(HERE, name), "w") as f:
+        json.dump(obj, f, indent=0, separators=(",", ":"))
+    print("wrote", name)
+
+
+def ref_tables(As, Bs, err, K_prior):
+    K, M = As.shape
+    D = np.array([[cl.distrib(As[k, m], Bs[k, m], err) for m in range(M)] for k in range(K)])
+    P = np.array([[cl.prior_fractions(K_prior) for m in range(M)] for k in range(K)])
+    return D, P
+
+
+def random_tree(rng, k):
+    """random labeled rooted tree as a parent vector with arbitrary root position."""
+    perm = rng.permutation(k)
+    parent = [-2] * k
+    parent[perm[0]] = -1
+    for i in range(1, k):
+        parent[perm[i]] = int(perm[rng.integers(0, i)])
+    return parent
+
+
+# ---------------------------------------------------------------- 1. tree scores
+def gen_scores():
+    cases = []
+    # SURVEY 8a G1..G8 inputs, recomputed here (not transcribed) -------------------
+    g_as = np.array([[17647, 28962, 31830], [65454, 115303, 57305], [2259, 8349, 3164], [13461, 6383, 11212]])
+    g_bs = np.array([[52353, 41038, 38170], [324546, 274697, 332695], [37741, 31651, 36836], [286539, 293617, 288788]])
+    fixed = [
+        ("G1", g_as, g_bs, 0.001, [-1, 0, 1, 2]),
+        ("G2", g_as, g_bs, 0.001, [-1, 0, 0, 0]),
+        ("G3", g_as, g_bs, 0.001, [-1, 0, 0, 1]),
+        ("G4", np.array([[90, 40]]), np.array([[110, 160]]), 0.003, [-1]),
+        ("G5", np.array([[95, 60], [30, 10]]), np.array([[105, 140], [170, 190]]), 0.003, [-1, 0]),
+        ("G6", np.array([[95, 60], [30, 10]]), np.array([[105, 140], [170, 190]]), 0.003, [1, -1]),
+        ("G7", np.array([[800], [300], [250]]), np.array([[1200], [1700], [1750]]), 0.003, [-1, 0, 0]),
+        ("G8", np.array([[400, 380], [150, 30], [120, 200], [60, 10], [20, 90]]),
+         np.array([[600, 620], [850, 970], [880, 800], [940, 990], [980, 910]]), 0.01, [2, 2, -1, 0, 0]),
+    ]
+    for name, As, Bs, err, tree in fixed:
+        D, P = ref_tables(As, Bs, err, As.shape[0])
+        s = cl.tree_integrate_multisample(tree, D, P)
+        cases.append(dict(id=name, var=As.tolist(), ref=Bs.tolist(), err=err, K_prior=int(As.shape[0]),
+                          tree=tree, nodes=list(range(As.shape[0])), per_sample=s.tolist(), total=float(np.sum(s))))
+    # random cases: varied K, coverage, err, root position, node subsets -------------
+    rng = np.random.default_rng(20261019)
+    n = 0
+    for K in (1, 2, 3, 4, 5, 6, 7):
+        for rep in range(3 if K <= 5 else 2):
+            M = int(rng.integers(1, 4))
+            cov = int(rng.choice([30, 200, 2000, 40000, 400000]))
+            frac = rng.dirichlet(np.ones(K + 1))[:K]
+            frac = np.sort(frac)[::-1]
+            cm = np.clip(np.cumsum(frac[::-1])[::-1][:, None] * rng.uniform(0.6, 1.0, size=(K, M)), 0, 1)
+            err = float(rng.choice([0.0005, 0.001, 0.003, 0.01]))
+            As = rng.binomial(cov, cm * (0.5 - err) + err)
+            Bs = cov - As
+            # a node subset (partial forest component) half of the time
+            k = K if (rep % 2 == 0 or K == 1) else int(rng.integers(1, K + 1))
+            nodes = sorted(rng.choice(K, size=k, replace=False).tolist()) if k < K else list(range(K))
+            if rep == 1 and k > 1:
+                nodes = [int(x) for x in rng.permutation(nodes)]
+            tree = random_tree(rng, k)
+            D, P = ref_tables(As, Bs, err, K)
+            s = cl.tree_integrate_multisample(np.array(tree), D[nodes], P[nodes])
+            cases.append(dict(id="R%d" % n, var=As.tolist(), ref=Bs.tolist(), err=err, K_prior=K, tree=tree,
+                              nodes=[int(x) for x in nodes], per_sample=s.tolist(), total=float(np.sum(s))))
+            n += 1
+    dump("tree_scores.json", cases)
+
+
+# ------------------------------------------------------------- 2. vector operators
+def gen_vectors():
+    rng = np.random.default_rng(7)
+    out = {"distrib": [], "convolve": [], "trap_int": []}
+    for a, b, err in [(0, 0, 0.001), (1, 0, 0.001), (0, 7, 0.01), (90, 110, 0.003), (17647, 52353, 0.001),
+                      (324546, 65454, 0.001), (2000000, 10, 0.0001)]:
+        y = cl.distrib(a, b, err)
+        out["distrib"].append(dict(a=a, b=b, err=err, idx=list(range(0, 512, 7)) + [511],
+                                   y=y[list(range(0, 512, 7)) + [511]].tolist()))
+    for (a1, b1, a2, b2, err) in [(90, 110, 30, 170, 0.003), (17647, 52353, 2259, 37741, 0.001),
+                                  (5, 3, 900, 100, 0.01), (65454, 324546, 13461, 286539, 0.001)]:
+        u = cl.distrib(a1, b1, err)
+        v = cl.distrib(a2, b2, err)
+        c = cl.my_convolve(u, v)
+        t = cl.trap_int(c)
+        sel = list(range(0, 512, 5)) + [511]
+        out["convolve"].append(dict(a1=a1, b1=b1, a2=a2, b2=b2, err=err, idx=sel, y=c[sel].tolist()))
+        out["trap_int"].append(dict(a1=a1, b1=b1, a2=a2, b2=b2, err=err, idx=sel, y=t[sel].tolist()))
+    dump("vectors.json", out)
+
+
+# --------------------------------------------------------------- 3. canon weights
+def gen_canon():
+    import pickle
+    with open("/root/reference/AllTrees.txt", "rb") as f:
+        T, S = pickle.load(f, encoding="latin1")
+    rng = np.random.default_rng(11)
+    out = {"alltrees_counts": [len(t) for t in T], "alltrees_scre": {}, "random": []}
+    for K in range(1, 8):
+        out["alltrees_scre"][str(K)] = [dict(tree=[int(x) for x in t], scre=int(tt.canonizeF(t)["scre"]),
+                                             canstr=tt.canonizeF(t)["canstr"]) for t in T[K]]
+    for K in range(2, 11):
+        for _ in range(40):
+            t = random_tree(rng, K)
+            r = tt.canonizeF(t)
+            out["random"].append(dict(tree=t, scre=int(r["scre"]), canstr=r["canstr"]))
+    # canonical strings of every AllTrees topology (for the set-equality test of our enumerator)
+    out["alltrees_canstr"] = {str(K): sorted(tt.canonizeF(t)["canstr"] for t in T[K]) for K in range(1, 11)}
+    dump("canon.json", out)
+
+
+# ----------------------------------------------------------- 4. clustering constants
+def gen_constants():
+    rng = np.random.default_rng(5)
+    out = {"part_func": [], "penalty": [], "clustering": []}
+    for n, kmax in [(1, 5), (3, 5), (4, 3), (10, 4), (50, 5), (80, 5), (500, 7), (80, 12), (6, 12)]:
+        out["part_func"].append(dict(n=n, kmax=kmax, pf=cl.part_func(n, kmax).tolist()))
+    for n, kmax, K in [(10, 4, 4), (50, 5, 3), (80, 5, 5), (80, 12, 9), (200, 8, 1)]:
+        pf = cl.part_func(n, kmax)
+        assign = np.concatenate([np.arange(K), rng.integers(0, K, n - K)])
+        rng.shuffle(assign)
+        out["penalty"].append(dict(n=n, kmax=kmax, assign=assign.tolist(),
+                                   value=float(cl.log_conf_penalty(assign, pf))))
+    for (N, M, K, cov) in [(12, 2, 3, 200), (30, 3, 4, 1000), (50, 3, 5, 200)]:
+        pf = cl.part_func(N, 6)
+        assign = np.concatenate([np.arange(K), rng.integers(0, K, N - K)])
+        am = rng.binomial(cov, rng.uniform(0.02, 0.45, size=(N, M)))
+        bm = cov - am
+        c = cl.clustering(am, bm, assign, pf, 0.002)
+        out["clustering"].append(dict(am=am.tolist(), bm=bm.tolist(), assign=assign.tolist(), pf=pf.tolist(), err=0.002,
+                                      As=c.As.tolist(), Bs=c.Bs.tolist(), maxlikelihood=float(c.maxlikelihood),
+                                      cluster_prior=float(c.cluster_prior)))
+    dump("constants.json", out)
+
+
+# ------------------------------------------------------------------ 5. search path
+def simdata(K, M, N, seed, T, coverage=200, error=0.003):
+    """simdata.py:18-31 through the reference's own get_matrix (legacy global RNG)."""
+    np.random.seed(seed)
+    ind = np.random.randint(len(T[K]))
+    true_tree = T[K][ind]
+    true_sm = np.array([np.random.dirichlet(np.ones(K + 1))[:K] for m in range(M)])
+    B = tt.get_matrix(true_tree)[0]
+    true_cm = np.array([B.dot(x) for x in true_sm]).transpose()
+    ps = np.random.dirichlet(np.ones(K))
+    assign = np.random.choice(range(K), N - 2 * K, p=ps)
+    assign = np.concatenate((np.repeat(np.arange(K), 2), assign))
+    covs = coverage * np.ones((N, M)).astype(int)
+    As = np.random.binomial(covs, true_cm[assign] * (0.5 - error) + error)
+    return As, covs - As, assign, [int(x) for x in true_tree]
+
+
+def gen_search():
+    """reorder -> candidate -> threshold -> get_trees2 -> analysed scores, on small inputs
+    (each reference eval costs 0.05-1 s, so K <= 4 here)."""
+    import contextlib
+    import io
+    import pickle
+    with open("/root/reference/AllTrees.txt", "rb") as f:
+        T, S = pickle.load(f, encoding="latin1")
+    out = []
+    specs = [dict(K=3, M=2, N=24, seed=101, err=0.003, cov=200),
+             dict(K=4, M=3, N=50, seed=12345, err=0.001, cov=200),
+             dict(K=4, M=2, N=40, seed=77, err=0.003, cov=60),
+             dict(K=2, M=3, N=20, seed=3, err=0.01, cov=500)]
+    for sp in specs:
+        t0 = time.time()
+        am, bm, assign, true_tree = simdata(sp["K"], sp["M"], sp["N"], sp["seed"], T, coverage=sp["cov"])
+        # clustering = the true assignment, first-seen relabelled (what bamse.py:23 does to KMeans labels)
+        assign = tt.reorder_assignmens(assign)
+        pf = cl.part_func(sp["N"], 6)
+        c = cl.clustering(am, bm, tuple(int(x) for x in assign), pf, sp["err"])
+        with contextlib.redirect_stdout(io.StringIO()):
+            c.reorder()
+            cand = c.get_candidate_tree()[0]
+            K = c.As.shape[0]
+            thr = c.get_tree_score(cand["tree"], list(range(K))) + np.log(tt.canonizeF(cand["tree"])["scre"])
+            trees = c.get_trees2(cand)
+        kept = []
+        for t in trees:
+            sc = c.get_tree_score(t["tree"], list(range(K)))
+            scre = int(tt.canonizeF(t["tree"])["scre"])
+            kept.append(dict(tree=[int(x) for x in t["tree"]], root=int(t["root"]), score=float(sc), scre=scre,
+                             totalscore=float(sc + np.log(scre) + c.cluster_prior + c.maxlikelihood)))
+        # the 2-node scores that drive reorder(), in ORIGINAL labels (before reorder)
+        out.append(dict(spec=sp, am=am.tolist(), bm=bm.tolist(), assign_in=[int(x) for x in assign],
+                        true_tree=true_tree, pf=pf.tolist(),
+                        order=[int(x) for x in c.order], assign_out=[int(x) for x in c.assign],
+                        As=c.As.tolist(), Bs=c.Bs.tolist(), candidate=[int(x) for x in cand["tree"]],
+                        threshold=float(thr), kept=kept, cluster_prior=float(c.cluster_prior),
+                        maxlikelihood=float(c.maxlikelihood)))
+        print("search case", sp, "kept", len(kept), "%.1fs" % (time.time() - t0))
+    dump("search.json", out)
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["scores", "vectors", "canon", "constants", "search"]
+    t0 = time.time()
+    if "scores" in which:
+        gen_scores()
+    if "vectors" in which:
+        gen_vectors()
+    if "canon" in which:
+        gen_canon()
+    if "constants" in which:
+        gen_constants()
+    if "search" in which:
+        gen_search()
+    print("done in %.1fs" % (time.time() - t0))
