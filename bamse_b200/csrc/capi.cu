@@ -1,0 +1,497 @@
+// C ABI of libbamse_cuda.so (include/bamse_cuda.h).  Host-side orchestration only:
+// argument checks, host<->device copies, kernel launches.  No CPU scoring path exists.
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "kernels.cuh"
+#include "tree_decode.cuh"
+
+using namespace bamse;
+
+namespace {
+thread_local std::string g_create_error;
+
+struct DBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e == cudaSuccess) cap = bytes;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+}  // namespace
+
+struct bamse_ctx {
+    int device = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    int64_t launches = 0;
+    int64_t last_evals = 0;
+
+    // resident problem
+    bool have_problem = false;
+    int P = 0, C = 0, M = 0, Kmax = 0;
+    std::vector<int32_t> K_of_c;
+    DBuf d_K, d_p0, d_var, d_ref, d_logc, d_logcf, d_log1mcf, d_D64, d_D32;
+
+    // work buffers
+    DBuf d_segs, d_scalars /* total_chunks, total_trees, next_chunk */, d_cand, d_items, d_scores;
+    DBuf d_const, d_thr, d_begin, d_end, d_records, d_dense0, d_dense1;
+    int grid[2] = {0, 0};
+
+    int fail(int code, const char* fmt, ...) {
+        char buf[512];
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(buf, sizeof buf, fmt, ap);
+        va_end(ap);
+        err = buf;
+        return code;
+    }
+    ProblemView view() const {
+        ProblemView v;
+        v.P = P; v.C = C; v.M = M; v.Kmax = Kmax;
+        v.K_of_c = d_K.as<int32_t>(); v.p0 = d_p0.as<double>();
+        v.D64 = d_D64.as<double>(); v.D32 = d_D32.as<float>();
+        return v;
+    }
+};
+
+#define CTX_CHECK(ctx)                      \
+    do {                                    \
+        if (!(ctx)) return BAMSE_EINVAL;    \
+        cudaSetDevice((ctx)->device);       \
+    } while (0)
+
+extern "C" {
+
+int bamse_abi_version(void) { return BAMSE_ABI_VERSION; }
+
+const char* bamse_last_error(const bamse_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int bamse_create(bamse_ctx** out, int device_ordinal) {
+    if (!out) { g_create_error = "bamse_create: out is NULL"; return BAMSE_EINVAL; }
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        g_create_error = std::string("bamse_create: no CUDA device (") + cudaGetErrorString(e) +
+                         "); libbamse_cuda has no CPU fallback";
+        cudaGetLastError();
+        return BAMSE_ENODEV;
+    }
+    if (device_ordinal < 0 || device_ordinal >= n) {
+        g_create_error = "bamse_create: device ordinal out of range";
+        return BAMSE_EINVAL;
+    }
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device_ordinal)) != cudaSuccess) {
+        g_create_error = std::string("bamse_create: ") + cudaGetErrorString(e);
+        return BAMSE_ECUDA;
+    }
+    if (prop.major != 10) {
+        char b[160];
+        snprintf(b, sizeof b, "bamse_create: device %d is sm_%d%d; this library is built for sm_100a only",
+                 device_ordinal, prop.major, prop.minor);
+        g_create_error = b;
+        return BAMSE_ENODEV;
+    }
+    bamse_ctx* c = new (std::nothrow) bamse_ctx();
+    if (!c) { g_create_error = "bamse_create: out of host memory"; return BAMSE_ENOMEM; }
+    c->device = device_ordinal;
+    cudaSetDevice(device_ordinal);
+    if ((e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking)) != cudaSuccess) {
+        g_create_error = std::string("bamse_create: ") + cudaGetErrorString(e);
+        delete c;
+        return BAMSE_ECUDA;
+    }
+    c->stream = c->own_stream;
+    *out = c;
+    return BAMSE_OK;
+}
+
+void bamse_destroy(bamse_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    DBuf* bufs[] = {&ctx->d_K, &ctx->d_p0, &ctx->d_var, &ctx->d_ref, &ctx->d_logc, &ctx->d_logcf, &ctx->d_log1mcf,
+                    &ctx->d_D64, &ctx->d_D32, &ctx->d_segs, &ctx->d_scalars, &ctx->d_cand, &ctx->d_items,
+                    &ctx->d_scores, &ctx->d_const, &ctx->d_thr, &ctx->d_begin, &ctx->d_end, &ctx->d_records,
+                    &ctx->d_dense0, &ctx->d_dense1};
+    for (DBuf* b : bufs) b->release();
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+}
+
+int bamse_set_stream(bamse_ctx* ctx, void* cuda_stream) {
+    CTX_CHECK(ctx);
+    ctx->stream = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : ctx->own_stream;
+    return BAMSE_OK;
+}
+
+int64_t bamse_launch_count(const bamse_ctx* ctx) { return ctx ? ctx->launches : 0; }
+int64_t bamse_last_eval_count(const bamse_ctx* ctx) { return ctx ? ctx->last_evals : 0; }
+
+int bamse_decode_tree(int K, uint64_t tree_index, int8_t* out_parent) {
+    if (K < 1 || K > KMAX || !out_parent) return BAMSE_EINVAL;
+    if (tree_index >= ipow_u64(K, K - 1)) return BAMSE_EINVAL;
+    decode_tree(K, tree_index, out_parent);
+    return BAMSE_OK;
+}
+
+int bamse_upload_problem(bamse_ctx* ctx, int P, const double* err, int C, int M, int Kmax, const int32_t* K_of_c,
+                         const int64_t* var_counts, const int64_t* ref_counts) {
+    CTX_CHECK(ctx);
+    ctx->have_problem = false;
+    if (P < 1 || C < 1 || M < 1 || M > BAMSE_MMAX || Kmax < 1 || Kmax > KMAX || !err || !K_of_c || !var_counts ||
+        !ref_counts)
+        return ctx->fail(BAMSE_EINVAL, "bamse_upload_problem: bad sizes (P=%d C=%d M=%d Kmax=%d) or NULL pointer", P,
+                         C, M, Kmax);
+    for (int p = 0; p < P; ++p)
+        if (!(err[p] > 0.0) || !(err[p] < 0.5))
+            return ctx->fail(BAMSE_EINVAL, "bamse_upload_problem: err[%d]=%g must be in (0, 0.5)", p, err[p]);
+    for (int c = 0; c < C; ++c)
+        if (K_of_c[c] < 1 || K_of_c[c] > Kmax)
+            return ctx->fail(BAMSE_EINVAL, "bamse_upload_problem: K_of_c[%d]=%d out of [1,%d]", c, K_of_c[c], Kmax);
+    const size_t ncnt = (size_t)C * Kmax * M;
+    std::vector<double> var(ncnt, 0.0), ref(ncnt, 0.0), logc(ncnt, 0.0), p0(C);
+    for (int c = 0; c < C; ++c) {
+        const int K = K_of_c[c];
+        p0[c] = 1.0 / K * (0.0 - lgamma((double)K));                         // clustering.py:29
+        for (int k = 0; k < K; ++k)
+            for (int m = 0; m < M; ++m) {
+                const size_t i = ((size_t)c * Kmax + k) * M + m;
+                const int64_t a = var_counts[i], b = ref_counts[i];
+                if (a < 0 || b < 0)
+                    return ctx->fail(BAMSE_EINVAL, "bamse_upload_problem: negative read count at c=%d k=%d m=%d", c,
+                                     k, m);
+                var[i] = (double)a; ref[i] = (double)b;
+                // gammaln(a+b+1) - gammaln(a+1) - gammaln(b+1)                  clustering.py:23
+                logc[i] = lgamma((double)(a + b) + 1.0) - lgamma((double)a + 1.0) - lgamma((double)b + 1.0);
+            }
+    }
+    // log(cf_x), log(1-cf_x) on x = linspace(0,1,512)                          clustering.py:21-23
+    std::vector<double> logcf((size_t)P * L), log1mcf((size_t)P * L);
+    const double step = 1.0 / (double)(L - 1);
+    for (int p = 0; p < P; ++p)
+        for (int x = 0; x < L; ++x) {
+            const double gx = (x == L - 1) ? 1.0 : (double)x * step;              // numpy linspace
+            volatile double scaled = gx * (0.5 - err[p]);                          // no FMA contraction
+            const double cf = scaled + err[p];
+            logcf[(size_t)p * L + x] = log(cf);
+            log1mcf[(size_t)p * L + x] = log(1.0 - cf);
+        }
+    const size_t nrows = (size_t)P * C * M * Kmax;
+    BAMSE_CUDA_TRY(ctx, ctx->d_K.ensure(sizeof(int32_t) * C));
+    BAMSE_CUDA_TRY(ctx, ctx->d_p0.ensure(sizeof(double) * C));
+    BAMSE_CUDA_TRY(ctx, ctx->d_var.ensure(sizeof(double) * ncnt));
+    BAMSE_CUDA_TRY(ctx, ctx->d_ref.ensure(sizeof(double) * ncnt));
+    BAMSE_CUDA_TRY(ctx, ctx->d_logc.ensure(sizeof(double) * ncnt));
+    BAMSE_CUDA_TRY(ctx, ctx->d_logcf.ensure(sizeof(double) * P * L));
+    BAMSE_CUDA_TRY(ctx, ctx->d_log1mcf.ensure(sizeof(double) * P * L));
+    BAMSE_CUDA_TRY(ctx, ctx->d_D64.ensure(sizeof(double) * nrows * L));
+    BAMSE_CUDA_TRY(ctx, ctx->d_D32.ensure(sizeof(float) * nrows * L));
+    cudaStream_t s = ctx->stream;
+    BAMSE_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_K.p, K_of_c, sizeof(int32_t) * C, cudaMemcpyHostToDevice, s));
+    BAMSE_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_p0.p, p0.data(), sizeof(double) * C, cudaMemcpyHostToDevice, s));
+    BAMSE_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_var.p, var.data(), sizeof(double) * ncnt, cudaMemcpyHostToDevice, s));
+    BAMSE_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_ref.p, ref.data(), sizeof(double) * ncnt, cudaMemcpyHostToDevice, s));
+    BAMSE_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_logc.p, logc.data(), sizeof(double) * ncnt, cudaMemcpyHostToDevice, s));
+    BAMSE_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_logcf.p, logcf.data(), sizeof(double) * P * L, cudaMemcpyHostToDevice, s));
+    BAMSE_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_log1mcf.p, log1mcf.data(), sizeof(double) * P * L, cudaMemcpyHostToDevice, s));
+    ctx->P = P; ctx->C = C; ctx->M = M; ctx->Kmax = Kmax;
+    ctx->K_of_c.assign(K_of_c, K_of_c + C);
+    launch_tables(ctx->view(), ctx->d_var.as<double>(), ctx->d_ref.as<double>(), ctx->d_logc.as<double>(),
+                  ctx->d_logcf.as<double>(), ctx->d_log1mcf.as<double>(), ctx->d_D64.as<double>(),
+                  ctx->d_D32.as<float>(), s);
+    ctx->launches++;
+    BAMSE_CUDA_TRY(ctx, cudaGetLastError());
+    BAMSE_CUDA_TRY(ctx, cudaStreamSynchronize(s));   // host staging vectors die at return
+    ctx->have_problem = true;
+    return BAMSE_OK;
+}
+
+// ---- internal: score a host vector of items, results to host ----------------------
+static int score_items_host(bamse_ctx* ctx, const std::vector<ScoreItem>& items, int precision, double* out) {
+    const size_t n = items.size();
+    if (n == 0) return BAMSE_OK;
+    BAMSE_CUDA_TRY(ctx, ctx->d_items.ensure(sizeof(ScoreItem) * n));
+    BAMSE_CUDA_TRY(ctx, ctx->d_scores.ensure(sizeof(double) * n));
+    cudaStream_t s = ctx->stream;
+    BAMSE_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_items.p, items.data(), sizeof(ScoreItem) * n, cudaMemcpyHostToDevice, s));
+    launch_score_items(precision, ctx->view(), ctx->d_items.as<ScoreItem>(), (int64_t)n, ctx->d_scores.as<double>(), s);
+    ctx->launches++;
+    BAMSE_CUDA_TRY(ctx, cudaGetLastError());
+    BAMSE_CUDA_TRY(ctx, cudaMemcpyAsync(out, ctx->d_scores.p, sizeof(double) * n, cudaMemcpyDeviceToHost, s));
+    BAMSE_CUDA_TRY(ctx, cudaStreamSynchronize(s));
+    return BAMSE_OK;
+}
+
+int bamse_score_list(bamse_ctx* ctx, int64_t n_items, const int32_t* item_clust, const int8_t* item_parent,
+                     const int8_t* item_nodes, int precision, double* out_score) {
+    CTX_CHECK(ctx);
+    if (!ctx->have_problem) return ctx->fail(BAMSE_ESTATE, "bamse_score_list: no problem uploaded");
+    if (n_items < 0 || (n_items > 0 && (!item_clust || !item_parent || !item_nodes || !out_score)))
+        return ctx->fail(BAMSE_EINVAL, "bamse_score_list: NULL pointer or negative n_items");
+    if (precision != BAMSE_FP32 && precision != BAMSE_FP64)
+        return ctx->fail(BAMSE_EINVAL, "bamse_score_list: precision must be BAMSE_FP32 or BAMSE_FP64");
+    const int Kmax = ctx->Kmax;
+    std::vector<ScoreItem> items((size_t)ctx->P * n_items);
+    for (int64_t i = 0; i < n_items; ++i) {
+        ScoreItem it;
+        memset(&it, 0, sizeof it);
+        it.c = item_clust[i];
+        if (it.c < 0 || it.c >= ctx->C) return ctx->fail(BAMSE_EINVAL, "bamse_score_list: item %lld: clustering %d out of range", (long long)i, it.c);
+        const int Kc = ctx->K_of_c[it.c];
+        int k = 0;
+        while (k < Kmax && item_nodes[i * Kmax + k] >= 0) ++k;
+        if (k < 1) return ctx->fail(BAMSE_EINVAL, "bamse_score_list: item %lld has no nodes", (long long)i);
+        uint32_t seen = 0;
+        for (int v = 0; v < k; ++v) {
+            const int nd = item_nodes[i * Kmax + v];
+            if (nd >= Kc || (seen >> nd) & 1u)
+                return ctx->fail(BAMSE_EINVAL, "bamse_score_list: item %lld: node id %d invalid or repeated", (long long)i, nd);
+            seen |= 1u << nd;
+            it.nodes[v] = (int8_t)nd;
+            it.parent[v] = item_parent[i * Kmax + v];
+        }
+        it.k = (int8_t)k;
+        TreeProgram prog;
+        if (!build_program(k, it.parent, it.nodes, &prog))
+            return ctx->fail(BAMSE_EINVAL, "bamse_score_list: item %lld is not a rooted tree (one -1, no cycles)", (long long)i);
+        for (int p = 0; p < ctx->P; ++p) { it.p = p; items[(size_t)p * n_items + i] = it; }
+    }
+    return score_items_host(ctx, items, precision, out_score);
+}
+
+// ---- internal: run an enumeration; records land in d_out [P][topk] ----------------
+static int enumerate_dev(bamse_ctx* ctx, const double* d_const, const double* d_thr, const uint64_t* d_begin,
+                         const uint64_t* d_end, int topk, int precision, double slack_abs, double slack_rel,
+                         bamse_record* d_out, double* d_dense_score, double* d_dense_logscre,
+                         const Segment* host_seg /* non-NULL: dense single-segment mode */) {
+    const int P = ctx->P, C = ctx->C;
+    cudaStream_t s = ctx->stream;
+    const int pi = precision == BAMSE_FP64 ? 1 : 0;
+    if (ctx->grid[pi] == 0) ctx->grid[pi] = enumerate_grid_size(precision, ctx->device);
+    const int grid = ctx->grid[pi];
+    const int chunk = 8;
+    BAMSE_CUDA_TRY(ctx, ctx->d_segs.ensure(sizeof(Segment) * P * C));
+    BAMSE_CUDA_TRY(ctx, ctx->d_scalars.ensure(sizeof(uint64_t) * 4));
+    uint64_t* scal = ctx->d_scalars.as<uint64_t>();
+    BAMSE_CUDA_TRY(ctx, cudaMemsetAsync(scal, 0, sizeof(uint64_t) * 4, s));
+    if (topk > 0) {
+        BAMSE_CUDA_TRY(ctx, ctx->d_cand.ensure(sizeof(bamse_record) * (size_t)P * grid * topk));
+        BAMSE_CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_cand.p, 0xFF, sizeof(bamse_record) * (size_t)P * grid * topk, s));
+    }
+    EnumWork w;
+    if (host_seg) {
+        const Segment seg = *host_seg;
+        const uint64_t chunks = (seg.n_trees + chunk - 1) / chunk;
+        BAMSE_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_segs.p, &seg, sizeof seg, cudaMemcpyHostToDevice, s));
+        BAMSE_CUDA_TRY(ctx, cudaMemcpyAsync(scal, &chunks, sizeof chunks, cudaMemcpyHostToDevice, s));
+        BAMSE_CUDA_TRY(ctx, cudaStreamSynchronize(s));
+        w.n_segs = 1;
+        ctx->last_evals = (int64_t)seg.n_trees;
+    } else {
+        launch_build_segments(P, C, ctx->d_K.as<int32_t>(), d_const, d_thr, d_begin, d_end, slack_abs, slack_rel,
+                              chunk, ctx->d_segs.as<Segment>(), scal, scal + 1, s);
+        ctx->launches++;
+        w.n_segs = P * C;
+    }
+    w.segs = ctx->d_segs.as<Segment>();
+    w.chunk = chunk;
+    w.total_chunks = scal;
+    w.next_chunk = reinterpret_cast<unsigned long long*>(scal + 2);
+    w.topk = topk;
+    w.cand = ctx->d_cand.as<bamse_record>();
+    w.dense_score = d_dense_score;
+    w.dense_logscre = d_dense_logscre;
+    launch_enumerate(precision, ctx->view(), w, grid, s);
+    ctx->launches++;
+    BAMSE_CUDA_TRY(ctx, cudaGetLastError());
+    if (topk > 0 && d_out) {
+        launch_merge_topk(ctx->d_cand.as<bamse_record>(), grid, 1, grid, P, topk, d_out, s);
+        ctx->launches++;
+        BAMSE_CUDA_TRY(ctx, cudaGetLastError());
+    }
+    return BAMSE_OK;
+}
+
+int bamse_score_range(bamse_ctx* ctx, int p, int c, uint64_t tree_begin, int64_t n, int precision, double* out_score,
+                      double* out_logscre) {
+    CTX_CHECK(ctx);
+    if (!ctx->have_problem) return ctx->fail(BAMSE_ESTATE, "bamse_score_range: no problem uploaded");
+    if (p < 0 || p >= ctx->P || c < 0 || c >= ctx->C || n < 0)
+        return ctx->fail(BAMSE_EINVAL, "bamse_score_range: p/c/n out of range");
+    if (precision != BAMSE_FP32 && precision != BAMSE_FP64)
+        return ctx->fail(BAMSE_EINVAL, "bamse_score_range: bad precision");
+    const int K = ctx->K_of_c[c];
+    const uint64_t T = ipow_u64(K, K - 1);
+    if (tree_begin > T || (uint64_t)n > T - tree_begin)
+        return ctx->fail(BAMSE_EINVAL, "bamse_score_range: range exceeds K^(K-1)=%llu", (unsigned long long)T);
+    if (n == 0) return BAMSE_OK;
+    BAMSE_CUDA_TRY(ctx, ctx->d_dense0.ensure(sizeof(double) * n));
+    BAMSE_CUDA_TRY(ctx, ctx->d_dense1.ensure(sizeof(double) * n));
+    Segment seg;
+    memset(&seg, 0, sizeof seg);
+    seg.p = p; seg.c = c; seg.K = K;
+    seg.tree_begin = tree_begin; seg.n_trees = (uint64_t)n;
+    seg.first_chunk = 0; seg.clust_const = 0.0; seg.threshold = -INFINITY;
+    int rc = enumerate_dev(ctx, nullptr, nullptr, nullptr, nullptr, 0, precision, 0.0, 0.0, nullptr,
+                           ctx->d_dense0.as<double>(), ctx->d_dense1.as<double>(), &seg);
+    if (rc) return rc;
+    cudaStream_t s = ctx->stream;
+    if (out_score) BAMSE_CUDA_TRY(ctx, cudaMemcpyAsync(out_score, ctx->d_dense0.p, sizeof(double) * n, cudaMemcpyDeviceToHost, s));
+    if (out_logscre) BAMSE_CUDA_TRY(ctx, cudaMemcpyAsync(out_logscre, ctx->d_dense1.p, sizeof(double) * n, cudaMemcpyDeviceToHost, s));
+    BAMSE_CUDA_TRY(ctx, cudaStreamSynchronize(s));
+    return BAMSE_OK;
+}
+
+int bamse_enumerate_topk_dev(bamse_ctx* ctx, const double* d_clust_const, const double* d_threshold,
+                             const uint64_t* d_tree_begin, const uint64_t* d_tree_end, int topk, int precision,
+                             double slack, bamse_record* d_out_records) {
+    CTX_CHECK(ctx);
+    if (!ctx->have_problem) return ctx->fail(BAMSE_ESTATE, "bamse_enumerate_topk_dev: no problem uploaded");
+    if (topk < 1 || topk > BAMSE_TOPK_MAX || !d_out_records)
+        return ctx->fail(BAMSE_EINVAL, "bamse_enumerate_topk_dev: topk must be in [1,%d], d_out_records non-NULL", BAMSE_TOPK_MAX);
+    if (precision != BAMSE_FP32 && precision != BAMSE_FP64)
+        return ctx->fail(BAMSE_EINVAL, "bamse_enumerate_topk_dev: bad precision");
+    // eval count (host arithmetic; ranges live on the device, so count full ranges unless given)
+    ctx->last_evals = -1;
+    return enumerate_dev(ctx, d_clust_const, d_threshold, d_tree_begin, d_tree_end, topk, precision, slack, 0.0,
+                         d_out_records, nullptr, nullptr, nullptr);
+}
+
+int bamse_merge_topk_dev(bamse_ctx* ctx, const bamse_record* d_lists, int n_lists, int P, int topk,
+                         bamse_record* d_out_records) {
+    CTX_CHECK(ctx);
+    if (!d_lists || !d_out_records || n_lists < 1 || P < 1 || topk < 1 || topk > BAMSE_TOPK_MAX)
+        return ctx->fail(BAMSE_EINVAL, "bamse_merge_topk_dev: bad arguments");
+    launch_merge_topk(d_lists, n_lists, P, 1, P, topk, d_out_records, ctx->stream);
+    ctx->launches++;
+    BAMSE_CUDA_TRY(ctx, cudaGetLastError());
+    return BAMSE_OK;
+}
+
+int bamse_score_topk(bamse_ctx* ctx, const double* clust_const, const double* threshold, const uint64_t* tree_begin,
+                     const uint64_t* tree_end, int topk, int precision, bamse_record* out_records, int8_t* out_parent,
+                     int32_t* out_count) {
+    CTX_CHECK(ctx);
+    if (!ctx->have_problem) return ctx->fail(BAMSE_ESTATE, "bamse_score_topk: no problem uploaded");
+    if (!clust_const || !out_records || topk < 1 || topk > BAMSE_TOPK_MAX)
+        return ctx->fail(BAMSE_EINVAL, "bamse_score_topk: clust_const/out_records NULL or topk not in [1,%d]", BAMSE_TOPK_MAX);
+    if (precision != BAMSE_FP32 && precision != BAMSE_FP64)
+        return ctx->fail(BAMSE_EINVAL, "bamse_score_topk: bad precision");
+    if ((tree_begin == nullptr) != (tree_end == nullptr))
+        return ctx->fail(BAMSE_EINVAL, "bamse_score_topk: tree_begin and tree_end must both be given or both NULL");
+    const int P = ctx->P, C = ctx->C, Kmax = ctx->Kmax;
+    cudaStream_t s = ctx->stream;
+    BAMSE_CUDA_TRY(ctx, ctx->d_const.ensure(sizeof(double) * P * C));
+    BAMSE_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_const.p, clust_const, sizeof(double) * P * C, cudaMemcpyHostToDevice, s));
+    if (threshold) {
+        BAMSE_CUDA_TRY(ctx, ctx->d_thr.ensure(sizeof(double) * P * C));
+        BAMSE_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_thr.p, threshold, sizeof(double) * P * C, cudaMemcpyHostToDevice, s));
+    }
+    int64_t evals = 0;
+    for (int c = 0; c < C; ++c) {
+        const int K = ctx->K_of_c[c];
+        const uint64_t T = ipow_u64(K, K - 1);
+        uint64_t b = tree_begin ? tree_begin[c] : 0, e = tree_end ? std::min<uint64_t>(tree_end[c], T) : T;
+        if (b < e) evals += (int64_t)(e - b);
+    }
+    evals *= P;
+    if (tree_begin) {
+        BAMSE_CUDA_TRY(ctx, ctx->d_begin.ensure(sizeof(uint64_t) * C));
+        BAMSE_CUDA_TRY(ctx, ctx->d_end.ensure(sizeof(uint64_t) * C));
+        BAMSE_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_begin.p, tree_begin, sizeof(uint64_t) * C, cudaMemcpyHostToDevice, s));
+        BAMSE_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_end.p, tree_end, sizeof(uint64_t) * C, cudaMemcpyHostToDevice, s));
+    }
+    // fp32: over-select with a slack that covers fp32 rounding, then re-score in fp64.
+    const int ksel = precision == BAMSE_FP64 ? topk : std::min(BAMSE_TOPK_MAX, topk + 8);
+    const double slack_abs = precision == BAMSE_FP64 ? 0.0 : 1e-3;
+    const double slack_rel = precision == BAMSE_FP64 ? 1e-12 : 1e-5;
+    BAMSE_CUDA_TRY(ctx, ctx->d_records.ensure(sizeof(bamse_record) * P * ksel));
+    int rc = enumerate_dev(ctx, ctx->d_const.as<double>(), threshold ? ctx->d_thr.as<double>() : nullptr,
+                           tree_begin ? ctx->d_begin.as<uint64_t>() : nullptr,
+                           tree_begin ? ctx->d_end.as<uint64_t>() : nullptr, ksel, precision, slack_abs, slack_rel,
+                           ctx->d_records.as<bamse_record>(), nullptr, nullptr, nullptr);
+    if (rc) return rc;
+    ctx->last_evals = evals;
+    std::vector<bamse_record> recs((size_t)P * ksel);
+    BAMSE_CUDA_TRY(ctx, cudaMemcpyAsync(recs.data(), ctx->d_records.p, sizeof(bamse_record) * P * ksel, cudaMemcpyDeviceToHost, s));
+    BAMSE_CUDA_TRY(ctx, cudaStreamSynchronize(s));
+
+    if (precision == BAMSE_FP32) {
+        // fp64 check-mode re-score of the short list, exact threshold, final ranking
+        std::vector<ScoreItem> items;
+        std::vector<size_t> where;
+        std::vector<double> logscre;
+        for (size_t i = 0; i < recs.size(); ++i) {
+            if (recs[i].clust < 0) continue;
+            ScoreItem it;
+            memset(&it, 0, sizeof it);
+            it.p = recs[i].param; it.c = recs[i].clust;
+            const int K = ctx->K_of_c[it.c];
+            it.k = (int8_t)K;
+            decode_tree(K, recs[i].tree, it.parent);
+            for (int v = 0; v < K; ++v) it.nodes[v] = (int8_t)v;
+            TreeProgram prog;
+            build_program(K, it.parent, it.nodes, &prog);
+            logscre.push_back(log((double)prog.scre));
+            items.push_back(it);
+            where.push_back(i);
+        }
+        std::vector<double> sc(items.size());
+        rc = score_items_host(ctx, items, BAMSE_FP64, sc.data());
+        if (rc) return rc;
+        for (size_t j = 0; j < items.size(); ++j) {
+            bamse_record& r = recs[where[j]];
+            r.score = sc[j] + logscre[j];
+            r.total = r.score + clust_const[(size_t)r.param * C + r.clust];
+            if (threshold) {
+                const double th = threshold[(size_t)r.param * C + r.clust];
+                if (!(r.score >= th - 1e-12 * fabs(th))) r.clust = -1;
+            }
+        }
+        for (int p = 0; p < P; ++p) {
+            bamse_record* b = recs.data() + (size_t)p * ksel;
+            std::stable_sort(b, b + ksel, [](const bamse_record& x, const bamse_record& y) {
+                if ((x.clust < 0) != (y.clust < 0)) return y.clust < 0;
+                if (x.clust < 0) return false;
+                if (x.total != y.total) return x.total > y.total;
+                if (x.clust != y.clust) return x.clust < y.clust;
+                return x.tree < y.tree;
+            });
+        }
+    }
+    for (int p = 0; p < P; ++p) {
+        int cnt = 0;
+        for (int j = 0; j < topk; ++j) {
+            bamse_record r = recs[(size_t)p * ksel + j];
+            if (r.clust < 0) { r.total = -INFINITY; r.score = -INFINITY; r.clust = -1; r.param = p; r.tree = 0; }
+            else ++cnt;
+            out_records[(size_t)p * topk + j] = r;
+            if (out_parent) {
+                int8_t* par = out_parent + ((size_t)p * topk + j) * Kmax;
+                for (int v = 0; v < Kmax; ++v) par[v] = -2;
+                if (r.clust >= 0) decode_tree(ctx->K_of_c[r.clust], r.tree, par);
+            }
+        }
+        if (out_count) out_count[p] = cnt;
+    }
+    return BAMSE_OK;
+}
+
+}  // extern "C"

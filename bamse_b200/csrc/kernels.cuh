@@ -1,0 +1,58 @@
+// Kernel declarations shared between the kernel translation units and the C ABI.
+#pragma once
+#include "common.cuh"
+
+namespace bamse {
+
+// One explicit work item of bamse_score_list / the fp64 re-score of a short list.
+struct ScoreItem {
+    int32_t p;
+    int32_t c;
+    int8_t k;
+    int8_t parent[KMAX];
+    int8_t nodes[KMAX];
+    int8_t pad[3];
+};
+static_assert(sizeof(ScoreItem) == 36, "ScoreItem layout");
+
+// One (parameter set, clustering, tree-index range) segment of an enumeration.
+struct Segment {
+    int32_t p;
+    int32_t c;
+    int32_t K;
+    int32_t pad;
+    uint64_t tree_begin;
+    uint64_t n_trees;
+    uint64_t first_chunk;    // prefix sum of chunk counts
+    double clust_const;      // cluster_prior + maxlikelihood        (clustering.py:183)
+    double threshold;        // candidate score + log scre (minus slack), -inf = keep all
+};
+
+struct EnumWork {
+    const Segment* segs;     // [n_segs]
+    int n_segs;
+    int chunk;               // trees per work chunk
+    const uint64_t* total_chunks;     // device scalar written by k_build_segments
+    unsigned long long* next_chunk;   // device work counter (zeroed before launch)
+    int topk;
+    bamse_record* cand;      // [P][gridDim.x][topk] per-CTA candidates (clust = -1 when unused)
+    double* dense_score;     // optional [n_trees of segment 0]
+    double* dense_logscre;   // optional
+};
+
+void launch_tables(const ProblemView& pv, const double* d_var, const double* d_ref, const double* d_logc,
+                   const double* d_logcf, const double* d_log1mcf, double* D64, float* D32,
+                   cudaStream_t s);
+void launch_build_segments(int P, int C, const int32_t* d_K_of_c, const double* d_const, const double* d_thr,
+                           const uint64_t* d_begin, const uint64_t* d_end, double slack_abs, double slack_rel,
+                           int chunk, Segment* d_segs, uint64_t* d_total_chunks, uint64_t* d_total_trees,
+                           cudaStream_t s);
+int enumerate_grid_size(int precision, int device);
+void launch_enumerate(int precision, const ProblemView& pv, const EnumWork& w, int grid, cudaStream_t s);
+void launch_score_items(int precision, const ProblemView& pv, const ScoreItem* d_items, int64_t n,
+                        double* d_out, cudaStream_t s);
+// list l of parameter set p starts at d_lists + (l * stride_list + p * stride_p) * topk
+void launch_merge_topk(const bamse_record* d_lists, int n_lists, int64_t stride_list, int64_t stride_p, int P,
+                       int topk, bamse_record* d_out, cudaStream_t s);
+
+}  // namespace bamse

@@ -1,0 +1,209 @@
+"""ctypes binding of libbamse_cuda.so (include/bamse_cuda.h).
+
+This is the only door between the Python host and the CUDA kernels.  There is NO CPU
+fallback: if the shared library is missing or no B200 is visible, construction raises.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libbamse_cuda.so")
+
+FP32 = 0
+FP64 = 1
+KMAX = 12
+TOPK_MAX = 64
+GRID = 512
+
+RECORD_DTYPE = np.dtype([("total", "<f8"), ("score", "<f8"), ("clust", "<i4"), ("param", "<i4"), ("tree", "<u8")])
+assert RECORD_DTYPE.itemsize == 32
+
+
+class BamseCudaError(RuntimeError):
+    def __init__(self, code, message):
+        RuntimeError.__init__(self, "libbamse_cuda error %d: %s" % (code, message))
+        self.code = code
+
+
+_lib = None
+
+
+def load_library():
+    """Loads libbamse_cuda.so once and declares every prototype of include/bamse_cuda.h."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH):
+        raise RuntimeError("%s not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(make -C bamse_b200/csrc).  There is no CPU fallback." % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    c_p = ctypes.c_void_p
+    i32, i64, u64, dbl = ctypes.c_int, ctypes.c_int64, ctypes.c_uint64, ctypes.c_double
+    lib.bamse_abi_version.restype = i32
+    lib.bamse_abi_version.argtypes = []
+    lib.bamse_create.restype = i32
+    lib.bamse_create.argtypes = [ctypes.POINTER(c_p), i32]
+    lib.bamse_destroy.restype = None
+    lib.bamse_destroy.argtypes = [c_p]
+    lib.bamse_last_error.restype = ctypes.c_char_p
+    lib.bamse_last_error.argtypes = [c_p]
+    lib.bamse_set_stream.restype = i32
+    lib.bamse_set_stream.argtypes = [c_p, c_p]
+    lib.bamse_launch_count.restype = i64
+    lib.bamse_launch_count.argtypes = [c_p]
+    lib.bamse_last_eval_count.restype = i64
+    lib.bamse_last_eval_count.argtypes = [c_p]
+    lib.bamse_decode_tree.restype = i32
+    lib.bamse_decode_tree.argtypes = [i32, u64, c_p]
+    lib.bamse_upload_problem.restype = i32
+    lib.bamse_upload_problem.argtypes = [c_p, i32, c_p, i32, i32, i32, c_p, c_p, c_p]
+    lib.bamse_score_list.restype = i32
+    lib.bamse_score_list.argtypes = [c_p, i64, c_p, c_p, c_p, i32, c_p]
+    lib.bamse_score_range.restype = i32
+    lib.bamse_score_range.argtypes = [c_p, i32, i32, u64, i64, i32, c_p, c_p]
+    lib.bamse_score_topk.restype = i32
+    lib.bamse_score_topk.argtypes = [c_p, c_p, c_p, c_p, c_p, i32, i32, c_p, c_p, c_p]
+    lib.bamse_enumerate_topk_dev.restype = i32
+    lib.bamse_enumerate_topk_dev.argtypes = [c_p, c_p, c_p, c_p, c_p, i32, i32, dbl, c_p]
+    lib.bamse_merge_topk_dev.restype = i32
+    lib.bamse_merge_topk_dev.argtypes = [c_p, c_p, i32, i32, i32, c_p]
+    if lib.bamse_abi_version() != 1:
+        raise RuntimeError("libbamse_cuda ABI version mismatch")
+    _lib = lib
+    return lib
+
+
+EXPORTED_SYMBOLS = [
+    "bamse_abi_version", "bamse_create", "bamse_destroy", "bamse_last_error", "bamse_set_stream",
+    "bamse_launch_count", "bamse_last_eval_count", "bamse_decode_tree", "bamse_upload_problem",
+    "bamse_score_list", "bamse_score_range", "bamse_score_topk", "bamse_enumerate_topk_dev",
+    "bamse_merge_topk_dev",
+]
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+
+def decode_tree(K, index):
+    """index -> parent vector (python ints) through the library's host decoder."""
+    lib = load_library()
+    out = np.empty(K, dtype=np.int8)
+    rc = lib.bamse_decode_tree(int(K), int(index), _ptr(out))
+    if rc != 0:
+        raise BamseCudaError(rc, "bamse_decode_tree(K=%d, index=%d)" % (K, index))
+    return [int(x) for x in out]
+
+
+class Context(object):
+    """One bamse_ctx (one CUDA device, one host thread)."""
+
+    def __init__(self, device=0):
+        self._lib = load_library()
+        h = ctypes.c_void_p()
+        rc = self._lib.bamse_create(ctypes.byref(h), int(device))
+        if rc != 0:
+            raise BamseCudaError(rc, self._lib.bamse_last_error(None).decode())
+        self._h = h
+        self.device = int(device)
+        self.P = self.C = self.M = self.Kmax = 0
+        self.K_of_c = None
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.bamse_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def _check(self, rc):
+        if rc != 0:
+            raise BamseCudaError(rc, self._lib.bamse_last_error(self._h).decode())
+
+    # ---------------------------------------------------------------- plumbing
+    def set_stream(self, cuda_stream):
+        self._check(self._lib.bamse_set_stream(self._h, ctypes.c_void_p(cuda_stream or 0)))
+
+    @property
+    def launch_count(self):
+        return int(self._lib.bamse_launch_count(self._h))
+
+    @property
+    def last_eval_count(self):
+        return int(self._lib.bamse_last_eval_count(self._h))
+
+    # ---------------------------------------------------------------- problem
+    def upload_problem(self, err, K_of_c, var_counts, ref_counts):
+        """err: [P] floats; K_of_c: [C]; var/ref_counts: [C][Kmax][M] integer arrays."""
+        err = np.ascontiguousarray(np.atleast_1d(err), dtype=np.float64)
+        K_of_c = np.ascontiguousarray(K_of_c, dtype=np.int32)
+        var = np.ascontiguousarray(var_counts, dtype=np.int64)
+        ref = np.ascontiguousarray(ref_counts, dtype=np.int64)
+        if var.ndim != 3 or var.shape != ref.shape or var.shape[0] != len(K_of_c):
+            raise ValueError("var_counts/ref_counts must be [C][Kmax][M] and match K_of_c")
+        C, Kmax, M = var.shape
+        self._check(self._lib.bamse_upload_problem(self._h, len(err), _ptr(err), C, M, Kmax, _ptr(K_of_c),
+                                                   _ptr(var), _ptr(ref)))
+        self.P, self.C, self.M, self.Kmax = len(err), C, M, Kmax
+        self.K_of_c = K_of_c.copy()
+
+    # ---------------------------------------------------------------- scoring
+    def score_list(self, item_clust, item_parent, item_nodes, precision=FP64):
+        """Returns [P][n] raw get_tree_score values.  item_parent/item_nodes: [n][Kmax] int8
+        (parent padding -2, nodes padding -1)."""
+        clust = np.ascontiguousarray(item_clust, dtype=np.int32)
+        par = np.ascontiguousarray(item_parent, dtype=np.int8)
+        nod = np.ascontiguousarray(item_nodes, dtype=np.int8)
+        n = len(clust)
+        if par.shape != (n, self.Kmax) or nod.shape != (n, self.Kmax):
+            raise ValueError("item_parent / item_nodes must be [n][Kmax=%d]" % self.Kmax)
+        out = np.empty((self.P, n), dtype=np.float64)
+        self._check(self._lib.bamse_score_list(self._h, n, _ptr(clust), _ptr(par), _ptr(nod), int(precision), _ptr(out)))
+        return out
+
+    def score_range(self, p, c, tree_begin, n, precision=FP64):
+        """Dense scores of trees [tree_begin, tree_begin+n): (get_tree_score, log scre)."""
+        score = np.empty(n, dtype=np.float64)
+        logscre = np.empty(n, dtype=np.float64)
+        self._check(self._lib.bamse_score_range(self._h, int(p), int(c), int(tree_begin), int(n), int(precision),
+                                                _ptr(score), _ptr(logscre)))
+        return score, logscre
+
+    def score_topk(self, clust_const, threshold=None, tree_begin=None, tree_end=None, topk=1, precision=FP32):
+        """Host-buffer enumeration + global top-k.  Returns (records [P][topk] structured array,
+        parents [P][topk][Kmax] int8, counts [P])."""
+        cc = np.ascontiguousarray(clust_const, dtype=np.float64).reshape(self.P, self.C)
+        th = None if threshold is None else np.ascontiguousarray(threshold, dtype=np.float64).reshape(self.P, self.C)
+        tb = None if tree_begin is None else np.ascontiguousarray(tree_begin, dtype=np.uint64)
+        te = None if tree_end is None else np.ascontiguousarray(tree_end, dtype=np.uint64)
+        rec = np.empty((self.P, topk), dtype=RECORD_DTYPE)
+        par = np.empty((self.P, topk, self.Kmax), dtype=np.int8)
+        cnt = np.empty(self.P, dtype=np.int32)
+        self._check(self._lib.bamse_score_topk(self._h, _ptr(cc), _ptr(th), _ptr(tb), _ptr(te), int(topk),
+                                               int(precision), _ptr(rec), _ptr(par), _ptr(cnt)))
+        return rec, par, cnt
+
+    # ---------------------------------------------------------------- device-resident
+    def enumerate_topk_dev(self, d_clust_const, d_threshold, d_tree_begin, d_tree_end, topk, precision, slack,
+                           d_out_records):
+        """All d_* are integer device addresses (e.g. torch.Tensor.data_ptr()); asynchronous."""
+        self._check(self._lib.bamse_enumerate_topk_dev(
+            self._h, ctypes.c_void_p(d_clust_const or 0), ctypes.c_void_p(d_threshold or 0),
+            ctypes.c_void_p(d_tree_begin or 0), ctypes.c_void_p(d_tree_end or 0), int(topk), int(precision),
+            float(slack), ctypes.c_void_p(d_out_records)))
+
+    def merge_topk_dev(self, d_lists, n_lists, P, topk, d_out_records):
+        self._check(self._lib.bamse_merge_topk_dev(self._h, ctypes.c_void_p(d_lists), int(n_lists), int(P), int(topk),
+                                                   ctypes.c_void_p(d_out_records)))

@@ -1,0 +1,150 @@
+/* libbamse_cuda.so -- C ABI of the B200-native BAMSE tree-likelihood scorer.
+ *
+ * The reference (HoseinT/BAMSE) is pure Python and has NO plugin / FFI interface
+ * (SURVEY.md section 8b).  The entry points below are what a ctypes binding for its hot
+ * path would bind; each cites the reference code it replaces (paths relative to the
+ * reference checkout).  INTEGRATION.md shows the ctypes stub a maintainer would add.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; every `const T*` without a `d_` prefix is
+ *    caller-owned HOST memory (C-contiguous), read-only; `out_*` are caller-owned host
+ *    buffers the library fills; `d_*` are DEVICE pointers on the ctx's device.
+ *  - return 0 on success, a negative BAMSE_E* code on failure; never throws/aborts across
+ *    the ABI; bamse_last_error() returns the message of the last failure on the ctx
+ *    (or of the last failed bamse_create when ctx == NULL).
+ *  - a ctx is bound to ONE CUDA device and is not re-entrant (one host thread at a
+ *    time); distinct ctxs may be used concurrently.  Multi-GPU = one process (rank)
+ *    per GPU, each with its own ctx, sharding by tree-index range; the only exchange
+ *    is an all-gather of bamse_record lists (done by the host with NCCL) followed by
+ *    bamse_merge_topk_dev on every rank.
+ *  - there is NO CPU fallback: with no usable CUDA device bamse_create fails with
+ *    BAMSE_ENODEV.
+ *  - a "tree index" t in [0, K^(K-1)) names a labeled rooted tree on K nodes:
+ *    root = t % K, and t / K holds the K-2 Pruefer digits in base K, least significant
+ *    first (oracle/bamse_oracle.py: decode_tree is the executable definition).
+ */
+#ifndef BAMSE_CUDA_H
+#define BAMSE_CUDA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BAMSE_ABI_VERSION 1
+#define BAMSE_GRID 512      /* clustering.py:20,26  hard-coded grid length              */
+#define BAMSE_KMAX 12       /* bamse.py:32          default of -nc; 12^11 fits uint64    */
+#define BAMSE_MMAX 64       /* samples per problem                                       */
+#define BAMSE_TOPK_MAX 64
+
+#define BAMSE_OK 0
+#define BAMSE_EINVAL (-1)   /* bad argument                                              */
+#define BAMSE_ENODEV (-2)   /* no CUDA device / not sm_100                               */
+#define BAMSE_ECUDA (-3)    /* CUDA runtime error (message has the cudaError string)     */
+#define BAMSE_ESTATE (-4)   /* call order (e.g. scoring before a problem is uploaded)    */
+#define BAMSE_ENOMEM (-5)
+
+#define BAMSE_FP32 0        /* production: fp32 arithmetic, fp64 accumulation over samples */
+#define BAMSE_FP64 1        /* check mode: everything in fp64                             */
+
+typedef struct bamse_ctx bamse_ctx;
+
+/* One ranked candidate.  32 bytes, identical on host and device.
+ * total = score + clust_const[param][clust]            (clustering.py:183 `totalscore`)
+ * score = get_tree_score + log(scre)                   (clustering.py:179,182)        */
+typedef struct bamse_record {
+    double total;
+    double score;
+    int32_t clust;
+    int32_t param;
+    uint64_t tree;
+} bamse_record;
+
+/* ---------------------------------------------------------------- life cycle */
+int bamse_abi_version(void);
+int bamse_create(bamse_ctx** out, int device_ordinal);
+void bamse_destroy(bamse_ctx* ctx);
+const char* bamse_last_error(const bamse_ctx* ctx);
+/* Launch all work of this ctx on `cuda_stream` (a cudaStream_t; NULL = the ctx's own
+ * stream).  Lets a host that owns streams (e.g. torch) time the kernels with its events. */
+int bamse_set_stream(bamse_ctx* ctx, void* cuda_stream);
+/* Number of kernels this ctx has launched since creation (for bench.py `gpu_launches`). */
+int64_t bamse_launch_count(const bamse_ctx* ctx);
+
+/* ------------------------------------------------------------ problem upload
+ * Replaces clustering.__init__'s table construction (clustering.py:56-62: As/Bs ->
+ * K*M distrib() tables and the prior constant) for a batch of C clusterings and P
+ * sequencing-error values.  var_counts/ref_counts are the aggregated per-cluster
+ * variant/reference read counts `As`,`Bs` (clustering.py:56-57), laid out
+ * [C][Kmax][M]; rows k >= K_of_c[c] are ignored.  Host work: the three lgamma terms of
+ * distrib (clustering.py:23) in fp64; device work (kernel k_tables): the 512-point
+ * tables.  The problem stays resident in HBM until the next upload / destroy. */
+int bamse_upload_problem(bamse_ctx* ctx, int P, const double* err, int C, int M, int Kmax,
+                         const int32_t* K_of_c, const int64_t* var_counts,
+                         const int64_t* ref_counts);
+
+/* ------------------------------------------------------------------ score a list
+ * Replaces clustering.get_tree_score(tree, nodes) (clustering.py:87-90) for a batch:
+ * item i scores parent vector item_parent[i][0..k) (local indices, -1 at the root, any
+ * root position, padding -2) over cluster ids item_nodes[i][0..k) (padding -1) of
+ * clustering item_clust[i], for every parameter set p.  The prior always uses the
+ * clustering's full K (clustering.py:61-62).  out_score is [P][n_items]: the raw
+ * get_tree_score (no log scre).  Used by reorder (clustering.py:95-96), the greedy
+ * candidate (:111) and the threshold (:121). */
+int bamse_score_list(bamse_ctx* ctx, int64_t n_items, const int32_t* item_clust,
+                     const int8_t* item_parent /* [n][Kmax] */,
+                     const int8_t* item_nodes /* [n][Kmax] */, int precision,
+                     double* out_score /* [P][n] */);
+
+/* ------------------------------------------------------ score a dense index range
+ * Scores trees [tree_begin, tree_begin + n) of clustering c under parameter set p by
+ * index.  out_score[i] = get_tree_score, out_logscre[i] = log(canonizeF scre)
+ * (tree_tools.py:47-63).  Either output may be NULL.  Parity-test / debugging entry. */
+int bamse_score_range(bamse_ctx* ctx, int p, int c, uint64_t tree_begin, int64_t n,
+                      int precision, double* out_score, double* out_logscre);
+
+/* -------------------------------------------------------- enumerate + global top-k
+ * Replaces the loop bamse.py:91-106 (get_trees2's exhaustive search space + score
+ * assembly clustering.py:179-183 + argsort(-totalscore)[:t]).  For every p and every
+ * clustering c, enumerates tree indices [tree_begin[c], tree_end[c]) (NULL, NULL = all
+ * K_c^(K_c-1)), keeps trees with score + log scre >= threshold[p][c] (NULL = keep all;
+ * clustering.py:144-147), ranks by total = score + log scre + clust_const[p][c]
+ * (ties: clust asc, tree asc) and returns the best `topk` per p.
+ *   precision BAMSE_FP32: candidates are selected in fp32 with a small slack, then
+ *   re-scored in fp64 before the exact threshold test and the final ranking, so the
+ *   returned totals/scores are fp64 check-mode values.
+ * out_records [P][topk] (unused slots: clust = -1), out_parent [P][topk][Kmax] parent
+ * vectors (padding -2), out_count [P] number of valid records.  Host buffers. */
+int bamse_score_topk(bamse_ctx* ctx, const double* clust_const /* [P][C] */,
+                     const double* threshold /* [P][C] or NULL */,
+                     const uint64_t* tree_begin /* [C] or NULL */,
+                     const uint64_t* tree_end /* [C] or NULL */, int topk, int precision,
+                     bamse_record* out_records, int8_t* out_parent, int32_t* out_count);
+
+/* ------------------------------------------------- device-resident variants
+ * Same enumeration, asynchronous on the ctx stream, no host copies: constants are read
+ * from device memory and the per-p top `topk` records (selected in `precision`, no fp64
+ * re-score) are written to d_out_records [P][topk].  d_threshold / d_tree_begin /
+ * d_tree_end may be NULL.  `slack` is subtracted from thresholds (0 for exact). */
+int bamse_enumerate_topk_dev(bamse_ctx* ctx, const double* d_clust_const,
+                             const double* d_threshold, const uint64_t* d_tree_begin,
+                             const uint64_t* d_tree_end, int topk, int precision,
+                             double slack, bamse_record* d_out_records);
+
+/* Merges n_lists device lists of [P][topk] records (e.g. the all-gathered per-rank
+ * results) into one [P][topk] list with the same ordering rule.  Deterministic. */
+int bamse_merge_topk_dev(bamse_ctx* ctx, const bamse_record* d_lists, int n_lists, int P,
+                         int topk, bamse_record* d_out_records);
+
+/* Number of trees the last bamse_enumerate_topk_dev / bamse_score_topk call on this ctx
+ * scored (sum over p, c of the index-range sizes). */
+int64_t bamse_last_eval_count(const bamse_ctx* ctx);
+
+/* Host helper shared with the oracle's definition: index -> parent vector. */
+int bamse_decode_tree(int K, uint64_t tree_index, int8_t* out_parent /* [K] */);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BAMSE_CUDA_H */
