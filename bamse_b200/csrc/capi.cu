@@ -50,6 +50,7 @@ struct bamse_ctx {
     DBuf d_segs, d_scalars /* total_chunks, total_trees, next_chunk */, d_cand, d_items, d_scores;
     DBuf d_const, d_thr, d_begin, d_end, d_records, d_dense0, d_dense1;
     int grid[2] = {0, 0};
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_used, ev_free;
 
     int fail(int code, const char* fmt, ...) {
         char buf[512];
@@ -131,6 +132,8 @@ void bamse_destroy(bamse_ctx* ctx) {
                     &ctx->d_scores, &ctx->d_const, &ctx->d_thr, &ctx->d_begin, &ctx->d_end, &ctx->d_records,
                     &ctx->d_dense0, &ctx->d_dense1};
     for (DBuf* b : bufs) b->release();
+    for (auto* v : {&ctx->ev_used, &ctx->ev_free})
+        for (auto& ev : *v) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }
@@ -143,6 +146,24 @@ int bamse_set_stream(bamse_ctx* ctx, void* cuda_stream) {
 
 int64_t bamse_launch_count(const bamse_ctx* ctx) { return ctx ? ctx->launches : 0; }
 int64_t bamse_last_eval_count(const bamse_ctx* ctx) { return ctx ? ctx->last_evals : 0; }
+
+int bamse_kernel_time(bamse_ctx* ctx, int reset, double* out_ms, int64_t* out_launches) {
+    CTX_CHECK(ctx);
+    BAMSE_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    double ms = 0.0;
+    for (auto& ev : ctx->ev_used) {
+        float t = 0.f;
+        BAMSE_CUDA_TRY(ctx, cudaEventElapsedTime(&t, ev.first, ev.second));
+        ms += t;
+    }
+    if (out_ms) *out_ms = ms;
+    if (out_launches) *out_launches = (int64_t)ctx->ev_used.size();
+    if (reset) {
+        for (auto& ev : ctx->ev_used) ctx->ev_free.push_back(ev);
+        ctx->ev_used.clear();
+    }
+    return BAMSE_OK;
+}
 
 int bamse_decode_tree(int K, uint64_t tree_index, int8_t* out_parent) {
     if (K < 1 || K > KMAX || !out_parent) return BAMSE_EINVAL;
@@ -318,7 +339,16 @@ static int enumerate_dev(bamse_ctx* ctx, const double* d_const, const double* d_
     w.cand = ctx->d_cand.as<bamse_record>();
     w.dense_score = d_dense_score;
     w.dense_logscre = d_dense_logscre;
+    std::pair<cudaEvent_t, cudaEvent_t> ev;
+    if (!ctx->ev_free.empty()) { ev = ctx->ev_free.back(); ctx->ev_free.pop_back(); }
+    else {
+        BAMSE_CUDA_TRY(ctx, cudaEventCreate(&ev.first));
+        BAMSE_CUDA_TRY(ctx, cudaEventCreate(&ev.second));
+    }
+    BAMSE_CUDA_TRY(ctx, cudaEventRecord(ev.first, s));
     launch_enumerate(precision, ctx->view(), w, grid, s);
+    BAMSE_CUDA_TRY(ctx, cudaEventRecord(ev.second, s));
+    ctx->ev_used.push_back(ev);
     ctx->launches++;
     BAMSE_CUDA_TRY(ctx, cudaGetLastError());
     if (topk > 0 && d_out) {

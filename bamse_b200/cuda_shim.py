@@ -69,6 +69,8 @@ def load_library():
     lib.bamse_enumerate_topk_dev.argtypes = [c_p, c_p, c_p, c_p, c_p, i32, i32, dbl, c_p]
     lib.bamse_merge_topk_dev.restype = i32
     lib.bamse_merge_topk_dev.argtypes = [c_p, c_p, i32, i32, i32, c_p]
+    lib.bamse_kernel_time.restype = i32
+    lib.bamse_kernel_time.argtypes = [c_p, i32, ctypes.POINTER(dbl), ctypes.POINTER(i64)]
     if lib.bamse_abi_version() != 1:
         raise RuntimeError("libbamse_cuda ABI version mismatch")
     _lib = lib
@@ -79,7 +81,7 @@ EXPORTED_SYMBOLS = [
     "bamse_abi_version", "bamse_create", "bamse_destroy", "bamse_last_error", "bamse_set_stream",
     "bamse_launch_count", "bamse_last_eval_count", "bamse_decode_tree", "bamse_upload_problem",
     "bamse_score_list", "bamse_score_range", "bamse_score_topk", "bamse_enumerate_topk_dev",
-    "bamse_merge_topk_dev",
+    "bamse_merge_topk_dev", "bamse_kernel_time",
 ]
 
 
@@ -143,6 +145,12 @@ class Context(object):
     @property
     def last_eval_count(self):
         return int(self._lib.bamse_last_eval_count(self._h))
+
+    def kernel_time(self, reset=True):
+        """(summed device ms of the enumeration kernel, launches) since the last reset."""
+        ms, n = ctypes.c_double(), ctypes.c_int64()
+        self._check(self._lib.bamse_kernel_time(self._h, 1 if reset else 0, ctypes.byref(ms), ctypes.byref(n)))
+        return ms.value, n.value
 
     # ---------------------------------------------------------------- problem
     def upload_problem(self, err, K_of_c, var_counts, ref_counts):

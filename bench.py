@@ -1,0 +1,444 @@
+#!/usr/bin/env python
+"""bench.py -- tree-likelihood evals/sec of the BAMSE hot path on B200 (contract in the task
+statement, section 4 of the tier framing).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--config c2] [--impl ours|reference]
+
+One "step" = one pass of the hot path over the configuration's whole work list: every labeled
+rooted tree (K^(K-1)) of every candidate clustering (x every (e,s) pair for c5), thresholded
+and merged into the global top-t.  With N > 1 (torchrun, one rank per GPU) the tree-index
+range of every clustering is split N ways (no data-path collective); the only exchange is one
+NCCL all-gather of each rank's top-t records per step, followed by the same merge everywhere.
+
+Prints ONE JSON line (rank 0).  `value` = evals/s with inputs resident in HBM (CUDA-event
+timed); `e2e` = the same pass through the host-buffer C ABI (bamse_upload_problem +
+bamse_score_topk: H2D of the read-count tables and constants, D2H of the records inside the
+timed region); `roofline` = the enumeration kernel against its binding SM pipe;
+`cpu_baseline` = the reference's own get_tree_score on this box's host cores (bounded sample).
+"""
+import argparse
+import json
+import math
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "tree-likelihood evals/sec (trees x clusterings)"
+UNIT = "evals/s"
+
+
+# ------------------------------------------------------------------------------------------
+# algorithmic operation counts
+def mean_leaves(K):
+    return K * (1.0 - 1.0 / K) ** (K - 1) if K > 1 else 1.0
+
+
+def algorithmic_ops_per_eval(K, M, L=512):
+    """(conv terms, transcendental ops, fp32 flops) averaged over all labeled rooted trees."""
+    lm1 = mean_leaves(K) - 1.0
+    n_c = M * lm1 * (L * (L + 1) / 2.0)
+    n_s = M * K * L
+    xu = n_c + M * lm1 * L + 2 * n_s + M * L + M
+    flops = 4 * n_c + 4 * n_s + 2 * M * K * L
+    return n_c, xu, flops
+
+
+# ------------------------------------------------------------------------------------------
+class ClockSampler(object):
+    """samples nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+                power.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------
+def pipe_peaks():
+    """measured SM-pipe peaks of this pool's B200 (profiles/pipe_peaks.json, produced by
+    profiles/pipe_peaks.cu under gpurun); nominal fallback = 148 SMs x lanes x 1.965 GHz."""
+    path = os.path.join(ROOT, "profiles", "pipe_peaks.json")
+    nominal = {"fp32_tflops": 148 * 128 * 2 * 1.965e9 / 1e12, "xu_tops": 148 * 16 * 1.965e9 / 1e12,
+               "fp64_tflops": 148 * 64 * 2 * 1.965e9 / 1e12, "source": "nominal (148 SM x lanes x 1.965 GHz)"}
+    try:
+        with open(path) as f:
+            d = json.load(f)
+        d.setdefault("source", "measured (profiles/pipe_peaks.json)")
+        for k, v in nominal.items():
+            d.setdefault(k, v)
+        return d
+    except Exception:
+        return nominal
+
+
+# ------------------------------------------------------------------------------------------
+def reference_eval_worker(args):
+    """scores a few work items with the reference's own clustering.get_tree_score (or the
+    numpy port when oracle/_ref is absent).  Runs in a worker process."""
+    kind, As_list, Bs_list, err, items = args
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import numpy as np
+    t0 = time.perf_counter()
+    if kind == "reference":
+        import ref_shim
+        cl = ref_shim.load().clustering
+        for ci, tree in items:
+            As, Bs = np.array(As_list[ci]), np.array(Bs_list[ci])
+            K, M = As.shape
+            D = np.array([[cl.distrib(As[k, m], Bs[k, m], err) for m in range(M)] for k in range(K)])
+            P = np.array([[cl.prior_fractions(K) for m in range(M)] for k in range(K)])
+            float(np.sum(cl.tree_integrate_multisample(np.array(tree), D, P)))
+    else:
+        import bamse_oracle as orc
+        for ci, tree in items:
+            As, Bs = np.array(As_list[ci]), np.array(Bs_list[ci])
+            K, M = As.shape
+            D = np.array([[orc.distrib(As[k, m], Bs[k, m], err) for m in range(M)] for k in range(K)])
+            float(orc.tree_score_samples(tree, D, orc.prior_const(K)).sum())
+    return len(items), time.perf_counter() - t0
+
+
+def cpu_reference_rate(work, n_items, cores, seed=0):
+    """evals/s of the reference CPU path on `cores` worker processes over a seeded random
+    sample of `n_items` (clustering, tree) work items of this workload."""
+    import multiprocessing as mp
+    import numpy as np
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import bamse_oracle as orc
+    import ref_shim
+    kind = "reference" if ref_shim.available() else "port"
+    rng = np.random.default_rng(seed)
+    clusts = work["clusts"]
+    weights = np.array([float(int(c.As.shape[0]) ** (int(c.As.shape[0]) - 1)) for c in clusts])
+    picks = rng.choice(len(clusts), size=n_items, p=weights / weights.sum())
+    items = []
+    for ci in picks:
+        K = int(clusts[ci].As.shape[0])
+        items.append((int(ci), orc.decode_tree(K, int(rng.integers(0, K ** (K - 1))))))
+    As_list = [c.As.tolist() for c in clusts]
+    Bs_list = [c.Bs.tolist() for c in clusts]
+    chunks = [items[i::cores] for i in range(cores)]
+    chunks = [c for c in chunks if c]
+    t0 = time.perf_counter()
+    if cores == 1:
+        res = [reference_eval_worker((kind, As_list, Bs_list, work["errs"][0], chunks[0]))]
+    else:
+        with mp.get_context("spawn").Pool(len(chunks)) as pool:
+            res = pool.map(reference_eval_worker, [(kind, As_list, Bs_list, work["errs"][0], c) for c in chunks])
+    wall = time.perf_counter() - t0
+    busy = max(r[1] for r in res)   # slowest worker, excludes process start-up
+    n = sum(r[0] for r in res)
+    return dict(value=n / busy, unit=UNIT, cores=len(chunks), kind=kind, wall_s=wall,
+                sample="%d seeded random (clustering, tree) items of %s, %d worker processes" % (n, work["name"], len(chunks)))
+
+
+# ------------------------------------------------------------------------------------------
+def run_reference_arm(args, rank, world):
+    """--impl reference: the reference's own CPU implementation on this box's host cores."""
+    if rank != 0:
+        return
+    from bamse_b200 import workloads
+    work = workloads.build(args.config)
+    cores = os.cpu_count() or 1
+    per_step = max(cores, args.ref_items)
+    rates = []
+    for _ in range(args.warmup):
+        cpu_reference_rate(work, max(1, cores), cores, seed=99)
+    t0 = time.perf_counter()
+    n_done = 0
+    for s in range(args.steps):
+        r = cpu_reference_rate(work, per_step, cores, seed=s)
+        rates.append(r)
+        n_done += per_step
+    wall = time.perf_counter() - t0
+    value = statistics.mean(r["value"] for r in rates)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / max(1, args.steps),
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": config_dict(args, work, world),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": rates[0]["cores"], "kind": rates[0]["kind"],
+                             "sample": "%d steps x %s" % (args.steps, rates[0]["sample"])},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def config_dict(args, work, world):
+    import collections
+    ks = collections.Counter(int(c.As.shape[0]) for c in work["clusts"])
+    return {"workload": "%s: simdata.py synthetic, %s; all K^(K-1) labeled rooted trees of every candidate clustering"
+                        % (work["name"], work["desc"]),
+            "clusterings": len(work["clusts"]), "K_histogram": {str(k): v for k, v in sorted(ks.items())},
+            "param_sets": len(work["errs"]), "samples": work["M"],
+            "evals_per_step": work["n_evals_per_param"] * len(work["errs"]),
+            "parallelism": "tree-index range sharding x%d + all-gather top-k" % world,
+            "l2": "256 MiB write between steps inside the timed region (inputs are KBs; kernel is SM-pipe bound)"}
+
+
+# ------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--config", default="c2", choices=["c1", "c2", "c3", "c4", "c5"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "fp64"])
+    ap.add_argument("--topk", type=int, default=5)
+    ap.add_argument("--ref-items", type=int, default=16, help="work items per step of the reference arm")
+    ap.add_argument("--cpu-items", type=int, default=16, help="sample size of the cpu_baseline leg")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from bamse_b200 import cuda_shim, workloads
+    from bamse_b200.clustering import _pack_items, _pack_problem
+    from bamse_b200.tree_tools import canonizeF
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    prec = cuda_shim.FP32 if args.precision == "fp32" else cuda_shim.FP64
+
+    ctx = cuda_shim.Context(local_rank)
+    work = workloads.build(args.config, ctx=ctx)     # identical on every rank (seeded)
+    clusts, errs = work["clusts"], work["errs"]
+    P, C = len(errs), len(clusts)
+
+    # ---- untimed preparation = the callers of the path (bamse.py:95-97): reorder, greedy
+    #      candidate, threshold -- batched GPU list-scoring calls, fp64 check mode.
+    from bamse_b200.clustering import analyse_clusterings  # noqa: F401  (same steps, inlined for P > 1)
+    Ks, var, ref, Kmax = _pack_problem(clusts)
+    ctx.upload_problem([errs[0]], Ks, var, ref)
+    items, spans = [], []
+    for ci, c in enumerate(clusts):
+        pi = c._pair_items()
+        spans.append((len(items), len(pi)))
+        items += [(ci, t, n) for t, n in pi]
+    if items:
+        s = ctx.score_list(*_pack_items(Kmax, items), cuda_shim.FP64)[0]
+        for c, (o, n) in zip(clusts, spans):
+            c._apply_order(s[o:o + n] if n else [])
+    Ks, var, ref, Kmax = _pack_problem(clusts)
+    ctx.upload_problem(errs, Ks, var, ref)            # all P parameter sets resident from here on
+    cand = [[[-1] for _ in clusts] for _ in range(P)]
+    for n in range(1, Kmax):
+        items, owners = [], []
+        for ci, c in enumerate(clusts):
+            if c.As.shape[0] > n:
+                # candidates depend on e: score each p's own partial tree (P x n items per clustering)
+                for p in range(P):
+                    owners.append((p, ci, len(items)))
+                    items += [(ci, cand[p][ci] + [x], list(range(n + 1))) for x in range(n)]
+        sc = ctx.score_list(*_pack_items(Kmax, items), cuda_shim.FP64)
+        for p, ci, o in owners:
+            cand[p][ci] = cand[p][ci] + [int(np.argmax(sc[p, o:o + n]))]
+    items = [(ci, cand[p][ci], list(range(int(Ks[ci])))) for p in range(P) for ci in range(C)]
+    sc = ctx.score_list(*_pack_items(Kmax, items), cuda_shim.FP64)
+    thr = np.array([[sc[p, p * C + ci] + math.log(canonizeF(cand[p][ci])['scre']) for ci in range(C)] for p in range(P)])
+    const = np.array([[c.cluster_prior + c.maxlikelihood for c in clusts] for _ in range(P)])
+
+    # ---- shard: rank r takes tree indices [T*r/W, T*(r+1)/W) of every clustering
+    T = [int(k) ** (int(k) - 1) for k in Ks]
+    tb = np.array([t * rank // world for t in T], dtype=np.uint64)
+    te = np.array([t * (rank + 1) // world for t in T], dtype=np.uint64)
+    my_evals = int(sum(int(e - b) for b, e in zip(tb, te))) * P
+    total_evals = work["n_evals_per_param"] * P
+    topk = args.topk
+
+    # ---- device-resident state for the `value` measurement
+    # a real (non-default) torch stream: handle 0 would mean "the ctx's own stream" to the ABI
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    ctx.set_stream(stream.cuda_stream)
+    d_const = torch.from_numpy(const).to(dev)
+    d_thr = torch.from_numpy(thr).to(dev)
+    d_tb = torch.from_numpy(tb.view(np.int64)).to(dev)
+    d_te = torch.from_numpy(te.view(np.int64)).to(dev)
+    rec_words = topk * P * 4                         # a bamse_record = 4 x 8 bytes
+    d_local = torch.zeros(rec_words, dtype=torch.int64, device=dev)
+    d_all = torch.zeros(world * rec_words, dtype=torch.int64, device=dev)
+    d_final = torch.zeros(rec_words, dtype=torch.int64, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    slack = 0.0
+
+    def step_resident():
+        flush.fill_(1)
+        ctx.enumerate_topk_dev(d_const.data_ptr(), d_thr.data_ptr(), d_tb.data_ptr(), d_te.data_ptr(), topk, prec,
+                               slack, d_local.data_ptr())
+        if world > 1:
+            dist.all_gather_into_tensor(d_all, d_local)
+            ctx.merge_topk_dev(d_all.data_ptr(), world, P, topk, d_final.data_ptr())
+        else:
+            d_final.copy_(d_local)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step_resident()
+    barrier()
+    ctx.kernel_time(reset=True)
+    launches0 = ctx.launch_count
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        step_resident()
+    ev1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms = ev0.elapsed_time(ev1)
+    kern_ms, kern_n = ctx.kernel_time(reset=True)
+    launches = ctx.launch_count - launches0
+    t = torch.tensor([ms, kern_ms / max(1, kern_n)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max, kern_ms_max = float(t[0]), float(t[1])
+    final = d_final.cpu().numpy().view(cuda_shim.RECORD_DTYPE).reshape(P, topk)
+
+    # ---- e2e: the host-buffer C ABI, H2D + D2H inside the timed region
+    ctx.set_stream(None)
+    h2d = var.nbytes + ref.nbytes + Ks.nbytes + 8 * P + const.nbytes + thr.nbytes + tb.nbytes + te.nbytes
+    d2h = topk * P * 32 if prec == cuda_shim.FP64 else min(64, topk + 8) * P * 32 * 2
+    var_pin = torch.from_numpy(var).pin_memory().numpy()
+    ref_pin = torch.from_numpy(ref).pin_memory().numpy()
+
+    def step_e2e():
+        ctx.upload_problem(errs, Ks, var_pin, ref_pin)
+        rec, par, cnt = ctx.score_topk(const, thr, tb, te, topk=topk, precision=prec)
+        if world > 1:
+            loc = torch.from_numpy(rec.view(np.int64).reshape(-1).copy()).to(dev)
+            dist.all_gather_into_tensor(d_all, loc)
+            ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+            ctx.merge_topk_dev(d_all.data_ptr(), world, P, topk, d_final.data_ptr())
+            out = d_final.cpu()
+            ctx.set_stream(None)
+            return out.numpy().view(cuda_shim.RECORD_DTYPE).reshape(P, topk)
+        return rec
+
+    for _ in range(min(args.warmup, 2)):
+        step_e2e()
+    barrier()
+    e2e_steps = args.steps
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_rec = step_e2e()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    te2e = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te2e, op=dist.ReduceOp.MAX)
+    e2e_s = float(te2e[0])
+
+    if rank == 0:
+        # sanity: the resident path and the host path agree on the winning trees
+        same = [int(x) for x in final["tree"][0]] == [int(x) for x in e2e_rec["tree"][0]]
+        value = total_evals * args.steps / (ms_max / 1e3)
+        e2e_value = total_evals * e2e_steps / e2e_s
+        # roofline of the enumeration kernel (per launch, this rank's share of the trees)
+        peaks = pipe_peaks()
+        terms = xu = flops = 0.0
+        for k in Ks:
+            n_c, x, f = algorithmic_ops_per_eval(int(k), work["M"])
+            share = (int(k) ** (int(k) - 1)) / world * P
+            terms += n_c * share
+            xu += x * share
+            flops += f * share
+        kernel_s = kern_ms_max / 1e3
+        if args.precision == "fp64":
+            bound, achieved, peak, unit = "fp64-pipe", 40 * terms / kernel_s / 1e12, peaks["fp64_tflops"], "TFLOP/s"
+        else:
+            bound, achieved, peak, unit = "xu (MUFU ex2/lg2)", xu / kernel_s / 1e12, peaks["xu_tops"], "Tops/s"
+        roofline = {"bound": bound, "achieved": achieved, "peak": peak, "unit": unit, "frac": achieved / peak,
+                    "traffic": None, "peak_source": peaks["source"], "kernel": "k_enumerate_logdomain",
+                    "kernel_ms_per_launch": kern_ms_max, "algorithmic_conv_terms_per_launch": terms,
+                    "hbm": {"algorithmic_bytes_per_launch": int(h2d), "note": "HBM idle: inputs are KBs per launch"}}
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f32" if prec == cuda_shim.FP32 else "f64",
+                "data": "synthetic", "config": config_dict(args, work, world), "clocks": clocks,
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                        "ms_per_step": 1e3 * e2e_s / e2e_steps, "agrees_with_resident_path": bool(same)},
+                "gpu_launches": int(launches), "roofline": roofline,
+                "best": {"total": float(final["total"][0, 0]), "clust": int(final["clust"][0, 0]),
+                         "tree": int(final["tree"][0, 0])}}
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_reference_rate(work, args.cpu_items, os.cpu_count() or 1)
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

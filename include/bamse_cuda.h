@@ -141,6 +141,12 @@ int bamse_merge_topk_dev(bamse_ctx* ctx, const bamse_record* d_lists, int n_list
  * scored (sum over p, c of the index-range sizes). */
 int64_t bamse_last_eval_count(const bamse_ctx* ctx);
 
+/* Device time of the enumeration kernel itself: every bamse_enumerate_topk_dev /
+ * bamse_score_topk launch of it is bracketed by CUDA events on the ctx stream.  Returns
+ * the summed elapsed milliseconds and the number of launches since the last reset
+ * (synchronises the stream).  reset != 0 clears the accumulator after reading. */
+int bamse_kernel_time(bamse_ctx* ctx, int reset, double* out_ms, int64_t* out_launches);
+
 /* Host helper shared with the oracle's definition: index -> parent vector. */
 int bamse_decode_tree(int K, uint64_t tree_index, int8_t* out_parent /* [K] */);
 

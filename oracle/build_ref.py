@@ -1,7 +1,8 @@
 """TEST INFRASTRUCTURE ONLY.  Byte-compiles the reference's three hot-path modules
-from where they lie under /root/reference into oracle/_ref/*.pyc (sourceless .pyc,
-git-ignored; no reference SOURCE is copied into the repo).  The GPU box has the same
-image (same CPython magic), so the .pyc files import there via oracle/ref_shim.py and
+from where they lie under /root/reference into oracle/_ref/*.refbc (sourceless CPython
+byte-code, git-ignored; no reference SOURCE is copied into the repo; the extension is not
+.pyc because the gpurun snapshot drops *.pyc files).  The GPU box has the same
+image (same CPython magic), so the byte-code files import there via oracle/ref_shim.py and
 let `bench.py --impl reference` time the reference's own get_tree_score on the box's
 host cores.  No-op when /root/reference is absent.
 """
@@ -24,7 +25,7 @@ def build(verbose=True):
     for m in MODULES:
         py_compile.compile(
             os.path.join(SRC, m + ".py"),
-            cfile=os.path.join(DST, m + ".pyc"),
+            cfile=os.path.join(DST, m + ".refbc"),
             dfile=m + ".py",
             doraise=True,
             optimize=0,

@@ -5,7 +5,7 @@ tests / golden-vector generation / the `bench.py --impl reference` arm can call 
 reference's own functions.  Two sources, tried in this order:
 
   1. /root/reference/*.py            (this container only; read-only mount)
-  2. oracle/_ref/*.pyc               (sourceless byte-code compiled from (1) by
+  2. oracle/_ref/*.refbc             (sourceless byte-code compiled from (1) by
                                       oracle/build_ref.py; git-ignored build output
                                       that travels to the GPU box like a built .so)
 
@@ -17,6 +17,8 @@ reference:
   asciitree    (tree_io.py:3; only used by the text writer)         -> tiny stub
 """
 import importlib
+import importlib.machinery
+import importlib.util
 import os
 import sys
 import types
@@ -56,7 +58,7 @@ def available():
     """Where the reference can be loaded from: 'source', 'pyc' or None."""
     if os.path.isfile(os.path.join(REF_SRC, "clustering.py")):
         return "source"
-    if os.path.isfile(os.path.join(REF_PYC, "clustering.pyc")):
+    if os.path.isfile(os.path.join(REF_PYC, "clustering.refbc")):
         return "pyc"
     return None
 
@@ -70,21 +72,28 @@ def load():
     if kind is None:
         raise ImportError("reference not available (neither /root/reference nor oracle/_ref)")
     _install_stubs()
-    path = REF_SRC if kind == "source" else REF_PYC
     saved = {k: sys.modules.pop(k, None) for k in ("clustering", "tree_tools", "tree_io")}
-    sys.path.insert(0, path)
     old_dont = sys.dont_write_bytecode
     sys.dont_write_bytecode = True  # never write __pycache__ into the read-only mount
+
+    def _load(name):
+        # the reference modules import each other by bare name; loading them in dependency
+        # order with sys.modules populated satisfies those imports from either source
+        if kind == "source":
+            loader = importlib.machinery.SourceFileLoader(name, os.path.join(REF_SRC, name + ".py"))
+        else:
+            loader = importlib.machinery.SourcelessFileLoader(name, os.path.join(REF_PYC, name + ".refbc"))
+        spec = importlib.util.spec_from_loader(name, loader)
+        mod = importlib.util.module_from_spec(spec)
+        sys.modules[name] = mod
+        loader.exec_module(mod)
+        return mod
+
     try:
-        ns = types.SimpleNamespace(
-            tree_tools=importlib.import_module("tree_tools"),
-            tree_io=importlib.import_module("tree_io"),
-            clustering=importlib.import_module("clustering"),
-            kind=kind,
-        )
+        ns = types.SimpleNamespace(tree_tools=_load("tree_tools"), tree_io=_load("tree_io"),
+                                   clustering=_load("clustering"), kind=kind)
     finally:
         sys.dont_write_bytecode = old_dont
-        sys.path.remove(path)
         # keep the reference modules out of the global namespace of the caller
         for k in ("clustering", "tree_tools", "tree_io"):
             mod = sys.modules.pop(k, None)
