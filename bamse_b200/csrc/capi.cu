@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "kernels.cuh"
+#include "score_fast.cuh"
 #include "tree_decode.cuh"
 
 using namespace bamse;
@@ -44,12 +45,12 @@ struct bamse_ctx {
     bool have_problem = false;
     int P = 0, C = 0, M = 0, Kmax = 0;
     std::vector<int32_t> K_of_c;
-    DBuf d_K, d_p0, d_var, d_ref, d_logc, d_logcf, d_log1mcf, d_D64, d_D32;
+    DBuf d_K, d_p0, d_var, d_ref, d_logc, d_logcf, d_log1mcf, d_D64, d_D32, d_D2, d_EL2, d_SEL2;
 
     // work buffers
     DBuf d_segs, d_scalars /* total_chunks, total_trees, next_chunk */, d_cand, d_items, d_scores;
     DBuf d_const, d_thr, d_begin, d_end, d_records, d_dense0, d_dense1;
-    int grid[2] = {0, 0};
+    int grid[3] = {0, 0, 0};
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_used, ev_free;
 
     int fail(int code, const char* fmt, ...) {
@@ -61,6 +62,11 @@ struct bamse_ctx {
         err = buf;
         return code;
     }
+    FastTables fast() const {
+        FastTables f;
+        f.D2 = d_D2.as<float>(); f.EL2 = d_EL2.as<float>(); f.SEL2 = d_SEL2.as<float>();
+        return f;
+    }
     ProblemView view() const {
         ProblemView v;
         v.P = P; v.C = C; v.M = M; v.Kmax = Kmax;
@@ -69,6 +75,8 @@ struct bamse_ctx {
         return v;
     }
 };
+
+static inline bool valid_precision(int p) { return p == BAMSE_FP32 || p == BAMSE_FP64 || p == BAMSE_FP32_LOGDOMAIN; }
 
 #define CTX_CHECK(ctx)                      \
     do {                                    \
@@ -128,7 +136,7 @@ void bamse_destroy(bamse_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     DBuf* bufs[] = {&ctx->d_K, &ctx->d_p0, &ctx->d_var, &ctx->d_ref, &ctx->d_logc, &ctx->d_logcf, &ctx->d_log1mcf,
-                    &ctx->d_D64, &ctx->d_D32, &ctx->d_segs, &ctx->d_scalars, &ctx->d_cand, &ctx->d_items,
+                    &ctx->d_D64, &ctx->d_D32, &ctx->d_D2, &ctx->d_EL2, &ctx->d_SEL2, &ctx->d_segs, &ctx->d_scalars, &ctx->d_cand, &ctx->d_items,
                     &ctx->d_scores, &ctx->d_const, &ctx->d_thr, &ctx->d_begin, &ctx->d_end, &ctx->d_records,
                     &ctx->d_dense0, &ctx->d_dense1};
     for (DBuf* b : bufs) b->release();
@@ -162,6 +170,18 @@ int bamse_kernel_time(bamse_ctx* ctx, int reset, double* out_ms, int64_t* out_la
         for (auto& ev : ctx->ev_used) ctx->ev_free.push_back(ev);
         ctx->ev_used.clear();
     }
+    return BAMSE_OK;
+}
+
+int bamse_kernel_stats(bamse_ctx* ctx, int reset, uint64_t* out4) {
+    CTX_CHECK(ctx);
+    if (!out4) return ctx->fail(BAMSE_EINVAL, "bamse_kernel_stats: out4 is NULL");
+    for (int i = 0; i < 4; ++i) out4[i] = 0;
+    if (!ctx->d_scalars.p) return BAMSE_OK;
+    uint64_t* scal = ctx->d_scalars.as<uint64_t>();
+    BAMSE_CUDA_TRY(ctx, cudaMemcpyAsync(out4, scal + 4, sizeof(uint64_t) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (reset) BAMSE_CUDA_TRY(ctx, cudaMemsetAsync(scal + 4, 0, sizeof(uint64_t) * 4, ctx->stream));
+    BAMSE_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     return BAMSE_OK;
 }
 
@@ -224,6 +244,9 @@ int bamse_upload_problem(bamse_ctx* ctx, int P, const double* err, int C, int M,
     BAMSE_CUDA_TRY(ctx, ctx->d_log1mcf.ensure(sizeof(double) * P * L));
     BAMSE_CUDA_TRY(ctx, ctx->d_D64.ensure(sizeof(double) * nrows * L));
     BAMSE_CUDA_TRY(ctx, ctx->d_D32.ensure(sizeof(float) * nrows * L));
+    BAMSE_CUDA_TRY(ctx, ctx->d_D2.ensure(sizeof(float) * nrows * L));
+    BAMSE_CUDA_TRY(ctx, ctx->d_EL2.ensure(sizeof(float) * nrows * L));
+    BAMSE_CUDA_TRY(ctx, ctx->d_SEL2.ensure(sizeof(float) * nrows * L));
     cudaStream_t s = ctx->stream;
     BAMSE_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_K.p, K_of_c, sizeof(int32_t) * C, cudaMemcpyHostToDevice, s));
     BAMSE_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_p0.p, p0.data(), sizeof(double) * C, cudaMemcpyHostToDevice, s));
@@ -237,7 +260,8 @@ int bamse_upload_problem(bamse_ctx* ctx, int P, const double* err, int C, int M,
     launch_tables(ctx->view(), ctx->d_var.as<double>(), ctx->d_ref.as<double>(), ctx->d_logc.as<double>(),
                   ctx->d_logcf.as<double>(), ctx->d_log1mcf.as<double>(), ctx->d_D64.as<double>(),
                   ctx->d_D32.as<float>(), s);
-    ctx->launches++;
+    launch_tables_fast(ctx->view(), ctx->d_D2.as<float>(), ctx->d_EL2.as<float>(), ctx->d_SEL2.as<float>(), s);
+    ctx->launches += 2;
     BAMSE_CUDA_TRY(ctx, cudaGetLastError());
     BAMSE_CUDA_TRY(ctx, cudaStreamSynchronize(s));   // host staging vectors die at return
     ctx->have_problem = true;
@@ -252,7 +276,10 @@ static int score_items_host(bamse_ctx* ctx, const std::vector<ScoreItem>& items,
     BAMSE_CUDA_TRY(ctx, ctx->d_scores.ensure(sizeof(double) * n));
     cudaStream_t s = ctx->stream;
     BAMSE_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_items.p, items.data(), sizeof(ScoreItem) * n, cudaMemcpyHostToDevice, s));
-    launch_score_items(precision, ctx->view(), ctx->d_items.as<ScoreItem>(), (int64_t)n, ctx->d_scores.as<double>(), s);
+    if (precision == BAMSE_FP32)
+        launch_score_items_fast(ctx->view(), ctx->fast(), ctx->d_items.as<ScoreItem>(), (int64_t)n, ctx->d_scores.as<double>(), s);
+    else
+        launch_score_items(precision, ctx->view(), ctx->d_items.as<ScoreItem>(), (int64_t)n, ctx->d_scores.as<double>(), s);
     ctx->launches++;
     BAMSE_CUDA_TRY(ctx, cudaGetLastError());
     BAMSE_CUDA_TRY(ctx, cudaMemcpyAsync(out, ctx->d_scores.p, sizeof(double) * n, cudaMemcpyDeviceToHost, s));
@@ -266,7 +293,7 @@ int bamse_score_list(bamse_ctx* ctx, int64_t n_items, const int32_t* item_clust,
     if (!ctx->have_problem) return ctx->fail(BAMSE_ESTATE, "bamse_score_list: no problem uploaded");
     if (n_items < 0 || (n_items > 0 && (!item_clust || !item_parent || !item_nodes || !out_score)))
         return ctx->fail(BAMSE_EINVAL, "bamse_score_list: NULL pointer or negative n_items");
-    if (precision != BAMSE_FP32 && precision != BAMSE_FP64)
+    if (!valid_precision(precision))
         return ctx->fail(BAMSE_EINVAL, "bamse_score_list: precision must be BAMSE_FP32 or BAMSE_FP64");
     const int Kmax = ctx->Kmax;
     std::vector<ScoreItem> items((size_t)ctx->P * n_items);
@@ -304,14 +331,16 @@ static int enumerate_dev(bamse_ctx* ctx, const double* d_const, const double* d_
                          const Segment* host_seg /* non-NULL: dense single-segment mode */) {
     const int P = ctx->P, C = ctx->C;
     cudaStream_t s = ctx->stream;
-    const int pi = precision == BAMSE_FP64 ? 1 : 0;
-    if (ctx->grid[pi] == 0) ctx->grid[pi] = enumerate_grid_size(precision, ctx->device);
+    const int pi = precision == BAMSE_FP64 ? 1 : (precision == BAMSE_FP32 ? 0 : 2);
+    if (precision == BAMSE_FP32) ctx->grid[pi] = enumerate_fast_grid_size(ctx->device, topk);
+    else if (ctx->grid[pi] == 0) ctx->grid[pi] = enumerate_grid_size(precision, ctx->device);
     const int grid = ctx->grid[pi];
-    const int chunk = 8;
+    const int chunk = precision == BAMSE_FP32 ? 32 : 8;
     BAMSE_CUDA_TRY(ctx, ctx->d_segs.ensure(sizeof(Segment) * P * C));
-    BAMSE_CUDA_TRY(ctx, ctx->d_scalars.ensure(sizeof(uint64_t) * 4));
+    const bool fresh_scalars = ctx->d_scalars.p == nullptr;
+    BAMSE_CUDA_TRY(ctx, ctx->d_scalars.ensure(sizeof(uint64_t) * 8));
     uint64_t* scal = ctx->d_scalars.as<uint64_t>();
-    BAMSE_CUDA_TRY(ctx, cudaMemsetAsync(scal, 0, sizeof(uint64_t) * 4, s));
+    BAMSE_CUDA_TRY(ctx, cudaMemsetAsync(scal, 0, sizeof(uint64_t) * (fresh_scalars ? 8 : 4), s));   // stats [4..8) accumulate until read
     if (topk > 0) {
         BAMSE_CUDA_TRY(ctx, ctx->d_cand.ensure(sizeof(bamse_record) * (size_t)P * grid * topk));
         BAMSE_CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_cand.p, 0xFF, sizeof(bamse_record) * (size_t)P * grid * topk, s));
@@ -339,6 +368,7 @@ static int enumerate_dev(bamse_ctx* ctx, const double* d_const, const double* d_
     w.cand = ctx->d_cand.as<bamse_record>();
     w.dense_score = d_dense_score;
     w.dense_logscre = d_dense_logscre;
+    w.stats = reinterpret_cast<unsigned long long*>(scal + 4);
     std::pair<cudaEvent_t, cudaEvent_t> ev;
     if (!ctx->ev_free.empty()) { ev = ctx->ev_free.back(); ctx->ev_free.pop_back(); }
     else {
@@ -346,7 +376,8 @@ static int enumerate_dev(bamse_ctx* ctx, const double* d_const, const double* d_
         BAMSE_CUDA_TRY(ctx, cudaEventCreate(&ev.second));
     }
     BAMSE_CUDA_TRY(ctx, cudaEventRecord(ev.first, s));
-    launch_enumerate(precision, ctx->view(), w, grid, s);
+    if (precision == BAMSE_FP32) launch_enumerate_fast(ctx->view(), ctx->fast(), w, grid, s);
+    else launch_enumerate(precision, ctx->view(), w, grid, s);
     BAMSE_CUDA_TRY(ctx, cudaEventRecord(ev.second, s));
     ctx->ev_used.push_back(ev);
     ctx->launches++;
@@ -365,7 +396,7 @@ int bamse_score_range(bamse_ctx* ctx, int p, int c, uint64_t tree_begin, int64_t
     if (!ctx->have_problem) return ctx->fail(BAMSE_ESTATE, "bamse_score_range: no problem uploaded");
     if (p < 0 || p >= ctx->P || c < 0 || c >= ctx->C || n < 0)
         return ctx->fail(BAMSE_EINVAL, "bamse_score_range: p/c/n out of range");
-    if (precision != BAMSE_FP32 && precision != BAMSE_FP64)
+    if (!valid_precision(precision))
         return ctx->fail(BAMSE_EINVAL, "bamse_score_range: bad precision");
     const int K = ctx->K_of_c[c];
     const uint64_t T = ipow_u64(K, K - 1);
@@ -396,7 +427,7 @@ int bamse_enumerate_topk_dev(bamse_ctx* ctx, const double* d_clust_const, const 
     if (!ctx->have_problem) return ctx->fail(BAMSE_ESTATE, "bamse_enumerate_topk_dev: no problem uploaded");
     if (topk < 1 || topk > BAMSE_TOPK_MAX || !d_out_records)
         return ctx->fail(BAMSE_EINVAL, "bamse_enumerate_topk_dev: topk must be in [1,%d], d_out_records non-NULL", BAMSE_TOPK_MAX);
-    if (precision != BAMSE_FP32 && precision != BAMSE_FP64)
+    if (!valid_precision(precision))
         return ctx->fail(BAMSE_EINVAL, "bamse_enumerate_topk_dev: bad precision");
     // eval count (host arithmetic; ranges live on the device, so count full ranges unless given)
     ctx->last_evals = -1;
@@ -422,7 +453,7 @@ int bamse_score_topk(bamse_ctx* ctx, const double* clust_const, const double* th
     if (!ctx->have_problem) return ctx->fail(BAMSE_ESTATE, "bamse_score_topk: no problem uploaded");
     if (!clust_const || !out_records || topk < 1 || topk > BAMSE_TOPK_MAX)
         return ctx->fail(BAMSE_EINVAL, "bamse_score_topk: clust_const/out_records NULL or topk not in [1,%d]", BAMSE_TOPK_MAX);
-    if (precision != BAMSE_FP32 && precision != BAMSE_FP64)
+    if (!valid_precision(precision))
         return ctx->fail(BAMSE_EINVAL, "bamse_score_topk: bad precision");
     if ((tree_begin == nullptr) != (tree_end == nullptr))
         return ctx->fail(BAMSE_EINVAL, "bamse_score_topk: tree_begin and tree_end must both be given or both NULL");

@@ -1,0 +1,247 @@
+// fp32 production kernels: table preparation and the warp-per-tree enumeration / list
+// scoring kernels built on score_fast.cuh.
+#include "kernels.cuh"
+#include "score_fast.cuh"
+#include "score_logdomain.cuh"
+
+namespace bamse {
+
+// ---------------------------------------------------------------- fast tables (fp64 -> fp32 log2)
+// one CTA (256 threads) per table row: EL = logcumsum(D) + p0 - log L, SEL = logcumsum(EL) + p0 - log L
+// computed in fp64 natural logs, stored as fp32 base-2 logs.
+__global__ void __launch_bounds__(LD_THREADS) k_tables_fast(ProblemView pv, float* __restrict__ D2,
+                                                            float* __restrict__ EL2, float* __restrict__ SEL2) {
+    __shared__ double v[L];
+    __shared__ double scratch[LD_THREADS / 32];
+    const int row = blockIdx.x;
+    const int c = (row / (pv.Kmax * pv.M)) % pv.C;
+    const int t = threadIdx.x;
+    const double log2e = 1.4426950408889634074;
+    const double add = pv.p0[c] - 6.2383246250395077847550890931236;
+    const double* src = pv.D64 + (size_t)row * L;
+    v[t] = src[t]; v[t + LD_THREADS] = src[t + LD_THREADS];
+    D2[(size_t)row * L + t] = (float)(v[t] * log2e);
+    D2[(size_t)row * L + t + LD_THREADS] = (float)(v[t + LD_THREADS] * log2e);
+    __syncthreads();
+    block_logcumsum<double>(v, add, scratch);
+    EL2[(size_t)row * L + t] = (float)(v[t] * log2e);
+    EL2[(size_t)row * L + t + LD_THREADS] = (float)(v[t + LD_THREADS] * log2e);
+    __syncthreads();
+    block_logcumsum<double>(v, add, scratch);
+    SEL2[(size_t)row * L + t] = (float)(v[t] * log2e);
+    SEL2[(size_t)row * L + t + LD_THREADS] = (float)(v[t + LD_THREADS] * log2e);
+}
+
+void launch_tables_fast(const ProblemView& pv, float* D2, float* EL2, float* SEL2, cudaStream_t s) {
+    const int rows = pv.P * pv.C * pv.M * pv.Kmax;
+    k_tables_fast<<<rows, LD_THREADS, 0, s>>>(pv, D2, EL2, SEL2);
+}
+
+// ------------------------------------------------------------------ per-warp evaluation
+struct alignas(16) WarpSmem {
+    float vec[FAST_SLOTS][VSTRIDE];
+    uint16_t jstar[L];
+    TreeProgram prog;
+    int ntop;
+};
+// dynamic shared memory: FAST_WARPS x WarpSmem, then FAST_WARPS x topk bamse_records
+
+__device__ inline void warp_init_guards(WarpSmem* ws, int lane) {
+    for (int s = 0; s < FAST_SLOTS; ++s) {
+        for (int i = lane; i < GUARD; i += 32) ws->vec[s][i] = -CUDART_INF_F;
+        if (lane < 4) ws->vec[s][GUARD + L + lane] = -CUDART_INF_F;
+    }
+    __syncwarp();
+}
+
+// score of the tree whose program sits in ws->prog, summed over samples (fp64), natural log
+__device__ inline double warp_eval_tree(const ProblemView& pv, const FastTables& ft, int p, int c, WarpSmem* ws,
+                                        int lane, unsigned* st_chunks, unsigned* st_convs, unsigned* st_scans) {
+    const float add2 = (float)((pv.p0[c] - 6.2383246250395077847550890931236) * 1.4426950408889634074);
+    const int n_ops = ws->prog.n_ops;
+    double total = 0.0;
+    for (int m = 0; m < pv.M; ++m) {
+        const size_t base = pv.table_offset(p, c, m);
+        int sp = 0;                                  // stack position == slot (convolution is in place)
+        for (int i = 0; i < n_ops; ++i) {
+            const int op = ws->prog.op[i];
+            const int arg = ws->prog.arg[i];
+            if (op == FOP_PUSH_EL || op == FOP_PUSH_SEL) {
+                float* dst = ws->vec[sp] + GUARD;
+                warp_load_vec(dst, (op == FOP_PUSH_EL ? ft.EL2 : ft.SEL2) + base + (size_t)arg * L, lane);
+                ++sp;
+            } else if (op == FOP_SCAN) {
+                warp_log2cumsum(ws->vec[sp - 1] + GUARD, add2, lane);
+                ++*st_scans;
+            } else if (op == FOP_CONV) {
+                *st_chunks += warp_logconv(ws->vec[sp - 2] + GUARD, ws->vec[sp - 1] + GUARD, ws->jstar, lane);
+                ++*st_convs;
+                --sp;
+            } else {  // FOP_ADDD
+                warp_add_table(ws->vec[sp - 1] + GUARD, ft.D2 + base + (size_t)arg * L, lane);
+            }
+        }
+        const float lse2 = warp_log2sumexp(ws->vec[0] + GUARD, lane);
+        total += (double)(lse2 - LOG2_L) * 0.69314718055994530942;
+    }
+    return total;
+}
+
+__device__ __forceinline__ bool rec_better_f(const bamse_record& a, const bamse_record& b) {
+    if (a.total != b.total) return a.total > b.total;
+    if (a.clust != b.clust) return a.clust < b.clust;
+    return a.tree < b.tree;
+}
+
+// ---------------------------------------------------------------------- enumerate (fp32)
+// Persistent CTAs pull chunks of consecutive tree indices from a global counter; inside a
+// chunk every warp pulls its next tree from a shared-memory counter, so a warp that drew
+// cheap trees (few leaves) simply scores more of them.
+__global__ void __launch_bounds__(FAST_THREADS, 7) k_enumerate_fast(ProblemView pv, FastTables ft, EnumWork w) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    WarpSmem* wsm = reinterpret_cast<WarpSmem*>(smem_raw);
+    bamse_record* s_top_all = reinterpret_cast<bamse_record*>(smem_raw + sizeof(WarpSmem) * FAST_WARPS);
+    __shared__ unsigned long long s_chunk;
+    __shared__ int s_next;
+    const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+    WarpSmem* ws = wsm + wid;
+    const int kcap = w.topk > 0 ? w.topk : 1;
+    warp_init_guards(ws, lane);
+    if (lane == 0) ws->ntop = 0;
+    int cur_p = -1;
+    const uint64_t total = *w.total_chunks;
+    unsigned st_chunks = 0, st_convs = 0, st_scans = 0, st_samples = 0;
+
+    auto flush = [&](int p) {
+        // merge the FAST_WARPS per-warp lists into cand[p][blockIdx.x][0..topk)
+        __syncthreads();
+        if (t == 0) {
+            bamse_record* dst = w.cand + ((size_t)p * gridDim.x + blockIdx.x) * w.topk;
+            int pos[FAST_WARPS];
+            for (int i = 0; i < FAST_WARPS; ++i) pos[i] = 0;
+            for (int r = 0; r < w.topk; ++r) {
+                int best = -1;
+                for (int i = 0; i < FAST_WARPS; ++i)
+                    if (pos[i] < wsm[i].ntop &&
+                        (best < 0 || rec_better_f(s_top_all[i * kcap + pos[i]], s_top_all[best * kcap + pos[best]])))
+                        best = i;
+                if (best < 0) break;
+                dst[r] = s_top_all[best * kcap + pos[best]++];
+            }
+            for (int i = 0; i < FAST_WARPS; ++i) wsm[i].ntop = 0;
+        }
+        __syncthreads();
+    };
+
+    for (;;) {
+        __syncthreads();
+        if (t == 0) { s_chunk = atomicAdd(w.next_chunk, 1ull); s_next = 0; }
+        __syncthreads();
+        const uint64_t chunk = s_chunk;
+        if (chunk >= total) break;
+        int lo = 0, hi = w.n_segs - 1;
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (w.segs[mid].first_chunk <= chunk) lo = mid; else hi = mid - 1;
+        }
+        const Segment seg = w.segs[lo];
+        if (seg.p != cur_p) {
+            if (cur_p >= 0) flush(cur_p);
+            cur_p = seg.p;
+        }
+        const uint64_t off = (chunk - seg.first_chunk) * (uint64_t)w.chunk;
+        const uint64_t remain = seg.n_trees - off;
+        const int n = remain < (uint64_t)w.chunk ? (int)remain : w.chunk;
+        for (;;) {
+            int i = 0;
+            if (lane == 0) i = atomicAdd(&s_next, 1);
+            i = __shfl_sync(0xffffffffu, i, 0);
+            if (i >= n) break;
+            const uint64_t tree = seg.tree_begin + off + i;
+            if (lane == 0) {
+                int8_t parent[KMAX];
+                decode_tree(seg.K, tree, parent);
+                build_program_fast(seg.K, parent, nullptr, &ws->prog);
+            }
+            __syncwarp();
+            const double score = warp_eval_tree(pv, ft, seg.p, seg.c, ws, lane, &st_chunks, &st_convs, &st_scans);
+            st_samples += pv.M;
+            if (lane == 0) {
+                const double logscre = log((double)ws->prog.scre);
+                const double full = score + logscre;
+                if (w.dense_score) w.dense_score[off + i] = score;
+                if (w.dense_logscre) w.dense_logscre[off + i] = logscre;
+                if (w.topk > 0 && full >= seg.threshold) {
+                    bamse_record r;
+                    r.total = full + seg.clust_const; r.score = full; r.clust = seg.c; r.param = seg.p; r.tree = tree;
+                    bamse_record* list = s_top_all + wid * kcap;
+                    int cnt = ws->ntop;
+                    if (!(cnt == w.topk && !rec_better_f(r, list[w.topk - 1]))) {
+                        int q = cnt < w.topk ? cnt : w.topk - 1;
+                        while (q > 0 && rec_better_f(r, list[q - 1])) { list[q] = list[q - 1]; --q; }
+                        list[q] = r;
+                        if (cnt < w.topk) ws->ntop = cnt + 1;
+                    }
+                }
+            }
+            __syncwarp();
+        }
+    }
+    if (cur_p >= 0) flush(cur_p);
+    if (w.stats && lane == 0) {
+        // thread-level MUFU ops: 4 ex2 per chunk per lane x 32 lanes, 16 passes x 1 lg2 x 32 per conv,
+        // 59 per lane per scan, 17 per lane per final log-sum-exp
+        const unsigned long long mufu = 128ull * st_chunks + 512ull * st_convs + 59ull * 32 * st_scans + 17ull * 32 * st_samples;
+        atomicAdd(w.stats + 0, mufu);
+        atomicAdd(w.stats + 1, 128ull * st_chunks);
+        atomicAdd(w.stats + 2, (unsigned long long)st_convs);
+        atomicAdd(w.stats + 3, (unsigned long long)st_scans);
+    }
+}
+
+static size_t fast_smem_bytes(int topk) {
+    return sizeof(WarpSmem) * FAST_WARPS + sizeof(bamse_record) * FAST_WARPS * (size_t)(topk > 0 ? topk : 1);
+}
+
+int enumerate_fast_grid_size(int device, int topk) {
+    int sms = 148, per_sm = 1;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    cudaFuncSetAttribute(k_enumerate_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_smem_bytes(BAMSE_TOPK_MAX));
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_enumerate_fast, FAST_THREADS, fast_smem_bytes(topk));
+    if (per_sm < 1) per_sm = 1;
+    return sms * per_sm;
+}
+
+void launch_enumerate_fast(const ProblemView& pv, const FastTables& ft, const EnumWork& w, int grid, cudaStream_t s) {
+    k_enumerate_fast<<<grid, FAST_THREADS, fast_smem_bytes(w.topk), s>>>(pv, ft, w);
+}
+
+// ---------------------------------------------------------------------- explicit items (fp32)
+__global__ void __launch_bounds__(FAST_THREADS) k_score_items_fast(ProblemView pv, FastTables ft,
+                                                                   const ScoreItem* __restrict__ items, int64_t n,
+                                                                   double* __restrict__ out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    WarpSmem* ws = reinterpret_cast<WarpSmem*>(smem_raw) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    const int64_t idx = (int64_t)blockIdx.x * FAST_WARPS + (threadIdx.x >> 5);
+    if (idx >= n) return;
+    warp_init_guards(ws, lane);
+    const ScoreItem it = items[idx];
+    int ok = 1;
+    if (lane == 0) ok = build_program_fast(it.k, it.parent, it.nodes, &ws->prog) ? 1 : 0;
+    ok = __shfl_sync(0xffffffffu, ok, 0);
+    if (!ok) { if (lane == 0) out[idx] = CUDART_NAN; return; }
+    unsigned s0 = 0, s1 = 0, s2 = 0;
+    const double score = warp_eval_tree(pv, ft, it.p, it.c, ws, lane, &s0, &s1, &s2);
+    if (lane == 0) out[idx] = score;
+}
+
+void launch_score_items_fast(const ProblemView& pv, const FastTables& ft, const ScoreItem* d_items, int64_t n,
+                             double* d_out, cudaStream_t s) {
+    if (n <= 0) return;
+    cudaFuncSetAttribute(k_score_items_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_smem_bytes(1));
+    const unsigned blocks = (unsigned)((n + FAST_WARPS - 1) / FAST_WARPS);
+    k_score_items_fast<<<blocks, FAST_THREADS, fast_smem_bytes(1), s>>>(pv, ft, d_items, n, d_out);
+}
+
+}  // namespace bamse

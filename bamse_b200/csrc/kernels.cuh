@@ -38,6 +38,7 @@ struct EnumWork {
     bamse_record* cand;      // [P][gridDim.x][topk] per-CTA candidates (clust = -1 when unused)
     double* dense_score;     // optional [n_trees of segment 0]
     double* dense_logscre;   // optional
+    unsigned long long* stats;   // optional [4]: executed MUFU ops (thread level), conv terms, convs, scans
 };
 
 void launch_tables(const ProblemView& pv, const double* d_var, const double* d_ref, const double* d_logc,
@@ -54,5 +55,12 @@ void launch_score_items(int precision, const ProblemView& pv, const ScoreItem* d
 // list l of parameter set p starts at d_lists + (l * stride_list + p * stride_p) * topk
 void launch_merge_topk(const bamse_record* d_lists, int n_lists, int64_t stride_list, int64_t stride_p, int P,
                        int topk, bamse_record* d_out, cudaStream_t s);
+
+struct FastTables;
+void launch_tables_fast(const ProblemView& pv, float* D2, float* EL2, float* SEL2, cudaStream_t s);
+int enumerate_fast_grid_size(int device, int topk);
+void launch_enumerate_fast(const ProblemView& pv, const FastTables& ft, const EnumWork& w, int grid, cudaStream_t s);
+void launch_score_items_fast(const ProblemView& pv, const FastTables& ft, const ScoreItem* d_items, int64_t n,
+                             double* d_out, cudaStream_t s);
 
 }  // namespace bamse

@@ -1,0 +1,314 @@
+// fp32 production scorer: one WARP per tree, vectors kept in shared memory as fp32 log2
+// values.  Every message in this computation is a log-concave sequence (binomial
+// likelihoods are log-concave; prefix sums, truncated convolutions and pointwise
+// products preserve log-concavity), which the convolution exploits:
+//
+//   * merge path: for log-concave a, b the maximising split (i*, j*) of every output
+//     x = i + j walks the merge of the two decreasing slope sequences, so the exact
+//     per-output max-shift M_x costs O(L) per convolution instead of an O(L^2) max pass;
+//   * windowing: the terms of one output are concave in j, so the ones within THETA bits
+//     of M_x form a contiguous window around j*; only those are exponentiated (MUFU.EX2),
+//     32 consecutive outputs at a time over the union of their windows.
+//
+// Results equal the reference's my_convolve (clustering.py:365-370) up to fp32 rounding:
+// dropped terms are below 2^-THETA of the output they belong to.
+#pragma once
+#include "common.cuh"
+#include "tree_decode.cuh"
+
+namespace bamse {
+
+constexpr int FAST_WARPS = 4;                       // warps per CTA
+constexpr int FAST_THREADS = FAST_WARPS * 32;
+constexpr int GUARD = 36;                           // -inf floats in front of every vector (a[x-j], j <= xmax+3)
+constexpr int VSTRIDE = GUARD + L + 4;              // floats per vector slot (4 trailing -inf: b[j], j <= 514)
+constexpr int FAST_SLOTS = 3;                       // max live vectors with the in-place convolution (brute-forced, K <= 12)
+constexpr float THETA = 36.0f;                      // window threshold in bits
+constexpr float LOG2_L = 9.0f;                      // log2(512)
+
+struct FastTables {
+    const float* D2;     // [rows][L] log2 of the binomial tables                (clustering.py:20-24)
+    const float* EL2;    // [rows][L] leaf message  log2cumsum(D) + p0 - log L   (clustering.py:377)
+    const float* SEL2;   // [rows][L] scanned leaf message (a leaf used as the scan factor)
+};
+
+// evaluation program of the fast path (convolution is commutative/associative, so the
+// factor that carries the prefix sum may be any child; a leaf child is preferred because
+// its scanned message is a table)
+enum : int8_t {
+    FOP_PUSH_EL = 0,    // push EL2[arg]
+    FOP_PUSH_SEL = 1,   // push SEL2[arg]
+    FOP_SCAN = 2,       // top = log2cumsum(top) + p0 - log L
+    FOP_CONV = 3,       // b = pop; top = top (*) b   (in place)
+    FOP_ADDD = 4,       // top += D2[arg]
+};
+
+// Builds the fast program + canonizeF weight.  Same validity rules as build_program.
+__host__ __device__ inline bool build_program_fast(int k, const int8_t* parent, const int8_t* nodes,
+                                                   TreeProgram* prog) {
+    // canon weight / validation through the reference-order builder
+    if (!build_program(k, parent, nodes, prog)) return false;
+    const int32_t scre = prog->scre;
+    const int n_leaves = prog->n_leaves;
+    int root = 0;
+    int8_t nchild[KMAX], size[KMAX], order[KMAX];
+    for (int v = 0; v < k; ++v) { nchild[v] = 0; size[v] = 1; if (parent[v] == -1) root = v; }
+    for (int v = 0; v < k; ++v) if (parent[v] >= 0) nchild[parent[v]]++;
+    // subtree sizes: process nodes in decreasing depth order (depth via parent walks)
+    int8_t depth[KMAX];
+    for (int v = 0; v < k; ++v) { int d = 0, w = v; while (parent[w] >= 0) { w = parent[w]; ++d; } depth[v] = (int8_t)d; order[v] = (int8_t)v; }
+    for (int i = 1; i < k; ++i) { int8_t o = order[i]; int j = i; while (j > 0 && depth[order[j - 1]] < depth[o]) { order[j] = order[j - 1]; --j; } order[j] = o; }
+    for (int i = 0; i < k; ++i) { const int v = order[i]; if (parent[v] >= 0) size[parent[v]] += size[v]; }
+
+    // iterative emission.  frame: node, phase; children lists are recomputed by scanning.
+    int8_t st_node[KMAX], st_stage[KMAX], st_done[KMAX];
+    uint16_t st_used[KMAX];              // internal children already evaluated (bit mask)
+    int n_ops = 0, sp = 0;
+    auto emit = [&](int8_t op, int8_t arg) { prog->op[n_ops] = op; prog->arg[n_ops] = arg; ++n_ops; };
+    if (nchild[root] == 0) { emit(FOP_PUSH_EL, nodes ? nodes[root] : (int8_t)root); }
+    else { st_node[0] = (int8_t)root; st_stage[0] = 0; st_done[0] = 0; st_used[0] = 0; sp = 1; }
+    while (sp > 0) {
+        const int f = sp - 1, v = st_node[f];
+        if (st_stage[f] == 0) {
+            // next unevaluated internal child with the largest subtree
+            int best = -1;
+            for (int c = 0; c < k; ++c)
+                if (parent[c] == v && nchild[c] > 0 && !((st_used[f] >> c) & 1) && (best < 0 || size[c] > size[best])) best = c;
+            if (best >= 0) {
+                st_used[f] |= (uint16_t)(1u << best);
+                st_stage[f] = 1;                     // after the child returns: fold it
+                st_node[sp] = (int8_t)best; st_stage[sp] = 0; st_done[sp] = 0; st_used[sp] = 0; ++sp;
+                continue;
+            }
+            // internal children done: leaves
+            bool first_leaf = true;
+            for (int c = 0; c < k; ++c)
+                if (parent[c] == v && nchild[c] == 0) {
+                    if (n_ops + 2 > MAX_OPS) return false;
+                    if (first_leaf) { emit(FOP_PUSH_SEL, nodes ? nodes[c] : (int8_t)c); first_leaf = false; }
+                    else emit(FOP_PUSH_EL, nodes ? nodes[c] : (int8_t)c);
+                    if (st_done[f] > 0) emit(FOP_CONV, 0);
+                    st_done[f]++;
+                }
+            if (n_ops + 2 > MAX_OPS) return false;
+            if (first_leaf) emit(FOP_SCAN, 0);       // no leaf child: the accumulated product carries the scan
+            emit(FOP_ADDD, nodes ? nodes[v] : (int8_t)v);
+            --sp;
+        } else {
+            // an internal child's message is on the stack
+            if (n_ops + 1 > MAX_OPS) return false;
+            if (st_done[f] > 0) emit(FOP_CONV, 0);
+            st_done[f]++;
+            st_stage[f] = 0;
+        }
+    }
+    prog->n_ops = (int8_t)n_ops; prog->k = (int8_t)k; prog->n_leaves = (int8_t)n_leaves; prog->scre = scre;
+    return true;
+}
+
+// ----------------------------------------------------------------------------- warp ops
+__device__ __forceinline__ float ex2f(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float lg2f(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+__device__ __forceinline__ float log2addexp(float a, float b) {
+    const float m = fmaxf(a, b), d = fminf(a, b) - m;      // d <= 0 (NaN only if both -inf)
+    if (!(d > -40.0f)) return m;                           // also catches -inf / NaN
+    return m + lg2f(1.0f + ex2f(d));
+}
+
+__device__ __forceinline__ void warp_load_vec(float* __restrict__ dst, const float* __restrict__ src, int lane) {
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(src) + lane + 32 * t);
+        reinterpret_cast<float4*>(dst)[lane + 32 * t] = v;
+    }
+    __syncwarp();
+}
+
+__device__ __forceinline__ void warp_add_table(float* __restrict__ v, const float* __restrict__ src, int lane) {
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        const float4 d = __ldg(reinterpret_cast<const float4*>(src) + lane + 32 * t);
+        float4 x = reinterpret_cast<float4*>(v)[lane + 32 * t];
+        x.x += d.x; x.y += d.y; x.z += d.z; x.w += d.w;
+        reinterpret_cast<float4*>(v)[lane + 32 * t] = x;
+    }
+    __syncwarp();
+}
+
+// in place: v[x] = log2(sum_{i<=x} 2^v[i]) + add                (trap_int / my_convolve(prior, .))
+__device__ inline void warp_log2cumsum(float* __restrict__ v, float add, int lane) {
+    float x[16];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        const float4 q = reinterpret_cast<const float4*>(v)[4 * lane + t];
+        x[4 * t] = q.x; x[4 * t + 1] = q.y; x[4 * t + 2] = q.z; x[4 * t + 3] = q.w;
+    }
+    float m = x[0];
+#pragma unroll
+    for (int i = 1; i < 16; ++i) m = fmaxf(m, x[i]);
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += ex2f(x[i] - m);
+    float tot = m + lg2f(s);                                  // this lane's chunk total
+    float run = tot;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const float o = __shfl_up_sync(0xffffffffu, run, d);
+        if (lane >= d) run = log2addexp(o, run);
+    }
+    float r = __shfl_up_sync(0xffffffffu, run, 1);            // exclusive carry
+    if (lane == 0) r = -CUDART_INF_F;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { r = log2addexp(r, x[i]); x[i] = r + add; }
+#pragma unroll
+    for (int t = 0; t < 4; ++t)
+        reinterpret_cast<float4*>(v)[4 * lane + t] = make_float4(x[4 * t], x[4 * t + 1], x[4 * t + 2], x[4 * t + 3]);
+    __syncwarp();
+}
+
+// log2(sum_x 2^v[x]) for all lanes
+__device__ inline float warp_log2sumexp(const float* __restrict__ v, int lane) {
+    float x[16];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        const float4 q = reinterpret_cast<const float4*>(v)[lane + 32 * t];
+        x[4 * t] = q.x; x[4 * t + 1] = q.y; x[4 * t + 2] = q.z; x[4 * t + 3] = q.w;
+    }
+    float m = x[0];
+#pragma unroll
+    for (int i = 1; i < 16; ++i) m = fmaxf(m, x[i]);
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, d));
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += ex2f(x[i] - m);
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+    return m + lg2f(s);
+}
+
+// merge path of the slope sequences of two log-concave vectors: jstar[x] = the b-index
+// of the maximising split of output x (x = i + j).
+__device__ inline void warp_merge_path(const float* __restrict__ a, const float* __restrict__ b,
+                                       uint16_t* __restrict__ jstar, int lane) {
+    const int x0 = 16 * lane;
+    int lo = 0, hi = x0;                                      // x0 <= 496 < L, so i in [0, x0]
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        const float sa = a[mid + 1] - a[mid];                 // gain of taking a's next step
+        const float sb = b[x0 - mid] - b[x0 - mid - 1];       // gain of b's last taken step
+        if (sa >= sb) lo = mid + 1; else hi = mid;
+    }
+    int i = lo, j = x0 - lo;
+    float ai = a[i], bj = b[j];
+#pragma unroll 4
+    for (int t = 0; t < 16; ++t) {
+        jstar[x0 + t] = (uint16_t)j;
+        const float an = (i < L - 1) ? a[i + 1] : -CUDART_INF_F;
+        const float bn = (j < L - 1) ? b[j + 1] : -CUDART_INF_F;
+        // advance along the larger slope (ties and NaNs go to a; the right edge forces b)
+        const bool take_b = (i >= L - 1) || ((bn - bj) > (an - ai) && j < L - 1);
+        if (take_b) { ++j; bj = bn; } else { ++i; ai = an; }
+    }
+    __syncwarp();
+}
+
+// Exact two-pass evaluation of the 32 outputs of one pass over the full range j <= x,
+// written in place over a[x].  Only used when the windowed sum looks inconsistent (inputs
+// that are not log-concave beyond rounding noise); makes no structural assumption.
+static __device__ __noinline__ void warp_logconv_exact_pass(float* __restrict__ a, const float* __restrict__ b,
+                                                            int pass, int lane) {
+    const int x = 32 * pass + lane, xmax = 32 * pass + 31;
+    float mx = -CUDART_INF_F;
+    for (int j = 0; j <= xmax; ++j) mx = fmaxf(mx, a[x - j] + b[j]);      // a[<0] is the -inf guard
+    float s = 0.f;
+    for (int j = 0; j <= xmax; ++j) s += ex2f((a[x - j] - mx) + b[j]);
+    __syncwarp();
+    a[x] = (mx == -CUDART_INF_F) ? mx : mx + lg2f(s) - LOG2_L;
+}
+
+// IN PLACE: a[x] <- log2( sum_{j<=x} 2^(a[x-j] + b[j]) ) - log2 L          (clustering.py:365-370)
+// a, b: distinct shared-memory vectors, each with GUARD -inf floats in front and 4 behind.
+// Passes run from the highest outputs down: output x only needs a[i], i <= x, so the 32
+// finished outputs of a pass can overwrite a[x] once the pass has read everything it needs.
+// Returns the number of 4-term chunks executed per lane (executed-op statistics).
+__device__ inline int warp_logconv(float* __restrict__ a, const float* __restrict__ b,
+                                   uint16_t* __restrict__ jstar, int lane) {
+    warp_merge_path(a, b, jstar, lane);
+    int chunks = 0;
+    int hl = 8, hr = 8;                                       // window half-widths, adapted pass to pass
+#pragma unroll 1
+    for (int pass = L / 32 - 1; pass >= 0; --pass) {
+        const int x0 = 32 * pass;
+        const int x = x0 + lane;
+        const int xmax = x0 + 31;
+        const int js = jstar[x];
+        // j* is non-decreasing inside each 16-output walk of the merge path
+        const int jmin = min((int)jstar[x0], (int)jstar[x0 + 16]);
+        const int jmax = max((int)jstar[x0 + 15], (int)jstar[xmax]);
+        const float mx = a[x - js] + b[js];
+        const float cut = mx - THETA;
+        // grow the common j-range until every lane's edge terms are negligible
+        int jl, jh;
+        for (;;) {
+            jl = max(jmin - hl, 0);
+            jh = min(jmax + hr, xmax);
+            const bool gl = (jl > 0) && ((a[x - jl] + b[jl]) >= cut);
+            const bool gr = (jh < x) && ((a[x - jh] + b[jh]) >= cut);
+            const bool al = __any_sync(0xffffffffu, gl), ar = __any_sync(0xffffffffu, gr);
+            if (!al && !ar) break;
+            if (al) hl *= 2;
+            if (ar) hr *= 2;
+        }
+        jl &= ~3;                                             // 16-byte aligned b loads
+        const int n4 = (jh - jl + 4) >> 2;                    // chunks of 4 covering [jl, jh]
+        chunks += n4;
+        const float* pa = a + (x - jl);                       // a[x - j], j increasing -> address decreasing
+        const float4* pb = reinterpret_cast<const float4*>(b + jl);
+        const float nmx = -mx;
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, s4 = 0.f, s5 = 0.f, s6 = 0.f, s7 = 0.f;
+        // j may run up to 3 past jh (<= xmax + 3): b reads the trailing -inf pad there and
+        // a[x - j] the -inf guard or a smaller, still valid term
+        int c = 0;
+#pragma unroll 1
+        for (; c + 2 <= n4; c += 2) {
+            const float4 bv = pb[c], bw = pb[c + 1];
+            const float a0 = pa[-4 * c], a1 = pa[-4 * c - 1], a2 = pa[-4 * c - 2], a3 = pa[-4 * c - 3];
+            const float a4 = pa[-4 * c - 4], a5 = pa[-4 * c - 5], a6 = pa[-4 * c - 6], a7 = pa[-4 * c - 7];
+            s0 += ex2f((a0 + nmx) + bv.x);
+            s1 += ex2f((a1 + nmx) + bv.y);
+            s2 += ex2f((a2 + nmx) + bv.z);
+            s3 += ex2f((a3 + nmx) + bv.w);
+            s4 += ex2f((a4 + nmx) + bw.x);
+            s5 += ex2f((a5 + nmx) + bw.y);
+            s6 += ex2f((a6 + nmx) + bw.z);
+            s7 += ex2f((a7 + nmx) + bw.w);
+        }
+        if (c < n4) {
+            const float4 bv = pb[c];
+            const float a0 = pa[-4 * c], a1 = pa[-4 * c - 1], a2 = pa[-4 * c - 2], a3 = pa[-4 * c - 3];
+            s0 += ex2f((a0 + nmx) + bv.x);
+            s1 += ex2f((a1 + nmx) + bv.y);
+            s2 += ex2f((a2 + nmx) + bv.z);
+            s3 += ex2f((a3 + nmx) + bv.w);
+        }
+        const float s = ((s0 + s1) + (s2 + s3)) + ((s4 + s5) + (s6 + s7));
+        // the window always contains the maximising term (2^0); a sum outside [~1, 2*terms]
+        // means M_x was not the maximum, i.e. the inputs were not log-concave
+        const bool bad = !(s >= 0.999f && s <= 2048.f);
+        if (__any_sync(0xffffffffu, bad)) {
+            warp_logconv_exact_pass(a, b, pass, lane);
+        } else {
+            __syncwarp();                                     // every lane has finished reading a[x0..xmax]
+            a[x] = mx + lg2f(s) - LOG2_L;
+        }
+        // let the windows shrink again (they are re-grown on demand)
+        hl = max(4, hl - (hl >> 2));
+        hr = max(4, hr - (hr >> 2));
+    }
+    __syncwarp();
+    return chunks;
+}
+
+}  // namespace bamse

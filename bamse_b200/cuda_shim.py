@@ -13,6 +13,7 @@ LIB_PATH = os.path.join(_HERE, "libbamse_cuda.so")
 
 FP32 = 0
 FP64 = 1
+FP32_LOGDOMAIN = 2
 KMAX = 12
 TOPK_MAX = 64
 GRID = 512
@@ -71,6 +72,8 @@ def load_library():
     lib.bamse_merge_topk_dev.argtypes = [c_p, c_p, i32, i32, i32, c_p]
     lib.bamse_kernel_time.restype = i32
     lib.bamse_kernel_time.argtypes = [c_p, i32, ctypes.POINTER(dbl), ctypes.POINTER(i64)]
+    lib.bamse_kernel_stats.restype = i32
+    lib.bamse_kernel_stats.argtypes = [c_p, i32, c_p]
     if lib.bamse_abi_version() != 1:
         raise RuntimeError("libbamse_cuda ABI version mismatch")
     _lib = lib
@@ -81,7 +84,7 @@ EXPORTED_SYMBOLS = [
     "bamse_abi_version", "bamse_create", "bamse_destroy", "bamse_last_error", "bamse_set_stream",
     "bamse_launch_count", "bamse_last_eval_count", "bamse_decode_tree", "bamse_upload_problem",
     "bamse_score_list", "bamse_score_range", "bamse_score_topk", "bamse_enumerate_topk_dev",
-    "bamse_merge_topk_dev", "bamse_kernel_time",
+    "bamse_merge_topk_dev", "bamse_kernel_time", "bamse_kernel_stats",
 ]
 
 
@@ -151,6 +154,12 @@ class Context(object):
         ms, n = ctypes.c_double(), ctypes.c_int64()
         self._check(self._lib.bamse_kernel_time(self._h, 1 if reset else 0, ctypes.byref(ms), ctypes.byref(n)))
         return ms.value, n.value
+
+    def kernel_stats(self, reset=True):
+        """dict of executed-work counters of the fp32 enumeration kernel since the last reset."""
+        out = np.zeros(4, dtype=np.uint64)
+        self._check(self._lib.bamse_kernel_stats(self._h, 1 if reset else 0, _ptr(out)))
+        return dict(mufu_ops=int(out[0]), conv_terms=int(out[1]), convs=int(out[2]), scans=int(out[3]))
 
     # ---------------------------------------------------------------- problem
     def upload_problem(self, err, K_of_c, var_counts, ref_counts):

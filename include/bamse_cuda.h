@@ -46,7 +46,8 @@ extern "C" {
 #define BAMSE_ENOMEM (-5)
 
 #define BAMSE_FP32 0        /* production: fp32 arithmetic, fp64 accumulation over samples */
-#define BAMSE_FP64 1        /* check mode: everything in fp64                             */
+#define BAMSE_FP64 1        /* check mode: everything in fp64, reference operation order  */
+#define BAMSE_FP32_LOGDOMAIN 2 /* the check-mode algorithm in fp32 (no structural assumptions) */
 
 typedef struct bamse_ctx bamse_ctx;
 
@@ -146,6 +147,11 @@ int64_t bamse_last_eval_count(const bamse_ctx* ctx);
  * the summed elapsed milliseconds and the number of launches since the last reset
  * (synchronises the stream).  reset != 0 clears the accumulator after reading. */
 int bamse_kernel_time(bamse_ctx* ctx, int reset, double* out_ms, int64_t* out_launches);
+
+/* Executed-work counters of the fp32 enumeration kernel since the last reset:
+ * out4 = { MUFU (ex2/lg2) thread-level ops, convolution terms exponentiated,
+ *          convolutions, prefix scans }.  For the pipe-utilisation side of the roofline. */
+int bamse_kernel_stats(bamse_ctx* ctx, int reset, uint64_t* out4);
 
 /* Host helper shared with the oracle's definition: index -> parent vector. */
 int bamse_decode_tree(int K, uint64_t tree_index, int8_t* out_parent /* [K] */);

@@ -50,8 +50,10 @@ def test_golden_tree_scores(ctx, shim, golden_scores):
         clust, par, nod = pack_items(K, [(0, case["tree"], case["nodes"])])
         s64 = ctx.score_list(clust, par, nod, shim.FP64)[0, 0]
         s32 = ctx.score_list(clust, par, nod, shim.FP32)[0, 0]
+        s32l = ctx.score_list(clust, par, nod, shim.FP32_LOGDOMAIN)[0, 0]
         assert abs(s64 - case["total"]) <= FP64_RTOL * abs(case["total"]), (case["id"], s64, case["total"])
         assert abs(s32 - case["total"]) <= FP32_RTOL * abs(case["total"]), (case["id"], s32, case["total"])
+        assert abs(s32l - case["total"]) <= FP32_RTOL * abs(case["total"]), (case["id"], s32l, case["total"])
 
 
 def _random_problem(rng, K, M, cov):
