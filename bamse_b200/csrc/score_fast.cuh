@@ -201,15 +201,20 @@ __device__ inline void warp_merge_path(const float* __restrict__ a, const float*
         if (sa >= sb) lo = mid + 1; else hi = mid;
     }
     int i = lo, j = x0 - lo;
-    float ai = a[i], bj = b[j];
-#pragma unroll 4
+    // current and next value on either side (-inf past the right edge: that side cannot advance)
+    float ai = a[i], an = (i < L - 1) ? a[i + 1] : -CUDART_INF_F;
+    float bj = b[j], bn = (j < L - 1) ? b[j + 1] : -CUDART_INF_F;
+    uint32_t packed = 0;                                      // two 16-bit j* per word
+#pragma unroll
     for (int t = 0; t < 16; ++t) {
-        jstar[x0 + t] = (uint16_t)j;
-        const float an = (i < L - 1) ? a[i + 1] : -CUDART_INF_F;
-        const float bn = (j < L - 1) ? b[j + 1] : -CUDART_INF_F;
-        // advance along the larger slope (ties and NaNs go to a; the right edge forces b)
-        const bool take_b = (i >= L - 1) || ((bn - bj) > (an - ai) && j < L - 1);
-        if (take_b) { ++j; bj = bn; } else { ++i; ai = an; }
+        if (t & 1) reinterpret_cast<uint32_t*>(jstar)[(x0 + t) >> 1] = packed | ((uint32_t)j << 16);
+        else packed = (uint32_t)j;
+        // advance along the larger slope (ties and NaNs go to a); one load per step
+        const bool take_b = (bn - bj) > (an - ai);
+        const float* src = take_b ? b : a;
+        const int k = (take_b ? j : i) + 2;                   // index of the new "next" value
+        const float nv = (k < L) ? src[k] : -CUDART_INF_F;
+        if (take_b) { ++j; bj = bn; bn = nv; } else { ++i; ai = an; an = nv; }
     }
     __syncwarp();
 }
@@ -266,34 +271,37 @@ __device__ inline int warp_logconv(float* __restrict__ a, const float* __restric
         chunks += n4;
         const float* pa = a + (x - jl);                       // a[x - j], j increasing -> address decreasing
         const float4* pb = reinterpret_cast<const float4*>(b + jl);
-        const float nmx = -mx;
-        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, s4 = 0.f, s5 = 0.f, s6 = 0.f, s7 = 0.f;
+        const float2 nm2 = make_float2(-mx, -mx);
+        float2 acc0 = make_float2(0.f, 0.f), acc1 = acc0, acc2 = acc0, acc3 = acc0;
         // j may run up to 3 past jh (<= xmax + 3): b reads the trailing -inf pad there and
-        // a[x - j] the -inf guard or a smaller, still valid term
-        int c = 0;
+        // a[x - j] the -inf guard or a smaller, still valid term.  Packed fp32x2 adds
+        // (FADD2) halve the issue slots of the two shifts and the accumulation.
 #pragma unroll 1
-        for (; c + 2 <= n4; c += 2) {
-            const float4 bv = pb[c], bw = pb[c + 1];
-            const float a0 = pa[-4 * c], a1 = pa[-4 * c - 1], a2 = pa[-4 * c - 2], a3 = pa[-4 * c - 3];
-            const float a4 = pa[-4 * c - 4], a5 = pa[-4 * c - 5], a6 = pa[-4 * c - 6], a7 = pa[-4 * c - 7];
-            s0 += ex2f((a0 + nmx) + bv.x);
-            s1 += ex2f((a1 + nmx) + bv.y);
-            s2 += ex2f((a2 + nmx) + bv.z);
-            s3 += ex2f((a3 + nmx) + bv.w);
-            s4 += ex2f((a4 + nmx) + bw.x);
-            s5 += ex2f((a5 + nmx) + bw.y);
-            s6 += ex2f((a6 + nmx) + bw.z);
-            s7 += ex2f((a7 + nmx) + bw.w);
+        for (int c = n4 >> 1; c > 0; --c) {
+            const float4 bv = pb[0], bw = pb[1];
+            pb += 2;
+            float2 t0 = make_float2(pa[0], pa[-1]), t1 = make_float2(pa[-2], pa[-3]);
+            float2 t2 = make_float2(pa[-4], pa[-5]), t3 = make_float2(pa[-6], pa[-7]);
+            pa -= 8;
+            t0 = __fadd2_rn(__fadd2_rn(t0, nm2), make_float2(bv.x, bv.y));
+            t1 = __fadd2_rn(__fadd2_rn(t1, nm2), make_float2(bv.z, bv.w));
+            t2 = __fadd2_rn(__fadd2_rn(t2, nm2), make_float2(bw.x, bw.y));
+            t3 = __fadd2_rn(__fadd2_rn(t3, nm2), make_float2(bw.z, bw.w));
+            acc0 = __fadd2_rn(acc0, make_float2(ex2f(t0.x), ex2f(t0.y)));
+            acc1 = __fadd2_rn(acc1, make_float2(ex2f(t1.x), ex2f(t1.y)));
+            acc2 = __fadd2_rn(acc2, make_float2(ex2f(t2.x), ex2f(t2.y)));
+            acc3 = __fadd2_rn(acc3, make_float2(ex2f(t3.x), ex2f(t3.y)));
         }
-        if (c < n4) {
-            const float4 bv = pb[c];
-            const float a0 = pa[-4 * c], a1 = pa[-4 * c - 1], a2 = pa[-4 * c - 2], a3 = pa[-4 * c - 3];
-            s0 += ex2f((a0 + nmx) + bv.x);
-            s1 += ex2f((a1 + nmx) + bv.y);
-            s2 += ex2f((a2 + nmx) + bv.z);
-            s3 += ex2f((a3 + nmx) + bv.w);
+        if (n4 & 1) {
+            const float4 bv = pb[0];
+            float2 t0 = make_float2(pa[0], pa[-1]), t1 = make_float2(pa[-2], pa[-3]);
+            t0 = __fadd2_rn(__fadd2_rn(t0, nm2), make_float2(bv.x, bv.y));
+            t1 = __fadd2_rn(__fadd2_rn(t1, nm2), make_float2(bv.z, bv.w));
+            acc0 = __fadd2_rn(acc0, make_float2(ex2f(t0.x), ex2f(t0.y)));
+            acc1 = __fadd2_rn(acc1, make_float2(ex2f(t1.x), ex2f(t1.y)));
         }
-        const float s = ((s0 + s1) + (s2 + s3)) + ((s4 + s5) + (s6 + s7));
+        acc0 = __fadd2_rn(__fadd2_rn(acc0, acc1), __fadd2_rn(acc2, acc3));
+        const float s = acc0.x + acc0.y;
         // the window always contains the maximising term (2^0); a sum outside [~1, 2*terms]
         // means M_x was not the maximum, i.e. the inputs were not log-concave
         const bool bad = !(s >= 0.999f && s <= 2048.f);
