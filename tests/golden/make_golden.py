@@ -221,8 +221,34 @@ def gen_search():
     dump("search.json", out)
 
 
+def gen_outputs():
+    """dot / text files written by the reference's own tree_io on a fixed tree dict.
+    asciitree is absent here, so its LeftAligned drawer is supplied by our restatement
+    (bamse_b200.tree_io.LeftAligned): everything except that drawer is pinned."""
+    sys.path.insert(0, ROOT)
+    from bamse_b200.tree_io import LeftAligned
+    ref.tree_io.LeftAligned = LeftAligned
+    rng = np.random.default_rng(3)
+    tree = [2, 2, -1, 0, 0, 1]
+    K, M = 6, 3
+    B = tt.get_matrix(tree)[0]
+    s = rng.dirichlet(np.ones(K + 1), size=M)[:, :K].T
+    s[3, :] = 0.0                      # an absent subclone (exercises the <0.04 pruning of the tiling)
+    spec = dict(tree=tree, root=2, assign=[int(x) for x in rng.integers(0, K, 40)], vaf=B.dot(s).tolist(),
+                clone_proportions=s.tolist(), totalscore=-1234.5678901234567, sample_names=["S1", "S2", "tumorB"],
+                sample_colors=["red", "firebrick4", "brown4", "darkgoldenrod4"],
+                cluster_colors=["plum", "lightyellow", "palegreen", "pink", "paleturquoise", "tan", "moccasin"])
+    t = dict(tree=np.array(spec["tree"]), root=spec["root"], assign=np.array(spec["assign"]), vaf=np.array(spec["vaf"]),
+             clone_proportions=np.array(spec["clone_proportions"]), totalscore=spec["totalscore"],
+             sample_names=spec["sample_names"])
+    ref.tree_io.write_dot_files(t, spec["sample_colors"], spec["cluster_colors"],
+                                os.path.join(HERE, "out_subclones.dot"), os.path.join(HERE, "out_samples.dot"))
+    ref.tree_io.write_text_output([t, t], os.path.join(HERE, "out_text.txt"))
+    dump("out_spec.json", spec)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["scores", "vectors", "canon", "constants", "search"]
+    which = sys.argv[1:] or ["scores", "vectors", "canon", "constants", "search", "outputs"]
     t0 = time.time()
     if "scores" in which:
         gen_scores()
@@ -234,4 +260,6 @@ if __name__ == "__main__":
         gen_constants()
     if "search" in which:
         gen_search()
+    if "outputs" in which:
+        gen_outputs()
     print("done in %.1fs" % (time.time() - t0))

@@ -1,0 +1,177 @@
+"""CPU-only tests of the host side: the C ABI loads and exports what include/*.h declares,
+argument/error behaviour without a GPU, tree utilities and clustering constants against the
+reference-generated golden vectors, writers, CLI parsing."""
+import ctypes
+import math
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, ROOT, has_cuda
+
+from bamse_b200 import cuda_shim, tree_tools
+from bamse_b200 import clustering as C
+
+
+def header_functions():
+    text = open(os.path.join(ROOT, "include", "bamse_cuda.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(bamse_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = cuda_shim.load_library()
+    declared = header_functions()
+    assert len(declared) >= 14
+    for name in declared:
+        assert hasattr(lib, name), "libbamse_cuda.so does not export %s" % name
+    assert sorted(cuda_shim.EXPORTED_SYMBOLS) == declared
+    assert lib.bamse_abi_version() == 1
+
+
+def test_record_layout_matches_header():
+    assert cuda_shim.RECORD_DTYPE.itemsize == 32
+    assert [cuda_shim.RECORD_DTYPE.fields[n][1] for n in ("total", "score", "clust", "param", "tree")] == [0, 8, 16, 20, 24]
+
+
+@pytest.mark.skipif(has_cuda(), reason="checks the no-GPU failure mode")
+def test_no_gpu_fails_loudly_no_cpu_fallback():
+    with pytest.raises(cuda_shim.BamseCudaError) as e:
+        cuda_shim.Context(0)
+    assert e.value.code == -2 and "no CPU fallback" in str(e.value)
+    c = C.clustering(np.ones((4, 2), dtype=int), np.ones((4, 2), dtype=int), [0, 0, 1, 1], C.part_func(4, 2), 0.01)
+    with pytest.raises(cuda_shim.BamseCudaError):
+        c.get_tree_score([-1, 0], [0, 1])
+
+
+def test_host_decoder_is_a_bijection():
+    import bamse_oracle as orc
+    for K in range(1, 7):
+        seen = set()
+        for i in range(K ** (K - 1)):
+            p = cuda_shim.decode_tree(K, i)
+            assert p == orc.decode_tree(K, i)
+            seen.add(tuple(p))
+        assert len(seen) == K ** (K - 1)
+    lib = cuda_shim.load_library()
+    buf = np.zeros(12, dtype=np.int8)
+    assert lib.bamse_decode_tree(3, 9, buf.ctypes.data_as(ctypes.c_void_p)) == -1      # index out of range
+    assert lib.bamse_decode_tree(13, 0, buf.ctypes.data_as(ctypes.c_void_p)) == -1     # K > KMAX
+    assert cuda_shim.decode_tree(12, 12 ** 11 - 1).count(-1) == 1                      # 64-bit indices
+
+
+def test_tree_tools_against_reference_golden(golden_canon):
+    for K, items in golden_canon["alltrees_scre"].items():
+        for it in items:
+            r = tree_tools.canonizeF(it["tree"])
+            assert (r["canstr"], r["scre"]) == (it["canstr"], it["scre"])
+    for it in golden_canon["random"]:
+        r = tree_tools.canonizeF(it["tree"])
+        assert (r["canstr"], r["scre"]) == (it["canstr"], it["scre"])
+    for K in range(1, 11):
+        mine = sorted(tree_tools.canonizeF(t)["canstr"] for t in tree_tools.unlabeled_rooted_trees(K))
+        assert mine == golden_canon["alltrees_canstr"][str(K)]
+
+
+def test_tree_tools_small_known_answers():
+    B, anc = tree_tools.get_matrix([-1, 0, 0, 1])
+    np.testing.assert_array_equal(B, [[1, 1, 1, 1], [0, 1, 0, 1], [0, 0, 1, 0], [0, 0, 0, 1]])
+    assert anc[3] == [3, 1, 0]
+    assert tree_tools.get_childs([2, 2, -1, 0, 0], 2) == [0, 1]
+    assert tree_tools.get_tree_depth([2, 2, -1, 0, 0]) == [2, 2, 1, 3, 3]
+    assert tree_tools.reorder_tree([-1, 0, 1], [5, 3, 4], [3, 4, 5]) == [2, 0, -1]
+    assert list(tree_tools.reorder_assignmens([2, 2, 0, 1, 0])) == [0, 0, 1, 2, 1]
+    assert list(tree_tools.collapse_node(np.array([-1, 0, 1, 2]), 1)) == [-1, 0, 1]
+    assert list(tree_tools.collapse_assign([0, 1, 2, 3, 1], 1, 2)) == [0, 1, 1, 2, 1]
+
+
+def test_remove_zeros_collapses_empty_single_child_nodes():
+    t = {'tree': np.array([-1, 0, 1, 1]), 'assign': np.array([0, 1, 2, 3, 1]),
+         'clone_proportions': np.array([[0.3, 0.2], [0.0, 0.0004], [0.4, 0.1], [0.1, 0.2]])}
+    out = tree_tools.remove_zeros(t)      # node 1 is empty but has two children: kept
+    assert list(out['tree']) == [-1, 0, 1, 1]
+    t = {'tree': np.array([-1, 0, 1, 2]), 'assign': np.array([0, 1, 2, 3, 1]),
+         'clone_proportions': np.array([[0.3, 0.2], [0.0, 0.0004], [0.4, 0.1], [0.1, 0.2]])}
+    out = tree_tools.remove_zeros(t)
+    assert list(out['tree']) == [-1, 0, 1]
+    assert list(out['assign']) == [0, 1, 1, 2, 1]
+    assert out['clone_proportions'].shape == (3, 2) and out['Bmatrix'].shape == (3, 3)
+
+
+def test_clustering_constants_against_reference_golden(golden_constants):
+    for p in golden_constants["part_func"]:
+        np.testing.assert_array_equal(C.part_func(p["n"], p["kmax"]), p["pf"])
+    for p in golden_constants["penalty"]:
+        assert C.log_conf_penalty(np.array(p["assign"]), C.part_func(p["n"], p["kmax"])) == pytest.approx(p["value"], rel=1e-14)
+    for c in golden_constants["clustering"]:
+        o = C.clustering(c["am"], c["bm"], c["assign"], np.array(c["pf"]), c["err"])
+        np.testing.assert_array_equal(o.As, c["As"])
+        np.testing.assert_array_equal(o.Bs, c["Bs"])
+        assert o.maxlikelihood == pytest.approx(c["maxlikelihood"], rel=1e-13)
+        assert o.cluster_prior == pytest.approx(c["cluster_prior"], rel=1e-13)
+    assert list(C.tree_numbers[:10]) == [1, 1, 1, 2, 4, 9, 20, 47, 108, 252]
+
+
+def test_writers_are_byte_compatible_with_the_reference():
+    """tests/golden/out_* were written by the reference's own tree_io functions."""
+    import json
+    from bamse_b200 import tree_io
+    spec = json.load(open(os.path.join(GOLDEN, "out_spec.json")))
+    tree = dict(tree=np.array(spec["tree"]), root=spec["root"], assign=np.array(spec["assign"]),
+                vaf=np.array(spec["vaf"]), clone_proportions=np.array(spec["clone_proportions"]),
+                totalscore=spec["totalscore"], sample_names=spec["sample_names"])
+    import tempfile
+    with tempfile.TemporaryDirectory() as d:
+        a, b, c = (os.path.join(d, n) for n in ("t.dot", "s.dot", "o.txt"))
+        tree_io.write_dot_files(tree, spec["sample_colors"], spec["cluster_colors"], a, b)
+        tree_io.write_text_output([tree, tree], c)
+        assert open(a).read() == open(os.path.join(GOLDEN, "out_subclones.dot")).read()
+        assert open(b).read() == open(os.path.join(GOLDEN, "out_samples.dot")).read()
+        assert open(c).read() == open(os.path.join(GOLDEN, "out_text.txt")).read()
+
+
+def test_ascii_tree_shape():
+    from bamse_b200.tree_io import get_ascii_tree
+    assert get_ascii_tree([-1, 0, 1, 0], ["A", "B", "C", "D"]) == "A\n +-- B\n |   +-- C\n +-- D"
+
+
+def test_cli_keeps_the_reference_options():
+    from bamse_b200.cli import build_parser
+    a = build_parser().parse_args(["x.dat"])
+    assert (a.e, a.nc, a.s, a.n, a.t, a.infile) == (0.001, 12, -1, 3, 1, ["x.dat"])
+    a = build_parser().parse_args(["-e", "0.01", "-nc", "5", "-s", "0.2", "-n", "10", "-t", "5", "a", "b"])
+    assert (a.e, a.nc, a.s, a.n, a.t, a.infile[0]) == (0.01, 5, 0.2, 10, 5, "a")
+
+
+def test_input_reader_matches_bamse_dat_layout(tmp_path):
+    from bamse_b200.cli import read_input
+    from bamse_b200 import simdata
+    d = simdata.simulate(3, 2, 20, seed=1)
+    p = tmp_path / "in.dat"
+    simdata.write_input_file(str(p), d["As"], d["Bs"])
+    As, Bs, names = read_input(str(p))
+    assert names == ["S1", "S2"]
+    np.testing.assert_array_equal(As, d["As"])
+    np.testing.assert_array_equal(Bs, d["Bs"])
+
+
+def test_simdata_shapes_and_seed():
+    from bamse_b200 import simdata
+    a = simdata.simulate(4, 3, 50, seed=12345)
+    b = simdata.simulate(4, 3, 50, seed=12345)
+    assert a["As"].shape == (50, 3) and (a["As"] + a["Bs"] == 200).all()
+    np.testing.assert_array_equal(a["As"], b["As"])
+    assert sorted(set(a["assign"])) == [0, 1, 2, 3] and np.bincount(a["assign"]).min() >= 2
+
+
+def test_fraction_solver_recovers_planted_fractions():
+    from bamse_b200.fractions import solve4
+    B = tree_tools.get_matrix([-1, 0, 0])[0]
+    x_true = np.array([[0.2, 0.5], [0.3, 0.1], [0.4, 0.3]])
+    prev = B.dot(x_true)
+    cov, er = 200000, 0.001
+    As = np.rint(cov * (er + prev * (0.5 - er))).astype(int)
+    res = solve4(B, As, cov - As, er, [np.ones(3)] * 2)
+    np.testing.assert_allclose(res['s'], x_true, atol=2e-3)
