@@ -204,3 +204,21 @@ def test_config1_pipeline_fp32_equals_check_mode(ctx, shim):
     c = w64["clusts"][t64[0]["clustering_index"]]
     thr = c.get_tree_score(c.candidate, list(range(c.As.shape[0]))) + math.log(orc.canon_weight(c.candidate)[1])
     assert t64[0]["score"] >= thr - 1e-9 * abs(thr)
+
+
+def test_cli_end_to_end(tmp_path, monkeypatch, ctx):
+    """bamse.py -e .. -nc .. -n .. -t .. inputfile -> the reference's four kinds of output files."""
+    import bamse_b200.clustering as C
+    from bamse_b200 import cli, simdata
+    d = simdata.simulate(3, 2, 30, seed=21)
+    inp = tmp_path / "in.dat"
+    simdata.write_input_file(str(inp), d["As"], d["Bs"])
+    monkeypatch.chdir(tmp_path)
+    monkeypatch.setattr(C, "_default_ctx", ctx)
+    assert cli.main(["-e", "0.003", "-nc", "4", "-n", "3", "-t", "2", "--seed", "5", str(inp)]) == 0
+    txt = (tmp_path / "bamse_output.txt").read_text()
+    assert txt.startswith("Solution Number 1\ntree = [") and "logscore = " in txt
+    assert "Mutations Subclone Membership = ['" in txt
+    for name in ("tree_number_0_subclones.dot", "tree_number_0_samples.dot", "tree_number_0.txt"):
+        assert (tmp_path / name).read_text()
+    assert (tmp_path / "tree_number_0_subclones.dot").read_text().startswith("digraph {\nSubcloneA [")
