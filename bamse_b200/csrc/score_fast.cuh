@@ -233,6 +233,39 @@ static __device__ __noinline__ void warp_logconv_exact_pass(float* __restrict__ 
     a[x] = (mx == -CUDART_INF_F) ? mx : mx + lg2f(s) - LOG2_L;
 }
 
+// acc += sum over n4 chunks of 4 consecutive j (starting at the 4-aligned j0) of
+// 2^((a[x-j] - mx) + b[j]); pa = &a[x - j0], pb = &b[j0].  b is a broadcast 128-bit load, a a
+// conflict-free scalar load per term; the two shifts and the accumulation are packed fp32x2
+// adds (FADD2), the exponentials MUFU.EX2.
+__device__ __forceinline__ void conv_accumulate(const float* __restrict__ pa, const float4* __restrict__ pb, int n4,
+                                                const float2 nm2, float2& acc0, float2& acc1, float2& acc2,
+                                                float2& acc3) {
+#pragma unroll 1
+    for (int c = n4 >> 1; c > 0; --c) {
+        const float4 bv = pb[0], bw = pb[1];
+        pb += 2;
+        float2 t0 = make_float2(pa[0], pa[-1]), t1 = make_float2(pa[-2], pa[-3]);
+        float2 t2 = make_float2(pa[-4], pa[-5]), t3 = make_float2(pa[-6], pa[-7]);
+        pa -= 8;
+        t0 = __fadd2_rn(__fadd2_rn(t0, nm2), make_float2(bv.x, bv.y));
+        t1 = __fadd2_rn(__fadd2_rn(t1, nm2), make_float2(bv.z, bv.w));
+        t2 = __fadd2_rn(__fadd2_rn(t2, nm2), make_float2(bw.x, bw.y));
+        t3 = __fadd2_rn(__fadd2_rn(t3, nm2), make_float2(bw.z, bw.w));
+        acc0 = __fadd2_rn(acc0, make_float2(ex2f(t0.x), ex2f(t0.y)));
+        acc1 = __fadd2_rn(acc1, make_float2(ex2f(t1.x), ex2f(t1.y)));
+        acc2 = __fadd2_rn(acc2, make_float2(ex2f(t2.x), ex2f(t2.y)));
+        acc3 = __fadd2_rn(acc3, make_float2(ex2f(t3.x), ex2f(t3.y)));
+    }
+    if (n4 & 1) {
+        const float4 bv = pb[0];
+        float2 t0 = make_float2(pa[0], pa[-1]), t1 = make_float2(pa[-2], pa[-3]);
+        t0 = __fadd2_rn(__fadd2_rn(t0, nm2), make_float2(bv.x, bv.y));
+        t1 = __fadd2_rn(__fadd2_rn(t1, nm2), make_float2(bv.z, bv.w));
+        acc0 = __fadd2_rn(acc0, make_float2(ex2f(t0.x), ex2f(t0.y)));
+        acc1 = __fadd2_rn(acc1, make_float2(ex2f(t1.x), ex2f(t1.y)));
+    }
+}
+
 // IN PLACE: a[x] <- log2( sum_{j<=x} 2^(a[x-j] + b[j]) ) - log2 L          (clustering.py:365-370)
 // a, b: distinct shared-memory vectors, each with GUARD -inf floats in front and 4 behind.
 // Passes run from the highest outputs down: output x only needs a[i], i <= x, so the 32
@@ -253,58 +286,43 @@ __device__ inline int warp_logconv(float* __restrict__ a, const float* __restric
         const int jmin = min((int)jstar[x0], (int)jstar[x0 + 16]);
         const int jmax = max((int)jstar[x0 + 15], (int)jstar[xmax]);
         const float mx = a[x - js] + b[js];
-        const float cut = mx - THETA;
-        // grow the common j-range until every lane's edge terms are negligible
-        int jl, jh;
-        for (;;) {
-            jl = max(jmin - hl, 0);
-            jh = min(jmax + hr, xmax);
-            const bool gl = (jl > 0) && ((a[x - jl] + b[jl]) >= cut);
-            const bool gr = (jh < x) && ((a[x - jh] + b[jh]) >= cut);
-            const bool al = __any_sync(0xffffffffu, gl), ar = __any_sync(0xffffffffu, gr);
-            if (!al && !ar) break;
-            if (al) hl *= 2;
-            if (ar) hr *= 2;
-        }
-        jl &= ~3;                                             // 16-byte aligned b loads
-        const int n4 = (jh - jl + 4) >> 2;                    // chunks of 4 covering [jl, jh]
-        chunks += n4;
-        const float* pa = a + (x - jl);                       // a[x - j], j increasing -> address decreasing
-        const float4* pb = reinterpret_cast<const float4*>(b + jl);
         const float2 nm2 = make_float2(-mx, -mx);
         float2 acc0 = make_float2(0.f, 0.f), acc1 = acc0, acc2 = acc0, acc3 = acc0;
-        // j may run up to 3 past jh (<= xmax + 3): b reads the trailing -inf pad there and
-        // a[x - j] the -inf guard or a smaller, still valid term.  Packed fp32x2 adds
-        // (FADD2) halve the issue slots of the two shifts and the accumulation.
-#pragma unroll 1
-        for (int c = n4 >> 1; c > 0; --c) {
-            const float4 bv = pb[0], bw = pb[1];
-            pb += 2;
-            float2 t0 = make_float2(pa[0], pa[-1]), t1 = make_float2(pa[-2], pa[-3]);
-            float2 t2 = make_float2(pa[-4], pa[-5]), t3 = make_float2(pa[-6], pa[-7]);
-            pa -= 8;
-            t0 = __fadd2_rn(__fadd2_rn(t0, nm2), make_float2(bv.x, bv.y));
-            t1 = __fadd2_rn(__fadd2_rn(t1, nm2), make_float2(bv.z, bv.w));
-            t2 = __fadd2_rn(__fadd2_rn(t2, nm2), make_float2(bw.x, bw.y));
-            t3 = __fadd2_rn(__fadd2_rn(t3, nm2), make_float2(bw.z, bw.w));
-            acc0 = __fadd2_rn(acc0, make_float2(ex2f(t0.x), ex2f(t0.y)));
-            acc1 = __fadd2_rn(acc1, make_float2(ex2f(t1.x), ex2f(t1.y)));
-            acc2 = __fadd2_rn(acc2, make_float2(ex2f(t2.x), ex2f(t2.y)));
-            acc3 = __fadd2_rn(acc3, make_float2(ex2f(t3.x), ex2f(t3.y)));
+        // first guess of the common j-range [jl, je] (4-aligned start, whole chunks); j may run
+        // up to 3 past xmax: b reads its trailing -inf pad there, a[x - j] its -inf guard
+        int jl = max(jmin - hl, 0) & ~3;
+        int n4 = (min(jmax + hr, xmax) - jl + 4) >> 2;
+        int je = jl + 4 * n4 - 1;
+        chunks += n4;
+        conv_accumulate(a + (x - jl), reinterpret_cast<const float4*>(b + jl), n4, nm2, acc0, acc1, acc2, acc3);
+        // the terms of one output are concave in j: if the edge terms of every lane are below
+        // 2^-THETA of its maximum, everything outside the range is too.  Otherwise extend.
+        for (;;) {
+            const bool need = (jl > 0) && (((a[x - jl] - mx) + b[jl]) >= -THETA);
+            if (!__any_sync(0xffffffffu, need)) break;
+            const int j2 = max(jl - max(hl, 8), 0) & ~3;
+            const int m4 = (jl - j2) >> 2;
+            chunks += m4;
+            conv_accumulate(a + (x - j2), reinterpret_cast<const float4*>(b + j2), m4, nm2, acc0, acc1, acc2, acc3);
+            hl += jl - j2;
+            jl = j2;
         }
-        if (n4 & 1) {
-            const float4 bv = pb[0];
-            float2 t0 = make_float2(pa[0], pa[-1]), t1 = make_float2(pa[-2], pa[-3]);
-            t0 = __fadd2_rn(__fadd2_rn(t0, nm2), make_float2(bv.x, bv.y));
-            t1 = __fadd2_rn(__fadd2_rn(t1, nm2), make_float2(bv.z, bv.w));
-            acc0 = __fadd2_rn(acc0, make_float2(ex2f(t0.x), ex2f(t0.y)));
-            acc1 = __fadd2_rn(acc1, make_float2(ex2f(t1.x), ex2f(t1.y)));
+        for (;;) {
+            // lanes with x <= je read the -inf guard here, so they never ask for more
+            const bool need = ((a[x - je] - mx) + b[je]) >= -THETA;
+            if (!__any_sync(0xffffffffu, need) || je >= xmax) break;
+            const int m4 = min((max(hr, 8) + 3) >> 2, ((xmax | 3) - je) >> 2);
+            chunks += m4;
+            conv_accumulate(a + (x - je - 1), reinterpret_cast<const float4*>(b + je + 1), m4, nm2, acc0, acc1, acc2, acc3);
+            hr += 4 * m4;
+            je += 4 * m4;
         }
         acc0 = __fadd2_rn(__fadd2_rn(acc0, acc1), __fadd2_rn(acc2, acc3));
         const float s = acc0.x + acc0.y;
-        // the window always contains the maximising term (2^0); a sum outside [~1, 2*terms]
-        // means M_x was not the maximum, i.e. the inputs were not log-concave
-        const bool bad = !(s >= 0.999f && s <= 2048.f);
+        // the range always contains the maximising term (2^0 up to the rounding of the shift,
+        // which is relative to |mx|); a sum far outside [1, 2*terms] means M_x was not the
+        // maximum, i.e. the inputs were not log-concave
+        const bool bad = !(s >= 0.7f && s <= 2048.f);
         if (__any_sync(0xffffffffu, bad)) {
             warp_logconv_exact_pass(a, b, pass, lane);
         } else {
