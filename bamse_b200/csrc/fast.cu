@@ -46,6 +46,14 @@ struct alignas(16) WarpSmem {
 };
 // dynamic shared memory: FAST_WARPS x WarpSmem, then FAST_WARPS x topk bamse_records
 
+// Keeps the warp's shared-memory base in a register: without the opaque move ptxas
+// rematerialises it from S2R tid / cta-id several times per convolution pass.
+__device__ __forceinline__ WarpSmem* pin_shared(WarpSmem* p) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(p);
+    asm volatile("" : "+r"(s));
+    return reinterpret_cast<WarpSmem*>(__cvta_shared_to_generic(s));
+}
+
 __device__ inline void warp_init_guards(WarpSmem* ws, int lane) {
     for (int s = 0; s < FAST_SLOTS; ++s) {
         for (int i = lane; i < GUARD; i += 32) ws->vec[s][i] = -CUDART_INF_F;
@@ -103,8 +111,10 @@ __global__ void __launch_bounds__(FAST_THREADS, 7) k_enumerate_fast(ProblemView 
     bamse_record* s_top_all = reinterpret_cast<bamse_record*>(smem_raw + sizeof(WarpSmem) * FAST_WARPS);
     __shared__ unsigned long long s_chunk;
     __shared__ int s_next;
-    const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
-    WarpSmem* ws = wsm + wid;
+    const int t = threadIdx.x, wid = t >> 5;
+    int lane = t & 31;
+    asm volatile("" : "+r"(lane));
+    WarpSmem* ws = pin_shared(wsm + wid);
     const int kcap = w.topk > 0 ? w.topk : 1;
     warp_init_guards(ws, lane);
     if (lane == 0) ws->ntop = 0;
@@ -221,8 +231,9 @@ __global__ void __launch_bounds__(FAST_THREADS) k_score_items_fast(ProblemView p
                                                                    const ScoreItem* __restrict__ items, int64_t n,
                                                                    double* __restrict__ out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    WarpSmem* ws = reinterpret_cast<WarpSmem*>(smem_raw) + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
+    WarpSmem* ws = pin_shared(reinterpret_cast<WarpSmem*>(smem_raw) + (threadIdx.x >> 5));
+    int lane = threadIdx.x & 31;
+    asm volatile("" : "+r"(lane));
     const int64_t idx = (int64_t)blockIdx.x * FAST_WARPS + (threadIdx.x >> 5);
     if (idx >= n) return;
     warp_init_guards(ws, lane);
