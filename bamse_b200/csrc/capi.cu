@@ -335,16 +335,24 @@ static int enumerate_dev(bamse_ctx* ctx, const double* d_const, const double* d_
     if (precision == BAMSE_FP32) ctx->grid[pi] = enumerate_fast_grid_size(ctx->device, topk);
     else if (ctx->grid[pi] == 0) ctx->grid[pi] = enumerate_grid_size(precision, ctx->device);
     const int grid = ctx->grid[pi];
-    const int chunk = precision == BAMSE_FP32 ? 32 : 8;
+    // work granularity: ~32 chunks per worker (warp for fp32, CTA for the check mode), 1..16 trees
+    const int workers = enumerate_workers(precision, grid);
+    uint64_t trees_upper = 0;
+    if (host_seg) trees_upper = host_seg->n_trees;
+    else {
+        for (int c = 0; c < C; ++c) trees_upper += ipow_u64(ctx->K_of_c[c], ctx->K_of_c[c] - 1);
+        trees_upper *= (uint64_t)P;
+    }
+    const int chunk = (int)std::min<uint64_t>(16, std::max<uint64_t>(1, trees_upper / ((uint64_t)workers * 32)));
+    const uint64_t chunks_upper = trees_upper / chunk + (uint64_t)P * C + 1;
+    const uint64_t cand_lists = std::min<uint64_t>((uint64_t)workers * P, chunks_upper + workers);
+    const uint64_t cand_cap = cand_lists * (uint64_t)(topk > 0 ? topk : 0);
     BAMSE_CUDA_TRY(ctx, ctx->d_segs.ensure(sizeof(Segment) * P * C));
     const bool fresh_scalars = ctx->d_scalars.p == nullptr;
     BAMSE_CUDA_TRY(ctx, ctx->d_scalars.ensure(sizeof(uint64_t) * 8));
     uint64_t* scal = ctx->d_scalars.as<uint64_t>();
     BAMSE_CUDA_TRY(ctx, cudaMemsetAsync(scal, 0, sizeof(uint64_t) * (fresh_scalars ? 8 : 4), s));   // stats [4..8) accumulate until read
-    if (topk > 0) {
-        BAMSE_CUDA_TRY(ctx, ctx->d_cand.ensure(sizeof(bamse_record) * (size_t)P * grid * topk));
-        BAMSE_CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_cand.p, 0xFF, sizeof(bamse_record) * (size_t)P * grid * topk, s));
-    }
+    if (topk > 0) BAMSE_CUDA_TRY(ctx, ctx->d_cand.ensure(sizeof(bamse_record) * (size_t)cand_cap));
     EnumWork w;
     if (host_seg) {
         const Segment seg = *host_seg;
@@ -366,6 +374,8 @@ static int enumerate_dev(bamse_ctx* ctx, const double* d_const, const double* d_
     w.next_chunk = reinterpret_cast<unsigned long long*>(scal + 2);
     w.topk = topk;
     w.cand = ctx->d_cand.as<bamse_record>();
+    w.cand_count = reinterpret_cast<unsigned long long*>(scal + 3);
+    w.cand_cap = cand_cap;
     w.dense_score = d_dense_score;
     w.dense_logscre = d_dense_logscre;
     w.stats = reinterpret_cast<unsigned long long*>(scal + 4);
@@ -383,7 +393,8 @@ static int enumerate_dev(bamse_ctx* ctx, const double* d_const, const double* d_
     ctx->launches++;
     BAMSE_CUDA_TRY(ctx, cudaGetLastError());
     if (topk > 0 && d_out) {
-        launch_merge_topk(ctx->d_cand.as<bamse_record>(), grid, 1, grid, P, topk, d_out, s);
+        launch_merge_topk(ctx->d_cand.as<bamse_record>(), reinterpret_cast<unsigned long long*>(scal + 3), 0, P, topk,
+                          d_out, s);
         ctx->launches++;
         BAMSE_CUDA_TRY(ctx, cudaGetLastError());
     }
@@ -440,7 +451,7 @@ int bamse_merge_topk_dev(bamse_ctx* ctx, const bamse_record* d_lists, int n_list
     CTX_CHECK(ctx);
     if (!d_lists || !d_out_records || n_lists < 1 || P < 1 || topk < 1 || topk > BAMSE_TOPK_MAX)
         return ctx->fail(BAMSE_EINVAL, "bamse_merge_topk_dev: bad arguments");
-    launch_merge_topk(d_lists, n_lists, P, 1, P, topk, d_out_records, ctx->stream);
+    launch_merge_topk(d_lists, nullptr, (unsigned long long)n_lists * P * topk, P, topk, d_out_records, ctx->stream);
     ctx->launches++;
     BAMSE_CUDA_TRY(ctx, cudaGetLastError());
     return BAMSE_OK;

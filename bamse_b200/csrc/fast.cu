@@ -42,7 +42,6 @@ struct alignas(16) WarpSmem {
     float vec[FAST_SLOTS][VSTRIDE];
     uint16_t jstar[L];
     TreeProgram prog;
-    int ntop;
 };
 // dynamic shared memory: FAST_WARPS x WarpSmem, then FAST_WARPS x topk bamse_records
 
@@ -102,52 +101,40 @@ __device__ __forceinline__ bool rec_better_f(const bamse_record& a, const bamse_
 }
 
 // ---------------------------------------------------------------------- enumerate (fp32)
-// Persistent CTAs pull chunks of consecutive tree indices from a global counter; inside a
-// chunk every warp pulls its next tree from a shared-memory counter, so a warp that drew
-// cheap trees (few leaves) simply scores more of them.
+// Persistent warps: every warp pulls small chunks of consecutive tree indices from one global
+// counter and scores them on its own -- no block-level barrier anywhere, so a warp that drew
+// cheap trees (few leaves) simply pulls more, and the tail of the launch is one tree long.
+// Each warp keeps a private top-k list in shared memory and appends it to a flat global bag
+// when its parameter set changes and at the end; k_merge_topk reduces the bag.
 __global__ void __launch_bounds__(FAST_THREADS, 7) k_enumerate_fast(ProblemView pv, FastTables ft, EnumWork w) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     WarpSmem* wsm = reinterpret_cast<WarpSmem*>(smem_raw);
     bamse_record* s_top_all = reinterpret_cast<bamse_record*>(smem_raw + sizeof(WarpSmem) * FAST_WARPS);
-    __shared__ unsigned long long s_chunk;
-    __shared__ int s_next;
     const int t = threadIdx.x, wid = t >> 5;
     int lane = t & 31;
     asm volatile("" : "+r"(lane));
     WarpSmem* ws = pin_shared(wsm + wid);
     const int kcap = w.topk > 0 ? w.topk : 1;
+    bamse_record* list = s_top_all + wid * kcap;
     warp_init_guards(ws, lane);
-    if (lane == 0) ws->ntop = 0;
+    int ntop = 0;                                    // meaningful in lane 0
     int cur_p = -1;
     const uint64_t total = *w.total_chunks;
     unsigned st_chunks = 0, st_convs = 0, st_scans = 0, st_samples = 0;
 
-    auto flush = [&](int p) {
-        // merge the FAST_WARPS per-warp lists into cand[p][blockIdx.x][0..topk)
-        __syncthreads();
-        if (t == 0) {
-            bamse_record* dst = w.cand + ((size_t)p * gridDim.x + blockIdx.x) * w.topk;
-            int pos[FAST_WARPS];
-            for (int i = 0; i < FAST_WARPS; ++i) pos[i] = 0;
-            for (int r = 0; r < w.topk; ++r) {
-                int best = -1;
-                for (int i = 0; i < FAST_WARPS; ++i)
-                    if (pos[i] < wsm[i].ntop &&
-                        (best < 0 || rec_better_f(s_top_all[i * kcap + pos[i]], s_top_all[best * kcap + pos[best]])))
-                        best = i;
-                if (best < 0) break;
-                dst[r] = s_top_all[best * kcap + pos[best]++];
-            }
-            for (int i = 0; i < FAST_WARPS; ++i) wsm[i].ntop = 0;
+    auto flush = [&]() {
+        if (lane == 0 && ntop > 0) {
+            const unsigned long long pos = atomicAdd(w.cand_count, (unsigned long long)ntop);
+            if (pos + ntop <= w.cand_cap)
+                for (int i = 0; i < ntop; ++i) w.cand[pos + i] = list[i];
+            ntop = 0;
         }
-        __syncthreads();
     };
 
     for (;;) {
-        __syncthreads();
-        if (t == 0) { s_chunk = atomicAdd(w.next_chunk, 1ull); s_next = 0; }
-        __syncthreads();
-        const uint64_t chunk = s_chunk;
+        unsigned long long chunk = 0;
+        if (lane == 0) chunk = atomicAdd(w.next_chunk, 1ull);
+        chunk = __shfl_sync(0xffffffffu, chunk, 0);
         if (chunk >= total) break;
         int lo = 0, hi = w.n_segs - 1;
         while (lo < hi) {
@@ -155,18 +142,11 @@ __global__ void __launch_bounds__(FAST_THREADS, 7) k_enumerate_fast(ProblemView 
             if (w.segs[mid].first_chunk <= chunk) lo = mid; else hi = mid - 1;
         }
         const Segment seg = w.segs[lo];
-        if (seg.p != cur_p) {
-            if (cur_p >= 0) flush(cur_p);
-            cur_p = seg.p;
-        }
+        if (seg.p != cur_p) { flush(); cur_p = seg.p; }
         const uint64_t off = (chunk - seg.first_chunk) * (uint64_t)w.chunk;
         const uint64_t remain = seg.n_trees - off;
         const int n = remain < (uint64_t)w.chunk ? (int)remain : w.chunk;
-        for (;;) {
-            int i = 0;
-            if (lane == 0) i = atomicAdd(&s_next, 1);
-            i = __shfl_sync(0xffffffffu, i, 0);
-            if (i >= n) break;
+        for (int i = 0; i < n; ++i) {
             const uint64_t tree = seg.tree_begin + off + i;
             if (lane == 0) {
                 int8_t parent[KMAX];
@@ -184,20 +164,18 @@ __global__ void __launch_bounds__(FAST_THREADS, 7) k_enumerate_fast(ProblemView 
                 if (w.topk > 0 && full >= seg.threshold) {
                     bamse_record r;
                     r.total = full + seg.clust_const; r.score = full; r.clust = seg.c; r.param = seg.p; r.tree = tree;
-                    bamse_record* list = s_top_all + wid * kcap;
-                    int cnt = ws->ntop;
-                    if (!(cnt == w.topk && !rec_better_f(r, list[w.topk - 1]))) {
-                        int q = cnt < w.topk ? cnt : w.topk - 1;
+                    if (!(ntop == w.topk && !rec_better_f(r, list[w.topk - 1]))) {
+                        int q = ntop < w.topk ? ntop : w.topk - 1;
                         while (q > 0 && rec_better_f(r, list[q - 1])) { list[q] = list[q - 1]; --q; }
                         list[q] = r;
-                        if (cnt < w.topk) ws->ntop = cnt + 1;
+                        if (ntop < w.topk) ++ntop;
                     }
                 }
             }
             __syncwarp();
         }
     }
-    if (cur_p >= 0) flush(cur_p);
+    flush();
     if (w.stats && lane == 0) {
         // thread-level MUFU ops: 4 ex2 per chunk per lane x 32 lanes, 16 passes x 1 lg2 x 32 per conv,
         // 59 per lane per scan, 17 per lane per final log-sum-exp
@@ -212,6 +190,8 @@ __global__ void __launch_bounds__(FAST_THREADS, 7) k_enumerate_fast(ProblemView 
 static size_t fast_smem_bytes(int topk) {
     return sizeof(WarpSmem) * FAST_WARPS + sizeof(bamse_record) * FAST_WARPS * (size_t)(topk > 0 ? topk : 1);
 }
+
+int enumerate_workers(int precision, int grid) { return precision == BAMSE_FP32 ? grid * FAST_WARPS : grid; }
 
 int enumerate_fast_grid_size(int device, int topk) {
     int sms = 148, per_sm = 1;

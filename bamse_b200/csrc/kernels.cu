@@ -119,9 +119,10 @@ __global__ void __launch_bounds__(LD_THREADS) k_enumerate_logdomain(ProblemView 
         const Segment seg = w.segs[lo];             // (empty segments share first_chunk with the next one;
                                                     //  the search lands on the last, i.e. the non-empty one)
         if (seg.p != cur_p) {
-            if (t == 0 && cur_p >= 0) {
-                bamse_record* dst = w.cand + ((size_t)cur_p * gridDim.x + blockIdx.x) * w.topk;
-                for (int i = 0; i < s_ntop; ++i) dst[i] = s_top[i];
+            if (t == 0 && cur_p >= 0 && s_ntop > 0) {
+                const unsigned long long pos = atomicAdd(w.cand_count, (unsigned long long)s_ntop);
+                if (pos + s_ntop <= w.cand_cap)
+                    for (int i = 0; i < s_ntop; ++i) w.cand[pos + i] = s_top[i];
                 s_ntop = 0;
             }
             cur_p = seg.p;
@@ -153,9 +154,10 @@ __global__ void __launch_bounds__(LD_THREADS) k_enumerate_logdomain(ProblemView 
             }
         }
     }
-    if (t == 0 && cur_p >= 0) {
-        bamse_record* dst = w.cand + ((size_t)cur_p * gridDim.x + blockIdx.x) * w.topk;
-        for (int i = 0; i < s_ntop; ++i) dst[i] = s_top[i];
+    if (t == 0 && cur_p >= 0 && s_ntop > 0) {
+        const unsigned long long pos = atomicAdd(w.cand_count, (unsigned long long)s_ntop);
+        if (pos + s_ntop <= w.cand_cap)
+            for (int i = 0; i < s_ntop; ++i) w.cand[pos + i] = s_top[i];
     }
 }
 
@@ -211,30 +213,31 @@ void launch_score_items(int precision, const ProblemView& pv, const ScoreItem* d
 }
 
 // ------------------------------------------------------------------------ merge
-// One CTA per parameter set: topk rounds of a block-wide arg-best over all candidates
-// that are strictly worse than the previous pick (the order is strict, so no marks).
-__global__ void __launch_bounds__(256) k_merge_topk(const bamse_record* __restrict__ lists, int n_lists,
-                                                    int64_t stride_list, int64_t stride_p, int topk,
+// One CTA per parameter set over an unordered bag of records: topk rounds of a block-wide
+// arg-best over the records of this parameter set that are strictly worse than the previous
+// pick (the order total desc, clust asc, tree asc is strict, so no marks are needed).
+__global__ void __launch_bounds__(512) k_merge_topk(const bamse_record* __restrict__ bag,
+                                                    const unsigned long long* __restrict__ count,
+                                                    unsigned long long n_given, int topk,
                                                     bamse_record* __restrict__ out) {
-    __shared__ bamse_record s_best[256 / 32];
+    constexpr int NT = 512;
+    __shared__ bamse_record s_best[NT / 32];
     __shared__ bamse_record s_prev;
-    __shared__ int s_has[256 / 32];
+    __shared__ int s_has[NT / 32];
     const int p = blockIdx.x, t = threadIdx.x, lane = t & 31, w = t >> 5;
-    const int n = n_lists * topk;
+    const unsigned long long n = count ? *count : n_given;
     bool have_prev = false;
     bool done = false;
     for (int r = 0; r < topk; ++r) {
         bamse_record best; best.clust = -1; best.total = 0; best.score = 0; best.param = p; best.tree = 0;
         bool has = false;
         if (!done)
-            for (int i = t; i < n; i += 256) {
-                const int l = i / topk, j = i - l * topk;
-                const bamse_record c = lists[((size_t)l * stride_list + (size_t)p * stride_p) * topk + j];
-                if (c.clust < 0 || c.total != c.total) continue;
+            for (unsigned long long i = t; i < n; i += NT) {
+                const bamse_record c = bag[i];
+                if (c.param != p || c.clust < 0 || c.total != c.total) continue;
                 if (have_prev && !rec_better(s_prev, c)) continue;
                 if (!has || rec_better(c, best)) { best = c; has = true; }
             }
-        // warp reduce
         for (int d = 16; d > 0; d >>= 1) {
             bamse_record o;
             o.total = __shfl_xor_sync(0xffffffffu, best.total, d);
@@ -249,7 +252,7 @@ __global__ void __launch_bounds__(256) k_merge_topk(const bamse_record* __restri
         __syncthreads();
         if (t == 0) {
             bool h = false; bamse_record b = s_best[0];
-            for (int i = 0; i < 256 / 32; ++i)
+            for (int i = 0; i < NT / 32; ++i)
                 if (s_has[i] && (!h || rec_better(s_best[i], b))) { b = s_best[i]; h = true; }
             if (h) { s_prev = b; out[(size_t)p * topk + r] = b; }
             else {
@@ -264,9 +267,9 @@ __global__ void __launch_bounds__(256) k_merge_topk(const bamse_record* __restri
     }
 }
 
-void launch_merge_topk(const bamse_record* d_lists, int n_lists, int64_t stride_list, int64_t stride_p, int P,
+void launch_merge_topk(const bamse_record* d_bag, const unsigned long long* d_count, unsigned long long n, int P,
                        int topk, bamse_record* d_out, cudaStream_t s) {
-    k_merge_topk<<<P, 256, 0, s>>>(d_lists, n_lists, stride_list, stride_p, topk, d_out);
+    k_merge_topk<<<P, 512, 0, s>>>(d_bag, d_count, n, topk, d_out);
 }
 
 }  // namespace bamse

@@ -35,7 +35,9 @@ struct EnumWork {
     const uint64_t* total_chunks;     // device scalar written by k_build_segments
     unsigned long long* next_chunk;   // device work counter (zeroed before launch)
     int topk;
-    bamse_record* cand;      // [P][gridDim.x][topk] per-CTA candidates (clust = -1 when unused)
+    bamse_record* cand;      // flat bag of candidate records appended by the workers (each carries its param)
+    unsigned long long* cand_count;   // append cursor (zeroed before launch)
+    unsigned long long cand_cap;      // capacity in records (sized so that it cannot overflow)
     double* dense_score;     // optional [n_trees of segment 0]
     double* dense_logscre;   // optional
     unsigned long long* stats;   // optional [4]: executed MUFU ops (thread level), conv terms, convs, scans
@@ -52,9 +54,11 @@ int enumerate_grid_size(int precision, int device);
 void launch_enumerate(int precision, const ProblemView& pv, const EnumWork& w, int grid, cudaStream_t s);
 void launch_score_items(int precision, const ProblemView& pv, const ScoreItem* d_items, int64_t n,
                         double* d_out, cudaStream_t s);
-// list l of parameter set p starts at d_lists + (l * stride_list + p * stride_p) * topk
-void launch_merge_topk(const bamse_record* d_lists, int n_lists, int64_t stride_list, int64_t stride_p, int P,
+// d_bag: n records (n read from d_count when non-NULL) in any order, each tagged with its param;
+// writes the best topk of every parameter set to d_out [P][topk]
+void launch_merge_topk(const bamse_record* d_bag, const unsigned long long* d_count, unsigned long long n, int P,
                        int topk, bamse_record* d_out, cudaStream_t s);
+int enumerate_workers(int precision, int grid);
 
 struct FastTables;
 void launch_tables_fast(const ProblemView& pv, float* D2, float* EL2, float* SEL2, cudaStream_t s);
