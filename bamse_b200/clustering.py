@@ -220,7 +220,7 @@ def analyse_clusterings(clusts, top_trees, ctx=None, precision=cuda_shim.FP32, s
     error rate: reorder -> greedy candidate -> threshold for all clusterings in batched GPU
     calls, then ONE enumeration of every labeled rooted tree of every clustering with a
     global top-`top_trees`.  Returns the ranked list of tree dicts (reference keys).
-    tree_shard = (rank, world) restricts the enumeration to this rank's index ranges."""
+    tree_shard = (rank, world) restricts the enumeration to this rank's interleaved share."""
     if not clusts:
         return []
     ctx = ctx or get_context()
@@ -263,13 +263,9 @@ def analyse_clusterings(clusts, top_trees, ctx=None, precision=cuda_shim.FP32, s
     thr = np.array([[s[ci] + math.log(canonizeF(cand[ci])['scre']) for ci in range(len(clusts))]])
     const = np.array([[c.cluster_prior + c.maxlikelihood for c in clusts]])
     # 4. exhaustive enumeration + global top-k
-    tb = te = None
     if tree_shard is not None:
-        r, w = tree_shard
-        T = [int(c.As.shape[0]) ** (int(c.As.shape[0]) - 1) for c in clusts]
-        tb = [t * r // w for t in T]
-        te = [t * (r + 1) // w for t in T]
-    rec, par, cnt = ctx.score_topk(const, thr, tb, te, topk=min(max(int(top_trees), 1), cuda_shim.TOPK_MAX),
+        ctx.set_shard(*tree_shard)
+    rec, par, cnt = ctx.score_topk(const, thr, None, None, topk=min(max(int(top_trees), 1), cuda_shim.TOPK_MAX),
                                    precision=precision)
     out = []
     for j in range(int(cnt[0])):

@@ -51,6 +51,7 @@ struct bamse_ctx {
     DBuf d_segs, d_scalars /* total_chunks, total_trees, next_chunk */, d_cand, d_items, d_scores;
     DBuf d_const, d_thr, d_begin, d_end, d_records, d_dense0, d_dense1;
     int grid[3] = {0, 0, 0};
+    int shard_rank = 0, shard_world = 1;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_used, ev_free;
 
     int fail(int code, const char* fmt, ...) {
@@ -149,6 +150,13 @@ void bamse_destroy(bamse_ctx* ctx) {
 int bamse_set_stream(bamse_ctx* ctx, void* cuda_stream) {
     CTX_CHECK(ctx);
     ctx->stream = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : ctx->own_stream;
+    return BAMSE_OK;
+}
+
+int bamse_set_shard(bamse_ctx* ctx, int rank, int world) {
+    CTX_CHECK(ctx);
+    if (world < 1 || rank < 0 || rank >= world) return ctx->fail(BAMSE_EINVAL, "bamse_set_shard: need 0 <= rank < world");
+    ctx->shard_rank = rank; ctx->shard_world = world;
     return BAMSE_OK;
 }
 
@@ -341,7 +349,7 @@ static int enumerate_dev(bamse_ctx* ctx, const double* d_const, const double* d_
     if (host_seg) trees_upper = host_seg->n_trees;
     else {
         for (int c = 0; c < C; ++c) trees_upper += ipow_u64(ctx->K_of_c[c], ctx->K_of_c[c] - 1);
-        trees_upper *= (uint64_t)P;
+        trees_upper = trees_upper * (uint64_t)P / (uint64_t)ctx->shard_world + (uint64_t)P * C;
     }
     const int chunk = (int)std::min<uint64_t>(16, std::max<uint64_t>(1, trees_upper / ((uint64_t)workers * 32)));
     const uint64_t chunks_upper = trees_upper / chunk + (uint64_t)P * C + 1;
@@ -364,7 +372,7 @@ static int enumerate_dev(bamse_ctx* ctx, const double* d_const, const double* d_
         ctx->last_evals = (int64_t)seg.n_trees;
     } else {
         launch_build_segments(P, C, ctx->d_K.as<int32_t>(), d_const, d_thr, d_begin, d_end, slack_abs, slack_rel,
-                              chunk, ctx->d_segs.as<Segment>(), scal, scal + 1, s);
+                              chunk, ctx->shard_rank, ctx->shard_world, ctx->d_segs.as<Segment>(), scal, scal + 1, s);
         ctx->launches++;
         w.n_segs = P * C;
     }
@@ -418,7 +426,7 @@ int bamse_score_range(bamse_ctx* ctx, int p, int c, uint64_t tree_begin, int64_t
     BAMSE_CUDA_TRY(ctx, ctx->d_dense1.ensure(sizeof(double) * n));
     Segment seg;
     memset(&seg, 0, sizeof seg);
-    seg.p = p; seg.c = c; seg.K = K;
+    seg.p = p; seg.c = c; seg.K = K; seg.stride = 1;
     seg.tree_begin = tree_begin; seg.n_trees = (uint64_t)n;
     seg.first_chunk = 0; seg.clust_const = 0.0; seg.threshold = -INFINITY;
     int rc = enumerate_dev(ctx, nullptr, nullptr, nullptr, nullptr, 0, precision, 0.0, 0.0, nullptr,
@@ -481,7 +489,8 @@ int bamse_score_topk(bamse_ctx* ctx, const double* clust_const, const double* th
         const int K = ctx->K_of_c[c];
         const uint64_t T = ipow_u64(K, K - 1);
         uint64_t b = tree_begin ? tree_begin[c] : 0, e = tree_end ? std::min<uint64_t>(tree_end[c], T) : T;
-        if (b < e) evals += (int64_t)(e - b);
+        if (b < e && e - b > (uint64_t)ctx->shard_rank)
+            evals += (int64_t)((e - b - ctx->shard_rank + ctx->shard_world - 1) / ctx->shard_world);
     }
     evals *= P;
     if (tree_begin) {

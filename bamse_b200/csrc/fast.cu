@@ -147,7 +147,7 @@ __global__ void __launch_bounds__(FAST_THREADS, 7) k_enumerate_fast(ProblemView 
         const uint64_t remain = seg.n_trees - off;
         const int n = remain < (uint64_t)w.chunk ? (int)remain : w.chunk;
         for (int i = 0; i < n; ++i) {
-            const uint64_t tree = seg.tree_begin + off + i;
+            const uint64_t tree = seg.tree_begin + (off + i) * (uint64_t)seg.stride;
             if (lane == 0) {
                 int8_t parent[KMAX];
                 decode_tree(seg.K, tree, parent);
@@ -175,7 +175,35 @@ __global__ void __launch_bounds__(FAST_THREADS, 7) k_enumerate_fast(ProblemView 
             __syncwarp();
         }
     }
-    flush();
+    // end of the launch: the warps of a CTA finish within one tree of each other, so a block-level
+    // merge of their lists is cheap and keeps the bag (and the merge kernel's input) 4x smaller
+    // (only records of the same parameter set compete; with mixed sets everything is appended)
+    __shared__ int s_ntop[FAST_WARPS];
+    __shared__ int s_p[FAST_WARPS];
+    if (lane == 0) { s_ntop[wid] = ntop; s_p[wid] = cur_p; }
+    __syncthreads();
+    if (t == 0 && w.topk > 0) {
+        int pos[FAST_WARPS];
+        int total_n = 0, p_seen = -1;
+        bool same_p = true;
+        for (int i = 0; i < FAST_WARPS; ++i) {
+            pos[i] = 0; total_n += s_ntop[i];
+            if (s_ntop[i] > 0) { if (p_seen < 0) p_seen = s_p[i]; else if (s_p[i] != p_seen) same_p = false; }
+        }
+        const int n_out = (same_p && total_n > w.topk) ? w.topk : total_n;
+        if (n_out > 0) {
+            const unsigned long long base = atomicAdd(w.cand_count, (unsigned long long)n_out);
+            for (int r = 0; r < n_out; ++r) {
+                int best = -1;
+                for (int i = 0; i < FAST_WARPS; ++i)
+                    if (pos[i] < s_ntop[i] &&
+                        (best < 0 || rec_better_f(s_top_all[i * kcap + pos[i]], s_top_all[best * kcap + pos[best]])))
+                        best = i;
+                if (base + r < w.cand_cap) w.cand[base + r] = s_top_all[best * kcap + pos[best]];
+                ++pos[best];
+            }
+        }
+    }
     if (w.stats && lane == 0) {
         // thread-level MUFU ops: 4 ex2 per chunk per lane x 32 lanes, 16 passes x 1 lg2 x 32 per conv,
         // 59 per lane per scan, 17 per lane per final log-sum-exp

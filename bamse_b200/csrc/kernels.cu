@@ -37,41 +37,54 @@ void launch_tables(const ProblemView& pv, const double* d_var, const double* d_r
 }
 
 // ----------------------------------------------------------------------- segments
-__global__ void k_build_segments(int P, int C, const int32_t* __restrict__ K_of_c, const double* __restrict__ cconst,
-                                 const double* __restrict__ thr, const uint64_t* __restrict__ begin,
-                                 const uint64_t* __restrict__ end, double slack_abs, double slack_rel, int chunk,
-                                 Segment* __restrict__ segs, uint64_t* __restrict__ total_chunks,
-                                 uint64_t* __restrict__ total_trees) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    uint64_t chunks = 0, trees = 0;
-    for (int p = 0; p < P; ++p)
-        for (int c = 0; c < C; ++c) {
-            const int K = K_of_c[c];
-            const uint64_t T = ipow_u64(K, K - 1);
-            uint64_t b = begin ? begin[c] : 0, e = end ? end[c] : T;
-            if (e > T) e = T;
-            if (b > e) b = e;
-            Segment s;
-            s.p = p; s.c = c; s.K = K; s.pad = 0;
-            s.tree_begin = b; s.n_trees = e - b; s.first_chunk = chunks;
-            s.clust_const = cconst ? cconst[p * C + c] : 0.0;
-            double th = thr ? thr[p * C + c] : -CUDART_INF;
-            if (th > -CUDART_INF) th -= slack_abs + slack_rel * fabs(th);
-            s.threshold = th;
-            segs[p * C + c] = s;
-            chunks += (s.n_trees + (uint64_t)chunk - 1) / (uint64_t)chunk;
-            trees += s.n_trees;
+__global__ void __launch_bounds__(256) k_build_segments(int P, int C, const int32_t* __restrict__ K_of_c,
+                                                        const double* __restrict__ cconst, const double* __restrict__ thr,
+                                                        const uint64_t* __restrict__ begin, const uint64_t* __restrict__ end,
+                                                        double slack_abs, double slack_rel, int chunk, int shard_rank,
+                                                        int shard_world, Segment* __restrict__ segs,
+                                                        uint64_t* __restrict__ total_chunks, uint64_t* __restrict__ total_trees) {
+    // one thread per (p, c) fills its segment, then thread 0 turns chunk counts into prefix sums
+    const int n = P * C;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int p = i / C, c = i - p * C;
+        const int K = K_of_c[c];
+        const uint64_t T = ipow_u64(K, K - 1);
+        uint64_t b = begin ? begin[c] : 0, e = end ? end[c] : T;
+        if (e > T) e = T;
+        if (b > e) b = e;
+        Segment s;
+        s.p = p; s.c = c; s.K = K; s.stride = shard_world;
+        // interleaved shard: indices b + rank, b + rank + world, ... below e
+        const uint64_t span = e - b;
+        s.tree_begin = b + (uint64_t)shard_rank;
+        s.n_trees = span > (uint64_t)shard_rank ? (span - shard_rank + shard_world - 1) / shard_world : 0;
+        s.first_chunk = (s.n_trees + (uint64_t)chunk - 1) / (uint64_t)chunk;   // count for now
+        s.clust_const = cconst ? cconst[i] : 0.0;
+        double th = thr ? thr[i] : -CUDART_INF;
+        if (th > -CUDART_INF) th -= slack_abs + slack_rel * fabs(th);
+        s.threshold = th;
+        segs[i] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint64_t chunks = 0, trees = 0;
+        for (int i = 0; i < n; ++i) {
+            const uint64_t cnt = segs[i].first_chunk;
+            segs[i].first_chunk = chunks;
+            chunks += cnt;
+            trees += segs[i].n_trees;
         }
-    *total_chunks = chunks;
-    *total_trees = trees;
+        *total_chunks = chunks;
+        *total_trees = trees;
+    }
 }
 
 void launch_build_segments(int P, int C, const int32_t* d_K_of_c, const double* d_const, const double* d_thr,
                            const uint64_t* d_begin, const uint64_t* d_end, double slack_abs, double slack_rel,
-                           int chunk, Segment* d_segs, uint64_t* d_total_chunks, uint64_t* d_total_trees,
-                           cudaStream_t s) {
-    k_build_segments<<<1, 32, 0, s>>>(P, C, d_K_of_c, d_const, d_thr, d_begin, d_end, slack_abs, slack_rel, chunk,
-                                      d_segs, d_total_chunks, d_total_trees);
+                           int chunk, int shard_rank, int shard_world, Segment* d_segs, uint64_t* d_total_chunks,
+                           uint64_t* d_total_trees, cudaStream_t s) {
+    k_build_segments<<<1, 256, 0, s>>>(P, C, d_K_of_c, d_const, d_thr, d_begin, d_end, slack_abs, slack_rel, chunk,
+                                      shard_rank, shard_world, d_segs, d_total_chunks, d_total_trees);
 }
 
 // --------------------------------------------------------------------- top-k helper
@@ -131,7 +144,7 @@ __global__ void __launch_bounds__(LD_THREADS) k_enumerate_logdomain(ProblemView 
         const uint64_t remain = seg.n_trees - off;
         const int n = remain < (uint64_t)w.chunk ? (int)remain : w.chunk;
         for (int i = 0; i < n; ++i) {
-            const uint64_t tree = seg.tree_begin + off + i;
+            const uint64_t tree = seg.tree_begin + (off + i) * (uint64_t)seg.stride;
             __syncthreads();
             if (t == 0) {
                 int8_t parent[KMAX];

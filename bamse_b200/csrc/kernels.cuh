@@ -20,7 +20,7 @@ struct Segment {
     int32_t p;
     int32_t c;
     int32_t K;
-    int32_t pad;
+    int32_t stride;          // tree index step (interleaved sharding: rank r scores begin + r + i * world)
     uint64_t tree_begin;
     uint64_t n_trees;
     uint64_t first_chunk;    // prefix sum of chunk counts
@@ -48,7 +48,7 @@ void launch_tables(const ProblemView& pv, const double* d_var, const double* d_r
                    cudaStream_t s);
 void launch_build_segments(int P, int C, const int32_t* d_K_of_c, const double* d_const, const double* d_thr,
                            const uint64_t* d_begin, const uint64_t* d_end, double slack_abs, double slack_rel,
-                           int chunk, Segment* d_segs, uint64_t* d_total_chunks, uint64_t* d_total_trees,
+                           int chunk, int shard_rank, int shard_world, Segment* d_segs, uint64_t* d_total_chunks, uint64_t* d_total_trees,
                            cudaStream_t s);
 int enumerate_grid_size(int precision, int device);
 void launch_enumerate(int precision, const ProblemView& pv, const EnumWork& w, int grid, cudaStream_t s);

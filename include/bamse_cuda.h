@@ -70,6 +70,11 @@ const char* bamse_last_error(const bamse_ctx* ctx);
 /* Launch all work of this ctx on `cuda_stream` (a cudaStream_t; NULL = the ctx's own
  * stream).  Lets a host that owns streams (e.g. torch) time the kernels with its events. */
 int bamse_set_stream(bamse_ctx* ctx, void* cuda_stream);
+/* Multi-GPU sharding: with (rank, world) set, every enumeration of this ctx scores only the
+ * tree indices begin + rank, begin + rank + world, ... of each requested range (interleaved,
+ * so that every rank sees the same mix of tree shapes).  Default (0, 1) = everything.
+ * bamse_score_range is not affected. */
+int bamse_set_shard(bamse_ctx* ctx, int rank, int world);
 /* Number of kernels this ctx has launched since creation (for bench.py `gpu_launches`). */
 int64_t bamse_launch_count(const bamse_ctx* ctx);
 

@@ -145,6 +145,20 @@ def test_tree_range_sharding_equals_single_range(ctx, shim):
     parts.sort(key=lambda r: (-r[0], r[2], r[4]))
     assert [r[4] for r in parts[:5]] == whole[0]["tree"].tolist()
     assert [r[0] for r in parts[:5]] == whole[0]["total"].tolist()
+    # interleaved shards (bamse_set_shard), fp32 selection + fp64 re-score, host merge
+    from bamse_b200 import multigpu
+    lists = []
+    evals = 0
+    for r in range(3):
+        ctx.set_shard(r, 3)
+        rec, _, _ = ctx.score_topk(const, topk=5, precision=shim.FP32)
+        evals += ctx.last_eval_count
+        lists.append(rec)
+    ctx.set_shard(0, 1)
+    assert evals == T
+    merged = multigpu.merge_records(np.stack(lists), 5)
+    assert merged[0]["tree"].tolist() == whole[0]["tree"].tolist()
+    np.testing.assert_allclose(merged[0]["total"], whole[0]["total"], rtol=1e-12)
 
 
 def test_errors_are_reported_not_thrown(ctx, shim):
