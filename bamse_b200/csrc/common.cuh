@@ -39,9 +39,10 @@ struct TreeProgram {
     int8_t n_ops;
     int8_t k;              // nodes in this tree
     int8_t n_leaves;
-    int8_t pad;
+    int8_t pad;            // fast path: how the per-sample scalar is finished (FIN_*)
     int8_t op[MAX_OPS];
     int8_t arg[MAX_OPS];   // table row (cluster id) for OP_LEAF / OP_ADDD
+    int8_t fin_r, fin_c;   // fast path: root row / leaf-child row of the finishing table
     int32_t scre;          // canonizeF 'scre'                              (tree_tools.py:47-63)
 };
 

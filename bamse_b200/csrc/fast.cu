@@ -10,7 +10,8 @@ namespace bamse {
 // one CTA (256 threads) per table row: EL = logcumsum(D) + p0 - log L, SEL = logcumsum(EL) + p0 - log L
 // computed in fp64 natural logs, stored as fp32 base-2 logs.
 __global__ void __launch_bounds__(LD_THREADS) k_tables_fast(ProblemView pv, float* __restrict__ D2,
-                                                            float* __restrict__ EL2, float* __restrict__ SEL2) {
+                                                            float* __restrict__ EL2, float* __restrict__ SEL2,
+                                                            float* __restrict__ SD2) {
     __shared__ double v[L];
     __shared__ double scratch[LD_THREADS / 32];
     const int row = blockIdx.x;
@@ -30,11 +31,20 @@ __global__ void __launch_bounds__(LD_THREADS) k_tables_fast(ProblemView pv, floa
     block_logcumsum<double>(v, add, scratch);
     SEL2[(size_t)row * L + t] = (float)(v[t] * log2e);
     SEL2[(size_t)row * L + t + LD_THREADS] = (float)(v[t + LD_THREADS] * log2e);
+    if (SD2) {
+        // suffix sums of d: the prefix scan of the reversed table; SD = e^p0 / L^2 * sum_{x>=i} d[x]
+        __syncthreads();
+        v[t] = src[L - 1 - t]; v[t + LD_THREADS] = src[L - 1 - t - LD_THREADS];
+        __syncthreads();
+        block_logcumsum<double>(v, add - 6.2383246250395077847550890931236, scratch);
+        SD2[(size_t)row * L + (L - 1 - t)] = (float)(v[t] * log2e);
+        SD2[(size_t)row * L + (L - 1 - t - LD_THREADS)] = (float)(v[t + LD_THREADS] * log2e);
+    }
 }
 
-void launch_tables_fast(const ProblemView& pv, float* D2, float* EL2, float* SEL2, cudaStream_t s) {
+void launch_tables_fast(const ProblemView& pv, float* D2, float* EL2, float* SEL2, float* SD2, cudaStream_t s) {
     const int rows = pv.P * pv.C * pv.M * pv.Kmax;
-    k_tables_fast<<<rows, LD_THREADS, 0, s>>>(pv, D2, EL2, SEL2);
+    k_tables_fast<<<rows, LD_THREADS, 0, s>>>(pv, D2, EL2, SEL2, SD2);
 }
 
 // ------------------------------------------------------------------ per-warp evaluation
@@ -88,10 +98,43 @@ __device__ inline double warp_eval_tree(const ProblemView& pv, const FastTables&
                 warp_add_table(ws->vec[sp - 1] + GUARD, ft.D2 + base + (size_t)arg * L, lane);
             }
         }
-        const float lse2 = warp_log2sumexp(ws->vec[0] + GUARD, lane);
-        total += (double)(lse2 - LOG2_L) * 0.69314718055994530942;
+        const int fin = ws->prog.pad;
+        float res2;
+        if (fin == FIN_LSE) res2 = warp_log2sumexp(ws->vec[0] + GUARD, lane) - LOG2_L;
+        else if (fin == FIN_DOT_D) res2 = warp_log2dot(ws->vec[0] + GUARD, ft.D2 + base + (size_t)ws->prog.fin_r * L, lane) - LOG2_L;
+        else if (fin == FIN_DOT_SD) res2 = warp_log2dot(ws->vec[0] + GUARD, ft.SD2 + base + (size_t)ws->prog.fin_r * L, lane);
+        else res2 = warp_log2dot(ws->vec[0] + GUARD,
+                                 ft.HS2 + base * pv.Kmax + ((size_t)ws->prog.fin_r * pv.Kmax + ws->prog.fin_c) * L, lane);
+        total += (double)res2 * 0.69314718055994530942;
     }
     return total;
+}
+
+// HS[r][c][i] = 1/L^2 * sum_j d_r[i+j] * sel_c[j]: the correlation of D[r] with the scanned leaf
+// message of c is the convolution of the REVERSED (still log-concave) D[r] with it, read backwards.
+// One warp per (p, c, m, r, c') with the production convolution.
+__global__ void __launch_bounds__(FAST_THREADS) k_tables_hs(ProblemView pv, FastTables ft, float* __restrict__ HS2) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int wid = threadIdx.x >> 5;
+    int lane = threadIdx.x & 31;
+    WarpSmem* ws = pin_shared(reinterpret_cast<WarpSmem*>(smem_raw) + wid);
+    const int64_t idx = (int64_t)blockIdx.x * FAST_WARPS + wid;     // ((pcm * Kmax) + r) * Kmax + c
+    const int Kmax = pv.Kmax;
+    const int64_t n = (int64_t)pv.P * pv.C * pv.M * Kmax * Kmax;
+    if (idx >= n) return;
+    const int cc = (int)(idx % Kmax), r = (int)((idx / Kmax) % Kmax);
+    const int64_t pcm = idx / ((int64_t)Kmax * Kmax);
+    const int c = (int)((pcm / pv.M) % pv.C);
+    if (r == cc || r >= pv.K_of_c[c] || cc >= pv.K_of_c[c]) return;
+    warp_init_guards(ws, lane);
+    float* a = ws->vec[0] + GUARD;
+    float* b = ws->vec[1] + GUARD;
+    const float* D = ft.D2 + ((size_t)pcm * Kmax + r) * L;
+    for (int t = 0; t < 16; ++t) a[lane + 32 * t] = __ldg(D + (L - 1 - lane - 32 * t));
+    warp_load_vec(b, ft.SEL2 + ((size_t)pcm * Kmax + cc) * L, lane);
+    warp_logconv(a, b, ws->jstar, lane);
+    float* out = HS2 + (size_t)idx * L;
+    for (int t = 0; t < 16; ++t) out[lane + 32 * t] = a[L - 1 - lane - 32 * t] - LOG2_L;
 }
 
 __device__ __forceinline__ bool rec_better_f(const bamse_record& a, const bamse_record& b) {
@@ -151,7 +194,7 @@ __global__ void __launch_bounds__(FAST_THREADS, 7) k_enumerate_fast(ProblemView 
             if (lane == 0) {
                 int8_t parent[KMAX];
                 decode_tree(seg.K, tree, parent);
-                build_program_fast(seg.K, parent, nullptr, &ws->prog);
+                build_program_fast(seg.K, parent, nullptr, &ws->prog, ft.HS2 != nullptr);
             }
             __syncwarp();
             const double score = warp_eval_tree(pv, ft, seg.p, seg.c, ws, lane, &st_chunks, &st_convs, &st_scans);
@@ -219,6 +262,13 @@ static size_t fast_smem_bytes(int topk) {
     return sizeof(WarpSmem) * FAST_WARPS + sizeof(bamse_record) * FAST_WARPS * (size_t)(topk > 0 ? topk : 1);
 }
 
+void launch_tables_hs(const ProblemView& pv, const FastTables& ft, float* HS2, cudaStream_t s) {
+    const int64_t n = (int64_t)pv.P * pv.C * pv.M * pv.Kmax * pv.Kmax;
+    const size_t smem = sizeof(WarpSmem) * FAST_WARPS;
+    cudaFuncSetAttribute(k_tables_hs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k_tables_hs<<<(unsigned)((n + FAST_WARPS - 1) / FAST_WARPS), FAST_THREADS, smem, s>>>(pv, ft, HS2);
+}
+
 int enumerate_workers(int precision, int grid) { return precision == BAMSE_FP32 ? grid * FAST_WARPS : grid; }
 
 int enumerate_fast_grid_size(int device, int topk) {
@@ -247,7 +297,7 @@ __global__ void __launch_bounds__(FAST_THREADS) k_score_items_fast(ProblemView p
     warp_init_guards(ws, lane);
     const ScoreItem it = items[idx];
     int ok = 1;
-    if (lane == 0) ok = build_program_fast(it.k, it.parent, it.nodes, &ws->prog) ? 1 : 0;
+    if (lane == 0) ok = build_program_fast(it.k, it.parent, it.nodes, &ws->prog, ft.HS2 != nullptr) ? 1 : 0;
     ok = __shfl_sync(0xffffffffu, ok, 0);
     if (!ok) { if (lane == 0) out[idx] = CUDART_NAN; return; }
     unsigned s0 = 0, s1 = 0, s2 = 0;

@@ -30,6 +30,10 @@ struct FastTables {
     const float* D2;     // [rows][L] log2 of the binomial tables                (clustering.py:20-24)
     const float* EL2;    // [rows][L] leaf message  log2cumsum(D) + p0 - log L   (clustering.py:377)
     const float* SEL2;   // [rows][L] scanned leaf message (a leaf used as the scan factor)
+    // root tables (may be NULL): only the scalar sum_x d_r[x] G[x] is needed at the root, so the
+    // last operation there is a dot product of the folded children message Q with
+    const float* SD2;    // [rows][L]       SD[r][i]    = e^p0 / L^2 * sum_{x>=i} d_r[x]              (no leaf child)
+    const float* HS2;    // [rows][Kmax][L] HS[r][c][i] = 1 / L^2 * sum_j d_r[i+j] * sel_c[j]         (leaf child c)
 };
 
 // evaluation program of the fast path (convolution is commutative/associative, so the
@@ -42,10 +46,18 @@ enum : int8_t {
     FOP_CONV = 3,       // b = pop; top = top (*) b   (in place)
     FOP_ADDD = 4,       // top += D2[arg]
 };
+// how the per-sample scalar is produced from the vector left on the stack (TreeProgram::pad;
+// the root node id is TreeProgram::fin_r, the leaf child of FIN_HS is TreeProgram::fin_c)
+enum : int8_t {
+    FIN_LSE = 0,        // log2sumexp(top) - log2 L                 (trap_int(...)[-1], clustering.py:385)
+    FIN_DOT_D = 1,      // log2 sum 2^(top + D2[r]) - log2 L        root with one (leaf) child
+    FIN_DOT_SD = 2,     // log2 sum 2^(top + SD2[r])                root without leaf children
+    FIN_DOT_HS = 3,     // log2 sum 2^(top + HS2[r][c])             root with leaf child c, top = the other children
+};
 
 // Builds the fast program + canonizeF weight.  Same validity rules as build_program.
 __host__ __device__ inline bool build_program_fast(int k, const int8_t* parent, const int8_t* nodes,
-                                                   TreeProgram* prog) {
+                                                   TreeProgram* prog, bool root_tables = false) {
     // canon weight / validation through the reference-order builder
     if (!build_program(k, parent, nodes, prog)) return false;
     const int32_t scre = prog->scre;
@@ -64,6 +76,7 @@ __host__ __device__ inline bool build_program_fast(int k, const int8_t* parent, 
     int8_t st_node[KMAX], st_stage[KMAX], st_done[KMAX];
     uint16_t st_used[KMAX];              // internal children already evaluated (bit mask)
     int n_ops = 0, sp = 0;
+    int8_t fin = FIN_LSE, fin_r = 0, fin_c = 0;
     auto emit = [&](int8_t op, int8_t arg) { prog->op[n_ops] = op; prog->arg[n_ops] = arg; ++n_ops; };
     if (nchild[root] == 0) { emit(FOP_PUSH_EL, nodes ? nodes[root] : (int8_t)root); }
     else { st_node[0] = (int8_t)root; st_stage[0] = 0; st_done[0] = 0; st_used[0] = 0; sp = 1; }
@@ -78,6 +91,28 @@ __host__ __device__ inline bool build_program_fast(int k, const int8_t* parent, 
                 st_used[f] |= (uint16_t)(1u << best);
                 st_stage[f] = 1;                     // after the child returns: fold it
                 st_node[sp] = (int8_t)best; st_stage[sp] = 0; st_done[sp] = 0; st_used[sp] = 0; ++sp;
+                continue;
+            }
+            if (root_tables && f == 0) {
+                // the root: its first leaf child (if any) is folded in by the HS table, the scan and
+                // D[root] by the SD / HS / D tables -- one convolution and one scan fewer
+                int cstar = -1;
+                for (int c = 0; c < k; ++c)
+                    if (parent[c] == v && nchild[c] == 0) {
+                        if (cstar < 0) { cstar = c; continue; }
+                        if (n_ops + 2 > MAX_OPS) return false;
+                        emit(FOP_PUSH_EL, nodes ? nodes[c] : (int8_t)c);
+                        if (st_done[f] > 0) emit(FOP_CONV, 0);
+                        st_done[f]++;
+                    }
+                fin_r = nodes ? nodes[v] : (int8_t)v;
+                if (cstar < 0) fin = FIN_DOT_SD;
+                else if (st_done[f] == 0) {
+                    if (n_ops + 1 > MAX_OPS) return false;
+                    emit(FOP_PUSH_SEL, nodes ? nodes[cstar] : (int8_t)cstar);
+                    fin = FIN_DOT_D;
+                } else { fin = FIN_DOT_HS; fin_c = nodes ? nodes[cstar] : (int8_t)cstar; }
+                --sp;
                 continue;
             }
             // internal children done: leaves
@@ -103,6 +138,7 @@ __host__ __device__ inline bool build_program_fast(int k, const int8_t* parent, 
         }
     }
     prog->n_ops = (int8_t)n_ops; prog->k = (int8_t)k; prog->n_leaves = (int8_t)n_leaves; prog->scre = scre;
+    prog->pad = fin; prog->fin_r = fin_r; prog->fin_c = fin_c;
     return true;
 }
 
@@ -174,6 +210,28 @@ __device__ inline float warp_log2sumexp(const float* __restrict__ v, int lane) {
     for (int t = 0; t < 4; ++t) {
         const float4 q = reinterpret_cast<const float4*>(v)[lane + 32 * t];
         x[4 * t] = q.x; x[4 * t + 1] = q.y; x[4 * t + 2] = q.z; x[4 * t + 3] = q.w;
+    }
+    float m = x[0];
+#pragma unroll
+    for (int i = 1; i < 16; ++i) m = fmaxf(m, x[i]);
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, d));
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += ex2f(x[i] - m);
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+    return m + lg2f(s);
+}
+
+// log2(sum_x 2^(v[x] + tab[x])), v in shared memory, tab a table row in global memory
+__device__ inline float warp_log2dot(const float* __restrict__ v, const float* __restrict__ tab, int lane) {
+    float x[16];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        const float4 q = reinterpret_cast<const float4*>(v)[lane + 32 * t];
+        const float4 d = __ldg(reinterpret_cast<const float4*>(tab) + lane + 32 * t);
+        x[4 * t] = q.x + d.x; x[4 * t + 1] = q.y + d.y; x[4 * t + 2] = q.z + d.z; x[4 * t + 3] = q.w + d.w;
     }
     float m = x[0];
 #pragma unroll
