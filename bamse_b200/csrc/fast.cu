@@ -48,22 +48,28 @@ void launch_tables_fast(const ProblemView& pv, float* D2, float* EL2, float* SEL
 }
 
 // ------------------------------------------------------------------ per-warp evaluation
-struct alignas(16) WarpSmem {
+template <bool FRAMED>
+struct alignas(16) WarpSmemT {
     float vec[FAST_SLOTS][VSTRIDE];
     uint16_t jstar[L];
+    float fa[FRAMED ? FR_A : 4];      // framed-path scratch: 2^(a - frame) of the current segment
+    float fb[FRAMED ? FR_SEG : 4];    // framed-path scratch: 2^(b - frame)
     TreeProgram prog;
 };
+using WarpSmem = WarpSmemT<false>;
 // dynamic shared memory: FAST_WARPS x WarpSmem, then FAST_WARPS x topk bamse_records
 
 // Keeps the warp's shared-memory base in a register: without the opaque move ptxas
 // rematerialises it from S2R tid / cta-id several times per convolution pass.
-__device__ __forceinline__ WarpSmem* pin_shared(WarpSmem* p) {
+template <class W>
+__device__ __forceinline__ W* pin_shared(W* p) {
     unsigned s = (unsigned)__cvta_generic_to_shared(p);
     asm volatile("" : "+r"(s));
-    return reinterpret_cast<WarpSmem*>(__cvta_shared_to_generic(s));
+    return reinterpret_cast<W*>(__cvta_shared_to_generic(s));
 }
 
-__device__ inline void warp_init_guards(WarpSmem* ws, int lane) {
+template <class W>
+__device__ inline void warp_init_guards(W* ws, int lane) {
     for (int s = 0; s < FAST_SLOTS; ++s) {
         for (int i = lane; i < GUARD; i += 32) ws->vec[s][i] = -CUDART_INF_F;
         if (lane < 4) ws->vec[s][GUARD + L + lane] = -CUDART_INF_F;
@@ -72,7 +78,8 @@ __device__ inline void warp_init_guards(WarpSmem* ws, int lane) {
 }
 
 // score of the tree whose program sits in ws->prog, summed over samples (fp64), natural log
-__device__ inline double warp_eval_tree(const ProblemView& pv, const FastTables& ft, int p, int c, WarpSmem* ws,
+template <bool FRAMED>
+__device__ inline double warp_eval_tree(const ProblemView& pv, const FastTables& ft, int p, int c, WarpSmemT<FRAMED>* ws,
                                         int lane, unsigned* st_chunks, unsigned* st_convs, unsigned* st_scans) {
     const float add2 = (float)((pv.p0[c] - 6.2383246250395077847550890931236) * 1.4426950408889634074);
     const int n_ops = ws->prog.n_ops;
@@ -91,7 +98,7 @@ __device__ inline double warp_eval_tree(const ProblemView& pv, const FastTables&
                 warp_log2cumsum(ws->vec[sp - 1] + GUARD, add2, lane);
                 ++*st_scans;
             } else if (op == FOP_CONV) {
-                *st_chunks += warp_logconv(ws->vec[sp - 2] + GUARD, ws->vec[sp - 1] + GUARD, ws->jstar, lane);
+                *st_chunks += warp_logconv<FRAMED>(ws->vec[sp - 2] + GUARD, ws->vec[sp - 1] + GUARD, ws->jstar, ws->fa, ws->fb, lane);
                 ++*st_convs;
                 --sp;
             } else {  // FOP_ADDD
@@ -132,7 +139,7 @@ __global__ void __launch_bounds__(FAST_THREADS) k_tables_hs(ProblemView pv, Fast
     const float* D = ft.D2 + ((size_t)pcm * Kmax + r) * L;
     for (int t = 0; t < 16; ++t) a[lane + 32 * t] = __ldg(D + (L - 1 - lane - 32 * t));
     warp_load_vec(b, ft.SEL2 + ((size_t)pcm * Kmax + cc) * L, lane);
-    warp_logconv(a, b, ws->jstar, lane);
+    warp_logconv<false>(a, b, ws->jstar, ws->fa, ws->fb, lane);
     float* out = HS2 + (size_t)idx * L;
     for (int t = 0; t < 16; ++t) out[lane + 32 * t] = a[L - 1 - lane - 32 * t] - LOG2_L;
 }
@@ -149,14 +156,16 @@ __device__ __forceinline__ bool rec_better_f(const bamse_record& a, const bamse_
 // cheap trees (few leaves) simply pulls more, and the tail of the launch is one tree long.
 // Each warp keeps a private top-k list in shared memory and appends it to a flat global bag
 // when its parameter set changes and at the end; k_merge_topk reduces the bag.
-__global__ void __launch_bounds__(FAST_THREADS, 7) k_enumerate_fast(ProblemView pv, FastTables ft, EnumWork w) {
+template <bool FRAMED>
+__global__ void __launch_bounds__(FAST_THREADS, FRAMED ? 6 : 7) k_enumerate_fast(ProblemView pv, FastTables ft, EnumWork w) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    WarpSmem* wsm = reinterpret_cast<WarpSmem*>(smem_raw);
-    bamse_record* s_top_all = reinterpret_cast<bamse_record*>(smem_raw + sizeof(WarpSmem) * FAST_WARPS);
+    using WS = WarpSmemT<FRAMED>;
+    WS* wsm = reinterpret_cast<WS*>(smem_raw);
+    bamse_record* s_top_all = reinterpret_cast<bamse_record*>(smem_raw + sizeof(WS) * FAST_WARPS);
     const int t = threadIdx.x, wid = t >> 5;
     int lane = t & 31;
     asm volatile("" : "+r"(lane));
-    WarpSmem* ws = pin_shared(wsm + wid);
+    WS* ws = pin_shared(wsm + wid);
     const int kcap = w.topk > 0 ? w.topk : 1;
     bamse_record* list = s_top_all + wid * kcap;
     warp_init_guards(ws, lane);
@@ -197,7 +206,7 @@ __global__ void __launch_bounds__(FAST_THREADS, 7) k_enumerate_fast(ProblemView 
                 build_program_fast(seg.K, parent, nullptr, &ws->prog, ft.HS2 != nullptr);
             }
             __syncwarp();
-            const double score = warp_eval_tree(pv, ft, seg.p, seg.c, ws, lane, &st_chunks, &st_convs, &st_scans);
+            const double score = warp_eval_tree<FRAMED>(pv, ft, seg.p, seg.c, ws, lane, &st_chunks, &st_convs, &st_scans);
             st_samples += pv.M;
             if (lane == 0) {
                 const double logscre = log((double)ws->prog.scre);
@@ -258,8 +267,9 @@ __global__ void __launch_bounds__(FAST_THREADS, 7) k_enumerate_fast(ProblemView 
     }
 }
 
-static size_t fast_smem_bytes(int topk) {
-    return sizeof(WarpSmem) * FAST_WARPS + sizeof(bamse_record) * FAST_WARPS * (size_t)(topk > 0 ? topk : 1);
+static size_t fast_smem_bytes(int topk, bool framed = false) {
+    return (framed ? sizeof(WarpSmemT<true>) : sizeof(WarpSmemT<false>)) * FAST_WARPS +
+           sizeof(bamse_record) * FAST_WARPS * (size_t)(topk > 0 ? topk : 1);
 }
 
 void launch_tables_hs(const ProblemView& pv, const FastTables& ft, float* HS2, cudaStream_t s) {
@@ -271,17 +281,24 @@ void launch_tables_hs(const ProblemView& pv, const FastTables& ft, float* HS2, c
 
 int enumerate_workers(int precision, int grid) { return precision == BAMSE_FP32 ? grid * FAST_WARPS : grid; }
 
-int enumerate_fast_grid_size(int device, int topk) {
+int enumerate_fast_grid_size(int device, int topk, bool framed) {
     int sms = 148, per_sm = 1;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-    cudaFuncSetAttribute(k_enumerate_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_smem_bytes(BAMSE_TOPK_MAX));
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_enumerate_fast, FAST_THREADS, fast_smem_bytes(topk));
+    if (framed) {
+        cudaFuncSetAttribute(k_enumerate_fast<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_smem_bytes(BAMSE_TOPK_MAX, true));
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_enumerate_fast<true>, FAST_THREADS, fast_smem_bytes(topk, true));
+    } else {
+        cudaFuncSetAttribute(k_enumerate_fast<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_smem_bytes(BAMSE_TOPK_MAX, false));
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_enumerate_fast<false>, FAST_THREADS, fast_smem_bytes(topk, false));
+    }
     if (per_sm < 1) per_sm = 1;
     return sms * per_sm;
 }
 
-void launch_enumerate_fast(const ProblemView& pv, const FastTables& ft, const EnumWork& w, int grid, cudaStream_t s) {
-    k_enumerate_fast<<<grid, FAST_THREADS, fast_smem_bytes(w.topk), s>>>(pv, ft, w);
+void launch_enumerate_fast(const ProblemView& pv, const FastTables& ft, const EnumWork& w, int grid, bool framed,
+                           cudaStream_t s) {
+    if (framed) k_enumerate_fast<true><<<grid, FAST_THREADS, fast_smem_bytes(w.topk, true), s>>>(pv, ft, w);
+    else k_enumerate_fast<false><<<grid, FAST_THREADS, fast_smem_bytes(w.topk, false), s>>>(pv, ft, w);
 }
 
 // ---------------------------------------------------------------------- explicit items (fp32)
@@ -301,7 +318,7 @@ __global__ void __launch_bounds__(FAST_THREADS) k_score_items_fast(ProblemView p
     ok = __shfl_sync(0xffffffffu, ok, 0);
     if (!ok) { if (lane == 0) out[idx] = CUDART_NAN; return; }
     unsigned s0 = 0, s1 = 0, s2 = 0;
-    const double score = warp_eval_tree(pv, ft, it.p, it.c, ws, lane, &s0, &s1, &s2);
+    const double score = warp_eval_tree<false>(pv, ft, it.p, it.c, ws, lane, &s0, &s1, &s2);
     if (lane == 0) out[idx] = score;
 }
 

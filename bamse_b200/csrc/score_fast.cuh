@@ -25,6 +25,12 @@ constexpr int VSTRIDE = GUARD + L + 4;              // floats per vector slot (4
 constexpr int FAST_SLOTS = 3;                       // max live vectors with the in-place convolution (brute-forced, K <= 12)
 constexpr float THETA = 36.0f;                      // window threshold in bits
 constexpr float LOG2_L = 9.0f;                      // log2(512)
+// framed (linear-domain) path of the convolution
+constexpr int FR_B = 64;                            // outputs per framed block (2 per lane)
+constexpr int FR_SEG = 128;                         // j's per framed segment
+constexpr int FR_A = FR_SEG + FR_B;                 // a-window floats of one segment
+constexpr float FR_DEV = 50.0f;                     // allowed deviation of M_x from linear inside a block (bits)
+constexpr float FR_MAXR = 30.0f;                    // a factor above 2^FR_MAXR of the centre aborts the frame
 
 struct FastTables {
     const float* D2;     // [rows][L] log2 of the binomial tables                (clustering.py:20-24)
@@ -324,72 +330,204 @@ __device__ __forceinline__ void conv_accumulate(const float* __restrict__ pa, co
     }
 }
 
+// One pass of the exponential path: outputs 32*pass .. 32*pass+31, lane = output, in place.
+__device__ __forceinline__ void conv_pass_mufu(float* __restrict__ a, const float* __restrict__ b,
+                                               const uint16_t* __restrict__ jstar, int pass, int lane, int& hl, int& hr,
+                                               int& chunks) {
+    const int x0 = 32 * pass;
+    const int x = x0 + lane;
+    const int xmax = x0 + 31;
+    const int js = jstar[x];
+    // j* is non-decreasing inside each 16-output walk of the merge path
+    const int jmin = min((int)jstar[x0], (int)jstar[x0 + 16]);
+    const int jmax = max((int)jstar[x0 + 15], (int)jstar[xmax]);
+    const float mx = a[x - js] + b[js];
+    const float2 nm2 = make_float2(-mx, -mx);
+    float2 acc0 = make_float2(0.f, 0.f), acc1 = acc0, acc2 = acc0, acc3 = acc0;
+    // first guess of the common j-range [jl, je] (4-aligned start, whole chunks); j may run
+    // up to 3 past xmax: b reads its trailing -inf pad there, a[x - j] its -inf guard
+    int jl = max(jmin - hl, 0) & ~3;
+    int n4 = (min(jmax + hr, xmax) - jl + 4) >> 2;
+    int je = jl + 4 * n4 - 1;
+    chunks += n4;
+    conv_accumulate(a + (x - jl), reinterpret_cast<const float4*>(b + jl), n4, nm2, acc0, acc1, acc2, acc3);
+    // the terms of one output are concave in j: if the edge terms of every lane are below
+    // 2^-THETA of its maximum, everything outside the range is too.  Otherwise extend.
+    for (;;) {
+        const bool need = (jl > 0) && (((a[x - jl] - mx) + b[jl]) >= -THETA);
+        if (!__any_sync(0xffffffffu, need)) break;
+        const int j2 = max(jl - max(hl, 8), 0) & ~3;
+        const int m4 = (jl - j2) >> 2;
+        chunks += m4;
+        conv_accumulate(a + (x - j2), reinterpret_cast<const float4*>(b + j2), m4, nm2, acc0, acc1, acc2, acc3);
+        hl += jl - j2;
+        jl = j2;
+    }
+    for (;;) {
+        // lanes with x <= je read the -inf guard here, so they never ask for more
+        const bool need = ((a[x - je] - mx) + b[je]) >= -THETA;
+        if (!__any_sync(0xffffffffu, need) || je >= xmax) break;
+        const int m4 = min((max(hr, 8) + 3) >> 2, ((xmax | 3) - je) >> 2);
+        chunks += m4;
+        conv_accumulate(a + (x - je - 1), reinterpret_cast<const float4*>(b + je + 1), m4, nm2, acc0, acc1, acc2, acc3);
+        hr += 4 * m4;
+        je += 4 * m4;
+    }
+    acc0 = __fadd2_rn(__fadd2_rn(acc0, acc1), __fadd2_rn(acc2, acc3));
+    const float s = acc0.x + acc0.y;
+    // the range always contains the maximising term (2^0 up to the rounding of the shift,
+    // which is relative to |mx|); a sum far outside [1, 2*terms] means M_x was not the
+    // maximum, i.e. the inputs were not log-concave
+    const bool bad = !(s >= 0.7f && s <= 2048.f);
+    if (__any_sync(0xffffffffu, bad)) {
+        warp_logconv_exact_pass(a, b, pass, lane);
+    } else {
+        __syncwarp();                                         // every lane has finished reading a[x0..xmax]
+        a[x] = mx + lg2f(s) - LOG2_L;
+    }
+    // let the windows shrink again (they are re-grown on demand)
+    hl = max(4, hl - (hl >> 2));
+    hr = max(4, hr - (hr >> 2));
+}
+
+// One block of the LINEAR-DOMAIN ("framed") path: outputs 64*q .. 64*q+63, two per lane, in place.
+// Inside a block M_x is close to linear in x.  After removing a common tilt s (a multiple of 1/64, so
+// s * index is exact) and the centre output's maximising factors (ca, cb), every factor that matters
+// fits fp32:  fa[e] = 2^(a[i] - ca - s (i - i0)),  fb[e] = 2^(b[j] - cb - s (j - j0)), and
+// sum_j fa[x-j] fb[j] = 2^-(ca + cb + s (x - xc)) sum_j a[x-j] b[j].  The exponentials are paid once
+// per ELEMENT (~9 per lane and segment) instead of once per TERM, the terms are plain FFMAs with
+// a register-resident sliding window (2 outputs x 4 terms per 2 LDS.64 + 1 broadcast LDS.128).
+// Returns false (warp-uniform, nothing written) when the block does not fit a frame: M_x bends by
+// more than 2^FR_DEV, a factor exceeds 2^FR_MAXR, or the result fails the sanity check; the caller
+// then runs the exponential path on the two halves.
+__device__ __forceinline__ bool conv_block_framed(float* __restrict__ a, const float* __restrict__ b,
+                                                  const uint16_t* __restrict__ jstar, float* __restrict__ fa,
+                                                  float* __restrict__ fb, int q, int lane, int& hl, int& hr,
+                                                  int& chunks) {
+    const int x0 = FR_B * q, xlo = x0 + 2 * lane, xmax = x0 + FR_B - 1;
+    const uint32_t jpair = reinterpret_cast<const uint32_t*>(jstar)[xlo >> 1];
+    const int js0 = (int)(jpair & 0xffffu), js1 = (int)(jpair >> 16);
+    const float mx0 = a[xlo - js0] + b[js0];
+    const float mx1 = a[xlo + 1 - js1] + b[js1];
+    const float mx_c = __shfl_sync(0xffffffffu, mx0, 16);
+    const int j0 = __shfl_sync(0xffffffffu, js0, 16);
+    const int i0 = x0 + 32 - j0;
+    const float s = rintf((__shfl_sync(0xffffffffu, mx1, 31) - __shfl_sync(0xffffffffu, mx0, 0)) * (64.0f / 63.0f)) *
+                    (1.0f / 64.0f);
+    const float dev0 = mx0 - fmaf(s, (float)(2 * lane - 32), mx_c);      // M_x minus its linear model
+    const float dev1 = mx1 - fmaf(s, (float)(2 * lane - 31), mx_c);
+    if (__any_sync(0xffffffffu, !(fabsf(dev0) <= FR_DEV && fabsf(dev1) <= FR_DEV)) || !(fabsf(s) < 256.f)) return false;
+    const float ca = a[i0], cb = b[j0];                       // ca + cb == mx_c: the centre's best term is 2^0
+    const int jmin = __reduce_min_sync(0xffffffffu, min(js0, js1));
+    const int jmax = __reduce_max_sync(0xffffffffu, max(js0, js1));
+    int jl = max(jmin - hl, 0) & ~3;
+    int n4 = (min(jmax + hr, xmax) - jl + 4) >> 2;
+    int je = jl + 4 * n4 - 1;
+    float f00 = 0.f, f01 = 0.f, f10 = 0.f, f11 = 0.f;
+    int my_chunks = 0;
+    int seg_j0 = jl, seg_m4 = n4, phase = 0;
+#pragma unroll 1
+    for (;;) {
+        my_chunks += 2 * seg_m4;
+#pragma unroll 1
+        for (int o = 0; o < seg_m4; o += FR_SEG / 4) {
+            const int mm = min(FR_SEG / 4, seg_m4 - o);
+            const int j0s = seg_j0 + 4 * o, nb = 4 * mm;
+            const int i_lo = x0 - (j0s + nb - 1);
+            bool over = false;
+#pragma unroll
+            for (int k = 0; k < FR_SEG / 32; ++k) {
+                const int e = lane + 32 * k;
+                if (e < nb) {
+                    const int j = j0s + e;
+                    const float r = fmaf(-s, (float)(j - j0), b[j] - cb);
+                    over |= r > FR_MAXR;
+                    fb[e] = ex2f(r);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < FR_A / 32; ++k) {
+                const int e = lane + 32 * k;
+                if (e < nb + FR_B - 1) {
+                    const int i = i_lo + e;                   // may be below -GUARD: a 64-wide block reaches 66 back
+                    const float r = fmaf(-s, (float)(i - i0), a[max(i, -GUARD)] - ca);
+                    over |= r > FR_MAXR;
+                    fa[e] = ex2f(r);
+                }
+            }
+            if (__any_sync(0xffffffffu, over)) return false;
+            __syncwarp();
+            // sliding window: output lo at j uses fa[E - (j - j0s)], E = 2 lane + nb - 1; output hi the next one
+            const float* pw = fa + 2 * lane + nb - 4;         // &fa[E - 3], even index
+            float w1 = pw[1], w2 = pw[2], w3 = pw[3], w4 = pw[4], w0 = pw[0];
+            const float4* pB = reinterpret_cast<const float4*>(fb);
+#pragma unroll 2
+            for (int c = 0; c < mm; ++c) {
+                const float4 bv = pB[c];
+                // lo: fa[E]*b0 + fa[E-1]*b1 + fa[E-2]*b2 + fa[E-3]*b3 ; hi: fa[E+1]*b0 + fa[E]*b1 + ...
+                f00 = fmaf(w3, bv.x, f00); f10 = fmaf(w4, bv.x, f10);
+                f01 = fmaf(w2, bv.y, f01); f11 = fmaf(w3, bv.y, f11);
+                f00 = fmaf(w1, bv.z, f00); f10 = fmaf(w2, bv.z, f10);
+                f01 = fmaf(w0, bv.w, f01); f11 = fmaf(w1, bv.w, f11);
+                pw -= 4;
+                w4 = w0;
+                const float2 u = *reinterpret_cast<const float2*>(pw);        // fa[E-7], fa[E-6]
+                const float2 v = *reinterpret_cast<const float2*>(pw + 2);    // fa[E-5], fa[E-4]
+                w0 = u.x; w1 = u.y; w2 = v.x; w3 = v.y;
+            }
+            __syncwarp();                                     // scratch is reused by the next segment
+        }
+        if (phase == 0) {
+            const bool need = (jl > 0) && ((((a[xlo - jl] - mx0) + b[jl]) >= -THETA) ||
+                                           (((a[xlo + 1 - jl] - mx1) + b[jl]) >= -THETA));   // jl <= j* <= xlo
+            if (__any_sync(0xffffffffu, need)) {
+                const int j2 = max(jl - max(hl, 8), 0) & ~3;
+                seg_j0 = j2; seg_m4 = (jl - j2) >> 2;
+                hl += jl - j2;
+                jl = j2;
+                continue;
+            }
+            phase = 1;
+        }
+        // lanes whose outputs end before je read the -inf guard here, so they never ask for more
+        const bool need = (((a[max(xlo - je, -GUARD)] - mx0) + b[je]) >= -THETA) ||
+                          (((a[max(xlo + 1 - je, -GUARD)] - mx1) + b[je]) >= -THETA);
+        if (!__any_sync(0xffffffffu, need) || je >= xmax) break;
+        seg_m4 = min((max(hr, 8) + 3) >> 2, ((xmax | 3) - je) >> 2);
+        seg_j0 = je + 1;
+        hr += 4 * seg_m4;
+        je += 4 * seg_m4;
+    }
+    // framed sums are relative to 2^(mx_c + s (x - xc)); bring them to 2^mx
+    const float s0 = (f00 + f01) * ex2f(-dev0), s1 = (f10 + f11) * ex2f(-dev1);
+    const bool bad = !(s0 >= 0.7f && s0 <= 2048.f && s1 >= 0.7f && s1 <= 2048.f);
+    if (__any_sync(0xffffffffu, bad)) return false;
+    __syncwarp();                                             // every lane has finished reading a[x0..xmax]
+    *reinterpret_cast<float2*>(a + xlo) = make_float2(mx0 + lg2f(s0) - LOG2_L, mx1 + lg2f(s1) - LOG2_L);
+    chunks += my_chunks;
+    hl = max(4, hl - (hl >> 2));
+    hr = max(4, hr - (hr >> 2));
+    return true;
+}
+
 // IN PLACE: a[x] <- log2( sum_{j<=x} 2^(a[x-j] + b[j]) ) - log2 L          (clustering.py:365-370)
 // a, b: distinct shared-memory vectors, each with GUARD -inf floats in front and 4 behind.
-// Passes run from the highest outputs down: output x only needs a[i], i <= x, so the 32
-// finished outputs of a pass can overwrite a[x] once the pass has read everything it needs.
-// Returns the number of 4-term chunks executed per lane (executed-op statistics).
+// Blocks run from the highest outputs down: output x only needs a[i], i <= x, so finished
+// outputs can overwrite a[x] once their block has read everything it needs.
+// fa / fb: per-warp scratch (FR_A / FR_SEG floats) of the framed path; FRAMED = false compiles
+// the exponential path only.  Returns the number of 4-term chunks executed per lane.
+template <bool FRAMED>
 __device__ inline int warp_logconv(float* __restrict__ a, const float* __restrict__ b,
-                                   uint16_t* __restrict__ jstar, int lane) {
+                                   uint16_t* __restrict__ jstar, float* __restrict__ fa, float* __restrict__ fb,
+                                   int lane) {
     warp_merge_path(a, b, jstar, lane);
     int chunks = 0;
-    int hl = 8, hr = 8;                                       // window half-widths, adapted pass to pass
+    int hl = 8, hr = 8;                                       // window half-widths, adapted block to block
 #pragma unroll 1
-    for (int pass = L / 32 - 1; pass >= 0; --pass) {
-        const int x0 = 32 * pass;
-        const int x = x0 + lane;
-        const int xmax = x0 + 31;
-        const int js = jstar[x];
-        // j* is non-decreasing inside each 16-output walk of the merge path
-        const int jmin = min((int)jstar[x0], (int)jstar[x0 + 16]);
-        const int jmax = max((int)jstar[x0 + 15], (int)jstar[xmax]);
-        const float mx = a[x - js] + b[js];
-        const float2 nm2 = make_float2(-mx, -mx);
-        float2 acc0 = make_float2(0.f, 0.f), acc1 = acc0, acc2 = acc0, acc3 = acc0;
-        // first guess of the common j-range [jl, je] (4-aligned start, whole chunks); j may run
-        // up to 3 past xmax: b reads its trailing -inf pad there, a[x - j] its -inf guard
-        int jl = max(jmin - hl, 0) & ~3;
-        int n4 = (min(jmax + hr, xmax) - jl + 4) >> 2;
-        int je = jl + 4 * n4 - 1;
-        chunks += n4;
-        conv_accumulate(a + (x - jl), reinterpret_cast<const float4*>(b + jl), n4, nm2, acc0, acc1, acc2, acc3);
-        // the terms of one output are concave in j: if the edge terms of every lane are below
-        // 2^-THETA of its maximum, everything outside the range is too.  Otherwise extend.
-        for (;;) {
-            const bool need = (jl > 0) && (((a[x - jl] - mx) + b[jl]) >= -THETA);
-            if (!__any_sync(0xffffffffu, need)) break;
-            const int j2 = max(jl - max(hl, 8), 0) & ~3;
-            const int m4 = (jl - j2) >> 2;
-            chunks += m4;
-            conv_accumulate(a + (x - j2), reinterpret_cast<const float4*>(b + j2), m4, nm2, acc0, acc1, acc2, acc3);
-            hl += jl - j2;
-            jl = j2;
-        }
-        for (;;) {
-            // lanes with x <= je read the -inf guard here, so they never ask for more
-            const bool need = ((a[x - je] - mx) + b[je]) >= -THETA;
-            if (!__any_sync(0xffffffffu, need) || je >= xmax) break;
-            const int m4 = min((max(hr, 8) + 3) >> 2, ((xmax | 3) - je) >> 2);
-            chunks += m4;
-            conv_accumulate(a + (x - je - 1), reinterpret_cast<const float4*>(b + je + 1), m4, nm2, acc0, acc1, acc2, acc3);
-            hr += 4 * m4;
-            je += 4 * m4;
-        }
-        acc0 = __fadd2_rn(__fadd2_rn(acc0, acc1), __fadd2_rn(acc2, acc3));
-        const float s = acc0.x + acc0.y;
-        // the range always contains the maximising term (2^0 up to the rounding of the shift,
-        // which is relative to |mx|); a sum far outside [1, 2*terms] means M_x was not the
-        // maximum, i.e. the inputs were not log-concave
-        const bool bad = !(s >= 0.7f && s <= 2048.f);
-        if (__any_sync(0xffffffffu, bad)) {
-            warp_logconv_exact_pass(a, b, pass, lane);
-        } else {
-            __syncwarp();                                     // every lane has finished reading a[x0..xmax]
-            a[x] = mx + lg2f(s) - LOG2_L;
-        }
-        // let the windows shrink again (they are re-grown on demand)
-        hl = max(4, hl - (hl >> 2));
-        hr = max(4, hr - (hr >> 2));
+    for (int q = L / FR_B - 1; q >= 0; --q) {
+        if (FRAMED && conv_block_framed(a, b, jstar, fa, fb, q, lane, hl, hr, chunks)) continue;
+#pragma unroll 1
+        for (int h = 1; h >= 0; --h) conv_pass_mufu(a, b, jstar, 2 * q + h, lane, hl, hr, chunks);
     }
     __syncwarp();
     return chunks;

@@ -92,12 +92,14 @@ def _pack(Kmax, items):
     return clust, par, nod
 
 
+@pytest.mark.parametrize("framed", ["0", "1"])
 @pytest.mark.parametrize("cov", [0, 3, 40, 2000, 60000, 5000000])
-def test_fp32_kernel_over_the_dynamic_range(ctx, shim, cov):
+def test_fp32_kernel_over_the_dynamic_range(ctx, shim, cov, framed, monkeypatch):
     """from empty / nearly flat tables (every term of a convolution matters) to 5e6 reads per
     cluster (peaks far narrower than a grid cell, steps of thousands of nats): the fp32
     production kernel stays within 1e-6 of the fp64 check mode on every tree of K = 4, and the
     check mode agrees with the numpy oracle."""
+    monkeypatch.setenv("BAMSE_FRAMED", framed)      # both instantiations of the fp32 kernel
     rng = np.random.default_rng(cov + 1)
     K, M = 4, 3
     prev = np.array([[0.9, 0.8, 0.95], [0.5, 0.1, 0.6], [0.3, 0.6, 0.02], [0.1, 0.05, 0.3]])
@@ -117,6 +119,33 @@ def test_fp32_kernel_over_the_dynamic_range(ctx, shim, cov):
     for i in (0, 7, 21, 42, 63):
         want = orc.tree_score_samples(orc.decode_tree(K, i), D, orc.prior_const(K)).sum()
         assert s64[i] == pytest.approx(want, rel=1e-10, abs=1e-12)
+
+
+def test_framed_variant_on_a_whole_clustering(ctx, shim, monkeypatch):
+    """all 7776 trees of a K = 6 clustering with flat-ish tables (where the framed path is used for
+    most blocks): framed and exponential instantiations agree with each other to fp32 accuracy and
+    return the same top-k (fp64 re-scored) as the check mode."""
+    rng = np.random.default_rng(123)
+    K, M = 6, 4
+    frac = np.sort(rng.dirichlet(np.ones(K + 1))[:K])[::-1]
+    cm = np.clip(np.cumsum(frac[::-1])[::-1][:, None] * rng.uniform(0.6, 1.0, size=(K, M)), 0, 1)
+    As = rng.binomial(150, cm * 0.497 + 0.003)
+    Bs = 150 - As
+    out = {}
+    for framed in ("0", "1"):
+        monkeypatch.setenv("BAMSE_FRAMED", framed)
+        ctx.upload_problem([0.003], [K], As[None], Bs[None])
+        out[framed] = (ctx.score_range(0, 0, 0, K ** (K - 1), shim.FP32)[0],
+                       ctx.score_topk(np.zeros((1, 1)), topk=8, precision=shim.FP32)[0])
+    monkeypatch.delenv("BAMSE_FRAMED")
+    np.testing.assert_allclose(out["1"][0], out["0"][0], rtol=5e-7)
+    ctx.upload_problem([0.003], [K], As[None], Bs[None])
+    ref, _, _ = ctx.score_topk(np.zeros((1, 1)), topk=8, precision=shim.FP64)
+    for framed in ("0", "1"):
+        assert out[framed][1]["tree"].tolist() == ref["tree"].tolist()
+        np.testing.assert_allclose(out[framed][1]["total"], ref["total"], rtol=1e-10)
+    s64 = ctx.score_range(0, 0, 0, 1000, shim.FP64)[0]
+    np.testing.assert_allclose(out["1"][0][:1000], s64, rtol=1e-6)
 
 
 def test_large_shapes_fp32_vs_check_mode(ctx, shim):
