@@ -167,6 +167,8 @@ int bamse_set_shard(bamse_ctx* ctx, int rank, int world) {
     return BAMSE_OK;
 }
 
+int bamse_fast_variant(const bamse_ctx* ctx) { return ctx ? ctx->use_framed : -1; }
+
 int64_t bamse_launch_count(const bamse_ctx* ctx) { return ctx ? ctx->launches : 0; }
 int64_t bamse_last_eval_count(const bamse_ctx* ctx) { return ctx ? ctx->last_evals : 0; }
 
@@ -309,8 +311,10 @@ int bamse_upload_problem(bamse_ctx* ctx, int P, const double* err, int C, int M,
 static int score_items_host(bamse_ctx* ctx, const std::vector<ScoreItem>& items, int precision, double* out) {
     const size_t n = items.size();
     if (n == 0) return BAMSE_OK;
+    // the log-domain kernels return one value per (item, sample); the fp32 production kernel one per item
+    const size_t per = precision == BAMSE_FP32 ? 1 : (size_t)ctx->M;
     BAMSE_CUDA_TRY(ctx, ctx->d_items.ensure(sizeof(ScoreItem) * n));
-    BAMSE_CUDA_TRY(ctx, ctx->d_scores.ensure(sizeof(double) * n));
+    BAMSE_CUDA_TRY(ctx, ctx->d_scores.ensure(sizeof(double) * n * per));
     cudaStream_t s = ctx->stream;
     BAMSE_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_items.p, items.data(), sizeof(ScoreItem) * n, cudaMemcpyHostToDevice, s));
     if (precision == BAMSE_FP32)
@@ -319,8 +323,19 @@ static int score_items_host(bamse_ctx* ctx, const std::vector<ScoreItem>& items,
         launch_score_items(precision, ctx->view(), ctx->d_items.as<ScoreItem>(), (int64_t)n, ctx->d_scores.as<double>(), s);
     ctx->launches++;
     BAMSE_CUDA_TRY(ctx, cudaGetLastError());
-    BAMSE_CUDA_TRY(ctx, cudaMemcpyAsync(out, ctx->d_scores.p, sizeof(double) * n, cudaMemcpyDeviceToHost, s));
-    BAMSE_CUDA_TRY(ctx, cudaStreamSynchronize(s));
+    if (per == 1) {
+        BAMSE_CUDA_TRY(ctx, cudaMemcpyAsync(out, ctx->d_scores.p, sizeof(double) * n, cudaMemcpyDeviceToHost, s));
+        BAMSE_CUDA_TRY(ctx, cudaStreamSynchronize(s));
+    } else {
+        std::vector<double> part(n * per);
+        BAMSE_CUDA_TRY(ctx, cudaMemcpyAsync(part.data(), ctx->d_scores.p, sizeof(double) * n * per, cudaMemcpyDeviceToHost, s));
+        BAMSE_CUDA_TRY(ctx, cudaStreamSynchronize(s));
+        for (size_t i = 0; i < n; ++i) {              // np.sum over samples (clustering.py:89), in sample order
+            double t = 0.0;
+            for (size_t m = 0; m < per; ++m) t += part[i * per + m];
+            out[i] = t;
+        }
+    }
     return BAMSE_OK;
 }
 

@@ -205,24 +205,27 @@ __global__ void __launch_bounds__(LD_THREADS) k_score_items_logdomain(ProblemVie
     __shared__ T scratch[LD_THREADS / 32];
     __shared__ TreeProgram prog;
     __shared__ int s_ok;
+    // grid = (items, samples): one CTA per (item, sample) so that a short list (the fp64 re-score of
+    // the fp32 selection) still fills the GPU; the host adds the per-sample values in sample order
     const ScoreItem it = items[blockIdx.x];
+    const int m = blockIdx.y;
     if (threadIdx.x == 0) s_ok = build_program(it.k, it.parent, it.nodes, &prog) ? 1 : 0;
     __syncthreads();
     if (!s_ok) {
-        if (threadIdx.x == 0) out[blockIdx.x] = CUDART_NAN;
+        if (threadIdx.x == 0) out[(size_t)blockIdx.x * pv.M + m] = CUDART_NAN;
         return;
     }
-    const double score = eval_tree_logdomain<T>(pv, it.p, it.c, &prog, pool, scratch);
-    if (threadIdx.x == 0) out[blockIdx.x] = score;
+    const double score = eval_tree_logdomain<T>(pv, it.p, it.c, &prog, pool, scratch, m, m + 1);
+    if (threadIdx.x == 0) out[(size_t)blockIdx.x * pv.M + m] = score;
 }
 
 void launch_score_items(int precision, const ProblemView& pv, const ScoreItem* d_items, int64_t n, double* d_out,
                         cudaStream_t s) {
     if (n <= 0) return;
     if (precision == BAMSE_FP64)
-        k_score_items_logdomain<double><<<(unsigned)n, LD_THREADS, pool_bytes<double>(), s>>>(pv, d_items, d_out);
+        k_score_items_logdomain<double><<<dim3((unsigned)n, pv.M), LD_THREADS, pool_bytes<double>(), s>>>(pv, d_items, d_out);
     else
-        k_score_items_logdomain<float><<<(unsigned)n, LD_THREADS, pool_bytes<float>(), s>>>(pv, d_items, d_out);
+        k_score_items_logdomain<float><<<dim3((unsigned)n, pv.M), LD_THREADS, pool_bytes<float>(), s>>>(pv, d_items, d_out);
 }
 
 // ------------------------------------------------------------------------ merge

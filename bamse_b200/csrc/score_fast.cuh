@@ -23,7 +23,8 @@ constexpr int FAST_THREADS = FAST_WARPS * 32;
 constexpr int GUARD = 36;                           // -inf floats in front of every vector (a[x-j], j <= xmax+3)
 constexpr int VSTRIDE = GUARD + L + 4;              // floats per vector slot (4 trailing -inf: b[j], j <= 514)
 constexpr int FAST_SLOTS = 3;                       // max live vectors with the in-place convolution (brute-forced, K <= 12)
-constexpr float THETA = 36.0f;                      // window threshold in bits
+constexpr float THETA = 30.0f;                      // window threshold in bits: terms below 2^-30 of an output's
+                                                    // maximum are dropped (<= 512 of them, decaying: < 2^-22 relative)
 constexpr float LOG2_L = 9.0f;                      // log2(512)
 // framed (linear-domain) path of the convolution
 constexpr int FR_B = 64;                            // outputs per framed block (2 per lane)

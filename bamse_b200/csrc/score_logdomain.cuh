@@ -120,13 +120,15 @@ template <> struct TableSel<float> { static __device__ const float* get(const Pr
 // in every thread.
 template <typename T>
 __device__ double eval_tree_logdomain(const ProblemView& pv, int p, int c, const TreeProgram* prog,
-                                      T* pool /* [MAX_STACK][L] */, T* scratch /* [LD_THREADS/32] */) {
+                                      T* pool /* [MAX_STACK][L] */, T* scratch /* [LD_THREADS/32] */,
+                                      int m_begin = 0, int m_end = -1) {
     const int t = threadIdx.x;
     const T log_len = (T)6.2383246250395077847550890931236;  // log(512)
     const T add = (T)pv.p0[c] - log_len;
     const T* table = TableSel<T>::get(pv);
     double total = 0.0;
-    for (int m = 0; m < pv.M; ++m) {
+    if (m_end < 0) m_end = pv.M;
+    for (int m = m_begin; m < m_end; ++m) {
         const T* D = table + pv.table_offset(p, c, m);
         // slot indirection: stack position i lives in pool slot (slots >> 4i) & 15
         uint64_t slots = 0x876543210ull;

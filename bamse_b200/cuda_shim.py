@@ -54,6 +54,8 @@ def load_library():
     lib.bamse_set_stream.argtypes = [c_p, c_p]
     lib.bamse_set_shard.restype = i32
     lib.bamse_set_shard.argtypes = [c_p, i32, i32]
+    lib.bamse_fast_variant.restype = i32
+    lib.bamse_fast_variant.argtypes = [c_p]
     lib.bamse_launch_count.restype = i64
     lib.bamse_launch_count.argtypes = [c_p]
     lib.bamse_last_eval_count.restype = i64
@@ -83,7 +85,7 @@ def load_library():
 
 
 EXPORTED_SYMBOLS = [
-    "bamse_abi_version", "bamse_create", "bamse_destroy", "bamse_last_error", "bamse_set_stream", "bamse_set_shard",
+    "bamse_abi_version", "bamse_create", "bamse_destroy", "bamse_last_error", "bamse_set_stream", "bamse_set_shard", "bamse_fast_variant",
     "bamse_launch_count", "bamse_last_eval_count", "bamse_decode_tree", "bamse_upload_problem",
     "bamse_score_list", "bamse_score_range", "bamse_score_topk", "bamse_enumerate_topk_dev",
     "bamse_merge_topk_dev", "bamse_kernel_time", "bamse_kernel_stats",
@@ -146,6 +148,11 @@ class Context(object):
     def set_shard(self, rank, world):
         """interleaved multi-GPU sharding of every enumeration of this context."""
         self._check(self._lib.bamse_set_shard(self._h, int(rank), int(world)))
+
+    @property
+    def fast_variant(self):
+        """0 = exponential-path kernel, 1 = kernel with the framed path, -1 = undecided."""
+        return int(self._lib.bamse_fast_variant(self._h))
 
     @property
     def launch_count(self):

@@ -360,6 +360,7 @@ def main():
     ms = ev0.elapsed_time(ev1)
     kern_ms, kern_n = ctx.kernel_time(reset=True)
     stats = ctx.kernel_stats(reset=True)
+    variant = ctx.fast_variant
     launches = ctx.launch_count - launches0
     t = torch.tensor([ms, kern_ms / max(1, kern_n)], dtype=torch.float64, device=dev)
     if world > 1:
@@ -421,7 +422,7 @@ def main():
             kname, executed = "k_enumerate_logdomain<double>", None
         else:
             bound, achieved, peak, unit = "xu (MUFU ex2/lg2)", xu / kernel_s / 1e12, peaks["xu_tops"], "Tops/s"
-            kname = "k_enumerate_fast"
+            kname = "k_enumerate_fast<framed=%s>" % ("true" if variant == 1 else "false")
             ex = stats["mufu_ops"] / max(1, kern_n) / kernel_s / 1e12     # this rank's executed MUFU ops per second
             executed = {"xu_tops": ex, "xu_pipe_frac": ex / peaks["xu_tops"],
                         "conv_terms_executed_per_launch": stats["conv_terms"] / max(1, kern_n),

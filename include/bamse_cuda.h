@@ -75,6 +75,10 @@ int bamse_set_stream(bamse_ctx* ctx, void* cuda_stream);
  * so that every rank sees the same mix of tree shapes).  Default (0, 1) = everything.
  * bamse_score_range is not affected. */
 int bamse_set_shard(bamse_ctx* ctx, int rank, int world);
+/* Which instantiation of the fp32 enumeration kernel the resident problem uses: 0 = exponential
+ * (MUFU) path only, 1 = with the linear-domain "framed" path, -1 = not decided yet.  Decided by a
+ * ~1 ms timing probe on the first enumeration of a problem (BAMSE_FRAMED=0/1 overrides). */
+int bamse_fast_variant(const bamse_ctx* ctx);
 /* Number of kernels this ctx has launched since creation (for bench.py `gpu_launches`). */
 int64_t bamse_launch_count(const bamse_ctx* ctx);
 
