@@ -51,7 +51,7 @@ struct bamse_ctx {
 
     // work buffers
     DBuf d_segs, d_scalars /* total_chunks, total_trees, next_chunk */, d_cand, d_items, d_scores;
-    DBuf d_const, d_thr, d_begin, d_end, d_records, d_dense0, d_dense1;
+    DBuf d_const, d_thr, d_begin, d_end, d_records, d_dense0, d_dense1, d_pb, d_pe;
     int grid[3] = {0, 0, 0};
     int shard_rank = 0, shard_world = 1;
     int use_framed = -1;     // fp32 kernel variant for the resident problem: -1 not probed yet, 0 exponential, 1 framed
@@ -146,7 +146,7 @@ void bamse_destroy(bamse_ctx* ctx) {
     DBuf* bufs[] = {&ctx->d_K, &ctx->d_p0, &ctx->d_var, &ctx->d_ref, &ctx->d_logc, &ctx->d_logcf, &ctx->d_log1mcf,
                     &ctx->d_D64, &ctx->d_D32, &ctx->d_D2, &ctx->d_EL2, &ctx->d_SEL2, &ctx->d_SD2, &ctx->d_HS2, &ctx->d_segs, &ctx->d_scalars, &ctx->d_cand, &ctx->d_items,
                     &ctx->d_scores, &ctx->d_const, &ctx->d_thr, &ctx->d_begin, &ctx->d_end, &ctx->d_records,
-                    &ctx->d_dense0, &ctx->d_dense1};
+                    &ctx->d_dense0, &ctx->d_dense1, &ctx->d_pb, &ctx->d_pe};
     for (DBuf* b : bufs) b->release();
     for (auto* v : {&ctx->ev_used, &ctx->ev_free})
         for (auto& ev : *v) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
@@ -384,40 +384,51 @@ static int enumerate_dev(bamse_ctx* ctx, const double* d_const, const double* d_
 // also carries the linear-domain "framed" path (6 CTAs/SM), which wins when the tables are flat
 // (low coverage: most terms of a convolution matter) and loses on sharply peaked tables.  Which one
 // is faster is a property of the data, so it is measured once per problem on <= 8192 trees of the
-// largest clustering (~1-2 ms) and remembered.  BAMSE_FRAMED=0/1 in the environment overrides.
+// sample of 8 192 - 40 000 trees (a few ms; only for problems of >= 50 000 trees) and remembered.  BAMSE_FRAMED=0/1 in the environment overrides.
 static int probe_fast_variant(bamse_ctx* ctx) {
     if (const char* f = getenv("BAMSE_FRAMED")) { ctx->use_framed = atoi(f) ? 1 : 0; return BAMSE_OK; }
-    int cbest = 0;
-    for (int c = 1; c < ctx->C; ++c) if (ctx->K_of_c[c] > ctx->K_of_c[cbest]) cbest = c;
-    const int K = ctx->K_of_c[cbest];
-    const uint64_t T = ipow_u64(K, K - 1);
-    Segment seg;
-    memset(&seg, 0, sizeof seg);
-    seg.p = 0; seg.c = cbest; seg.K = K;
-    seg.n_trees = std::min<uint64_t>(T, 8192);
-    seg.stride = (int32_t)std::min<uint64_t>(std::max<uint64_t>(1, T / seg.n_trees), 1u << 30);
-    seg.tree_begin = 0; seg.first_chunk = 0; seg.clust_const = 0.0; seg.threshold = -INFINITY;
+    const int P = ctx->P, C = ctx->C;
+    uint64_t total = 0;
+    for (int c = 0; c < C; ++c) total += ipow_u64(ctx->K_of_c[c], ctx->K_of_c[c] - 1);
+    total *= (uint64_t)P;
+    // small problems: a probe would cost more than it can save -- exponential instantiation
+    if (total < 50000) { ctx->use_framed = 0; return BAMSE_OK; }
+    // sample: the first `quota` trees of every clustering, total/8 but 8 192 .. 40 000 trees in all --
+    // enough to fill every warp slot of the GPU several times (a shorter run measures latency, not
+    // throughput) while both timed runs together cost at most a quarter of one full enumeration
+    const uint64_t sample = std::min<uint64_t>(40000, std::max<uint64_t>(8192, total / 8));
+    const uint64_t quota = std::max<uint64_t>(16, sample / ((uint64_t)P * C) + 1);
+    std::vector<uint64_t> b(C, 0), e(C);
+    for (int c = 0; c < C; ++c) e[c] = std::min<uint64_t>(ipow_u64(ctx->K_of_c[c], ctx->K_of_c[c] - 1), quota);
+    BAMSE_CUDA_TRY(ctx, ctx->d_pb.ensure(sizeof(uint64_t) * C));
+    BAMSE_CUDA_TRY(ctx, ctx->d_pe.ensure(sizeof(uint64_t) * C));
+    BAMSE_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_pb.p, b.data(), sizeof(uint64_t) * C, cudaMemcpyHostToDevice, ctx->stream));
+    BAMSE_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_pe.p, e.data(), sizeof(uint64_t) * C, cudaMemcpyHostToDevice, ctx->stream));
+    BAMSE_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    const int save_rank = ctx->shard_rank, save_world = ctx->shard_world;
+    ctx->shard_rank = 0; ctx->shard_world = 1;
     ctx->probing = true;
     float best_ms = 0.f;
-    int best = 0;
-    for (int v = 0; v < 2; ++v) {
+    int best = 0, rc = BAMSE_OK;
+    for (int v = 0; v < 2 && rc == BAMSE_OK; ++v) {
         ctx->use_framed = v;
-        int rc = enumerate_dev(ctx, nullptr, nullptr, nullptr, nullptr, 0, BAMSE_FP32, 0.0, 0.0, nullptr, nullptr,
-                               nullptr, &seg);
-        if (rc) { ctx->probing = false; ctx->use_framed = 0; return rc; }
-        BAMSE_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        rc = enumerate_dev(ctx, nullptr, nullptr, ctx->d_pb.as<uint64_t>(), ctx->d_pe.as<uint64_t>(), 0, BAMSE_FP32, 0.0,
+                           0.0, nullptr, nullptr, nullptr, nullptr);
+        if (rc) break;
+        if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) { rc = ctx->fail(BAMSE_ECUDA, "probe: stream sync failed"); break; }
         auto ev = ctx->ev_used.back();
         ctx->ev_used.pop_back();
         ctx->ev_free.push_back(ev);
         float ms = 0.f;
-        BAMSE_CUDA_TRY(ctx, cudaEventElapsedTime(&ms, ev.first, ev.second));
+        cudaEventElapsedTime(&ms, ev.first, ev.second);
         if (v == 0 || ms < best_ms) { best_ms = ms; best = v; }
     }
     ctx->probing = false;
+    ctx->shard_rank = save_rank; ctx->shard_world = save_world;
+    if (rc) { ctx->use_framed = 0; return rc; }
     ctx->use_framed = best;
     ctx->probed_choice = best;
     ctx->probed_sig = ctx->problem_sig;
-    ctx->launches -= 0;   // probe launches stay counted: they are real launches of our kernels
     // probe work must not appear in the executed-op statistics of the caller
     BAMSE_CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_scalars.as<uint64_t>() + 4, 0, sizeof(uint64_t) * 4, ctx->stream));
     return BAMSE_OK;

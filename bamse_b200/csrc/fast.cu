@@ -47,6 +47,14 @@ void launch_tables_fast(const ProblemView& pv, float* D2, float* EL2, float* SEL
     k_tables_fast<<<rows, LD_THREADS, 0, s>>>(pv, D2, EL2, SEL2, SD2);
 }
 
+// Index -> program: executed by one lane once per tree.  Kept out of line so that its (large, fully
+// unrolled) code does not sit between the hot loops in the instruction cache.
+static __device__ __noinline__ void build_tree_program(int K, uint64_t tree, TreeProgram* prog, bool root_tables) {
+    int8_t parent[KMAX];
+    decode_tree(K, tree, parent);
+    build_program_fast(K, parent, nullptr, prog, root_tables);
+}
+
 // ------------------------------------------------------------------ per-warp evaluation
 template <bool FRAMED>
 struct alignas(16) WarpSmemT {
@@ -200,11 +208,7 @@ __global__ void __launch_bounds__(FAST_THREADS, FRAMED ? 6 : 7) k_enumerate_fast
         const int n = remain < (uint64_t)w.chunk ? (int)remain : w.chunk;
         for (int i = 0; i < n; ++i) {
             const uint64_t tree = seg.tree_begin + (off + i) * (uint64_t)seg.stride;
-            if (lane == 0) {
-                int8_t parent[KMAX];
-                decode_tree(seg.K, tree, parent);
-                build_program_fast(seg.K, parent, nullptr, &ws->prog, ft.HS2 != nullptr);
-            }
+            if (lane == 0) build_tree_program(seg.K, tree, &ws->prog, ft.HS2 != nullptr);
             __syncwarp();
             const double score = warp_eval_tree<FRAMED>(pv, ft, seg.p, seg.c, ws, lane, &st_chunks, &st_convs, &st_scans);
             st_samples += pv.M;

@@ -436,7 +436,7 @@ __device__ __forceinline__ bool conv_block_framed(float* __restrict__ a, const f
             const int j0s = seg_j0 + 4 * o, nb = 4 * mm;
             const int i_lo = x0 - (j0s + nb - 1);
             bool over = false;
-#pragma unroll
+#pragma unroll 1
             for (int k = 0; k < FR_SEG / 32; ++k) {
                 const int e = lane + 32 * k;
                 if (e < nb) {
@@ -446,7 +446,7 @@ __device__ __forceinline__ bool conv_block_framed(float* __restrict__ a, const f
                     fb[e] = ex2f(r);
                 }
             }
-#pragma unroll
+#pragma unroll 1
             for (int k = 0; k < FR_A / 32; ++k) {
                 const int e = lane + 32 * k;
                 if (e < nb + FR_B - 1) {
