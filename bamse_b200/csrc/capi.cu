@@ -46,8 +46,8 @@ struct bamse_ctx {
     bool have_problem = false;
     int P = 0, C = 0, M = 0, Kmax = 0;
     std::vector<int32_t> K_of_c;
-    DBuf d_K, d_p0, d_var, d_ref, d_logc, d_logcf, d_log1mcf, d_D64, d_D32, d_D2, d_EL2, d_SEL2, d_SD2, d_HS2;
-    bool root_tables = false;
+    DBuf d_K, d_p0, d_var, d_ref, d_logc, d_logcf, d_log1mcf, d_D64, d_D32, d_D2, d_EL2, d_SEL2, d_SD2, d_HS2, d_PSE2, d_PEE2;
+    bool root_tables = false, pair_tables = false;
 
     // work buffers
     DBuf d_segs, d_scalars /* total_chunks, total_trees, next_chunk */, d_cand, d_items, d_scores;
@@ -73,6 +73,7 @@ struct bamse_ctx {
         FastTables f;
         f.D2 = d_D2.as<float>(); f.EL2 = d_EL2.as<float>(); f.SEL2 = d_SEL2.as<float>();
         f.SD2 = root_tables ? d_SD2.as<float>() : nullptr; f.HS2 = root_tables ? d_HS2.as<float>() : nullptr;
+        f.PSE2 = pair_tables ? d_PSE2.as<float>() : nullptr; f.PEE2 = pair_tables ? d_PEE2.as<float>() : nullptr;
         return f;
     }
     ProblemView view() const {
@@ -144,7 +145,7 @@ void bamse_destroy(bamse_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     DBuf* bufs[] = {&ctx->d_K, &ctx->d_p0, &ctx->d_var, &ctx->d_ref, &ctx->d_logc, &ctx->d_logcf, &ctx->d_log1mcf,
-                    &ctx->d_D64, &ctx->d_D32, &ctx->d_D2, &ctx->d_EL2, &ctx->d_SEL2, &ctx->d_SD2, &ctx->d_HS2, &ctx->d_segs, &ctx->d_scalars, &ctx->d_cand, &ctx->d_items,
+                    &ctx->d_D64, &ctx->d_D32, &ctx->d_D2, &ctx->d_EL2, &ctx->d_SEL2, &ctx->d_SD2, &ctx->d_HS2, &ctx->d_PSE2, &ctx->d_PEE2, &ctx->d_segs, &ctx->d_scalars, &ctx->d_cand, &ctx->d_items,
                     &ctx->d_scores, &ctx->d_const, &ctx->d_thr, &ctx->d_begin, &ctx->d_end, &ctx->d_records,
                     &ctx->d_dense0, &ctx->d_dense1, &ctx->d_pb, &ctx->d_pe};
     for (DBuf* b : bufs) b->release();
@@ -270,6 +271,13 @@ int bamse_upload_problem(bamse_ctx* ctx, int P, const double* err, int C, int M,
         BAMSE_CUDA_TRY(ctx, ctx->d_SD2.ensure(sizeof(float) * nrows * L));
         BAMSE_CUDA_TRY(ctx, ctx->d_HS2.ensure(sizeof(float) * nrows * Kmax * L));
     }
+    // leaf-pair tables: Kmax (Kmax - 1) / 2 rows per (p, c, m), two kinds
+    const size_t npair_rows = (nrows / Kmax) * (size_t)n_pairs(Kmax);
+    ctx->pair_tables = Kmax >= 3 && (double)npair_rows * 2 * L * sizeof(float) <= 16e9;
+    if (ctx->pair_tables) {
+        BAMSE_CUDA_TRY(ctx, ctx->d_PSE2.ensure(sizeof(float) * npair_rows * L));
+        BAMSE_CUDA_TRY(ctx, ctx->d_PEE2.ensure(sizeof(float) * npair_rows * L));
+    }
     cudaStream_t s = ctx->stream;
     BAMSE_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_K.p, K_of_c, sizeof(int32_t) * C, cudaMemcpyHostToDevice, s));
     BAMSE_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_p0.p, p0.data(), sizeof(double) * C, cudaMemcpyHostToDevice, s));
@@ -288,6 +296,10 @@ int bamse_upload_problem(bamse_ctx* ctx, int P, const double* err, int C, int M,
     ctx->launches += 2;
     if (ctx->root_tables) {
         launch_tables_hs(ctx->view(), ctx->fast(), ctx->d_HS2.as<float>(), s);
+        ctx->launches++;
+    }
+    if (ctx->pair_tables) {
+        launch_tables_pairs(ctx->view(), ctx->fast(), ctx->d_PSE2.as<float>(), ctx->d_PEE2.as<float>(), s);
         ctx->launches++;
     }
     BAMSE_CUDA_TRY(ctx, cudaGetLastError());

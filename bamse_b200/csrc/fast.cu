@@ -49,10 +49,11 @@ void launch_tables_fast(const ProblemView& pv, float* D2, float* EL2, float* SEL
 
 // Index -> program: executed by one lane once per tree.  Kept out of line so that its (large, fully
 // unrolled) code does not sit between the hot loops in the instruction cache.
-static __device__ __noinline__ void build_tree_program(int K, uint64_t tree, TreeProgram* prog, bool root_tables) {
+static __device__ __noinline__ void build_tree_program(int K, uint64_t tree, TreeProgram* prog, bool root_tables,
+                                                       int pair_kmax) {
     int8_t parent[KMAX];
     decode_tree(K, tree, parent);
-    build_program_fast(K, parent, nullptr, prog, root_tables);
+    build_program_fast(K, parent, nullptr, prog, root_tables, pair_kmax);
 }
 
 // ------------------------------------------------------------------ per-warp evaluation
@@ -102,6 +103,11 @@ __device__ inline double warp_eval_tree(const ProblemView& pv, const FastTables&
                 float* dst = ws->vec[sp] + GUARD;
                 warp_load_vec(dst, (op == FOP_PUSH_EL ? ft.EL2 : ft.SEL2) + base + (size_t)arg * L, lane);
                 ++sp;
+            } else if (op == FOP_PUSH_PSE || op == FOP_PUSH_PEE) {
+                float* dst = ws->vec[sp] + GUARD;
+                const size_t row = (base / ((size_t)pv.Kmax * L)) * n_pairs(pv.Kmax) + (size_t)arg;
+                warp_load_vec(dst, (op == FOP_PUSH_PSE ? ft.PSE2 : ft.PEE2) + row * L, lane);
+                ++sp;
             } else if (op == FOP_SCAN) {
                 warp_log2cumsum(ws->vec[sp - 1] + GUARD, add2, lane);
                 ++*st_scans;
@@ -150,6 +156,36 @@ __global__ void __launch_bounds__(FAST_THREADS) k_tables_hs(ProblemView pv, Fast
     warp_logconv<false>(a, b, ws->jstar, ws->fa, ws->fb, lane);
     float* out = HS2 + (size_t)idx * L;
     for (int t = 0; t < 16; ++t) out[lane + 32 * t] = a[L - 1 - lane - 32 * t] - LOG2_L;
+}
+
+// Leaf-pair tables: PSE[c1,c2] = SEL[c1] (*) EL[c2], PEE[c1,c2] = EL[c1] (*) EL[c2] (both symmetric in
+// the pair), one warp per (p, c, m, pair, kind) with the production convolution.
+__global__ void __launch_bounds__(FAST_THREADS) k_tables_pairs(ProblemView pv, FastTables ft, float* __restrict__ PSE2,
+                                                               float* __restrict__ PEE2) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int wid = threadIdx.x >> 5;
+    int lane = threadIdx.x & 31;
+    WarpSmem* ws = pin_shared(reinterpret_cast<WarpSmem*>(smem_raw) + wid);
+    const int Kmax = pv.Kmax, NP = n_pairs(Kmax);
+    const int64_t idx = (int64_t)blockIdx.x * FAST_WARPS + wid;     // (pcm * NP + pair) * 2 + kind
+    const int64_t n = (int64_t)pv.P * pv.C * pv.M * NP * 2;
+    if (idx >= n) return;
+    const int kind = (int)(idx & 1);
+    const int pair = (int)((idx >> 1) % NP);
+    const int64_t pcm = (idx >> 1) / NP;
+    const int c = (int)((pcm / pv.M) % pv.C);
+    int c1 = 0, rem = pair;                                         // invert the triangular index
+    while (rem >= Kmax - 1 - c1) { rem -= Kmax - 1 - c1; ++c1; }
+    const int c2 = c1 + 1 + rem;
+    if (c2 >= pv.K_of_c[c]) return;
+    warp_init_guards(ws, lane);
+    float* a = ws->vec[0] + GUARD;
+    float* b = ws->vec[1] + GUARD;
+    warp_load_vec(a, (kind == 0 ? ft.SEL2 : ft.EL2) + ((size_t)pcm * Kmax + c1) * L, lane);
+    warp_load_vec(b, ft.EL2 + ((size_t)pcm * Kmax + c2) * L, lane);
+    warp_logconv<false>(a, b, ws->jstar, ws->fa, ws->fb, lane);
+    float* out = (kind == 0 ? PSE2 : PEE2) + ((size_t)pcm * NP + pair) * L;
+    for (int t = 0; t < 16; ++t) out[lane + 32 * t] = a[lane + 32 * t];
 }
 
 __device__ __forceinline__ bool rec_better_f(const bamse_record& a, const bamse_record& b) {
@@ -208,7 +244,7 @@ __global__ void __launch_bounds__(FAST_THREADS, FRAMED ? 6 : 7) k_enumerate_fast
         const int n = remain < (uint64_t)w.chunk ? (int)remain : w.chunk;
         for (int i = 0; i < n; ++i) {
             const uint64_t tree = seg.tree_begin + (off + i) * (uint64_t)seg.stride;
-            if (lane == 0) build_tree_program(seg.K, tree, &ws->prog, ft.HS2 != nullptr);
+            if (lane == 0) build_tree_program(seg.K, tree, &ws->prog, ft.HS2 != nullptr, ft.PSE2 ? pv.Kmax : 0);
             __syncwarp();
             const double score = warp_eval_tree<FRAMED>(pv, ft, seg.p, seg.c, ws, lane, &st_chunks, &st_convs, &st_scans);
             st_samples += pv.M;
@@ -283,6 +319,14 @@ void launch_tables_hs(const ProblemView& pv, const FastTables& ft, float* HS2, c
     k_tables_hs<<<(unsigned)((n + FAST_WARPS - 1) / FAST_WARPS), FAST_THREADS, smem, s>>>(pv, ft, HS2);
 }
 
+void launch_tables_pairs(const ProblemView& pv, const FastTables& ft, float* PSE2, float* PEE2, cudaStream_t s) {
+    const int64_t n = (int64_t)pv.P * pv.C * pv.M * n_pairs(pv.Kmax) * 2;
+    if (n <= 0) return;
+    const size_t smem = sizeof(WarpSmem) * FAST_WARPS;
+    cudaFuncSetAttribute(k_tables_pairs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k_tables_pairs<<<(unsigned)((n + FAST_WARPS - 1) / FAST_WARPS), FAST_THREADS, smem, s>>>(pv, ft, PSE2, PEE2);
+}
+
 int enumerate_workers(int precision, int grid) { return precision == BAMSE_FP32 ? grid * FAST_WARPS : grid; }
 
 int enumerate_fast_grid_size(int device, int topk, bool framed) {
@@ -318,7 +362,7 @@ __global__ void __launch_bounds__(FAST_THREADS) k_score_items_fast(ProblemView p
     warp_init_guards(ws, lane);
     const ScoreItem it = items[idx];
     int ok = 1;
-    if (lane == 0) ok = build_program_fast(it.k, it.parent, it.nodes, &ws->prog, ft.HS2 != nullptr) ? 1 : 0;
+    if (lane == 0) ok = build_program_fast(it.k, it.parent, it.nodes, &ws->prog, ft.HS2 != nullptr, ft.PSE2 ? pv.Kmax : 0) ? 1 : 0;
     ok = __shfl_sync(0xffffffffu, ok, 0);
     if (!ok) { if (lane == 0) out[idx] = CUDART_NAN; return; }
     unsigned s0 = 0, s1 = 0, s2 = 0;

@@ -41,7 +41,17 @@ struct FastTables {
     // last operation there is a dot product of the folded children message Q with
     const float* SD2;    // [rows][L]       SD[r][i]    = e^p0 / L^2 * sum_{x>=i} d_r[x]              (no leaf child)
     const float* HS2;    // [rows][Kmax][L] HS[r][c][i] = 1 / L^2 * sum_j d_r[i+j] * sel_c[j]         (leaf child c)
+    // leaf-pair tables (may be NULL): two leaf siblings fold into one table, indexed by the
+    // triangular pair index of (c1 < c2) among Kmax nodes
+    const float* PSE2;   // [pcm][NP][L]  SEL[c1] (*) EL[c2]   (the pair carries the scan factor)
+    const float* PEE2;   // [pcm][NP][L]  EL[c1]  (*) EL[c2]
 };
+
+__host__ __device__ inline int pair_index(int c1, int c2, int Kmax) {      // c1 != c2, both < Kmax
+    const int lo = c1 < c2 ? c1 : c2, hi = c1 < c2 ? c2 : c1;
+    return lo * (2 * Kmax - lo - 1) / 2 + (hi - lo - 1);
+}
+__host__ __device__ inline int n_pairs(int Kmax) { return Kmax * (Kmax - 1) / 2; }
 
 // evaluation program of the fast path (convolution is commutative/associative, so the
 // factor that carries the prefix sum may be any child; a leaf child is preferred because
@@ -52,6 +62,8 @@ enum : int8_t {
     FOP_SCAN = 2,       // top = log2cumsum(top) + p0 - log L
     FOP_CONV = 3,       // b = pop; top = top (*) b   (in place)
     FOP_ADDD = 4,       // top += D2[arg]
+    FOP_PUSH_PSE = 5,   // push PSE2[arg]   (arg = triangular pair index)
+    FOP_PUSH_PEE = 6,   // push PEE2[arg]
 };
 // how the per-sample scalar is produced from the vector left on the stack (TreeProgram::pad;
 // the root node id is TreeProgram::fin_r, the leaf child of FIN_HS is TreeProgram::fin_c)
@@ -64,7 +76,8 @@ enum : int8_t {
 
 // Builds the fast program + canonizeF weight.  Same validity rules as build_program.
 __host__ __device__ inline bool build_program_fast(int k, const int8_t* parent, const int8_t* nodes,
-                                                   TreeProgram* prog, bool root_tables = false) {
+                                                   TreeProgram* prog, bool root_tables = false,
+                                                   int pair_kmax = 0 /* > 0: leaf-pair tables exist */) {
     // canon weight / validation through the reference-order builder
     if (!build_program(k, parent, nodes, prog)) return false;
     const int32_t scre = prog->scre;
@@ -103,15 +116,25 @@ __host__ __device__ inline bool build_program_fast(int k, const int8_t* parent, 
             if (root_tables && f == 0) {
                 // the root: its first leaf child (if any) is folded in by the HS table, the scan and
                 // D[root] by the SD / HS / D tables -- one convolution and one scan fewer
-                int cstar = -1;
+                int cstar = -1, held = -1;                    // held: a leaf waiting for a partner
                 for (int c = 0; c < k; ++c)
                     if (parent[c] == v && nchild[c] == 0) {
                         if (cstar < 0) { cstar = c; continue; }
+                        if (pair_kmax > 0 && held < 0) { held = c; continue; }
                         if (n_ops + 2 > MAX_OPS) return false;
-                        emit(FOP_PUSH_EL, nodes ? nodes[c] : (int8_t)c);
+                        if (held >= 0) {
+                            emit(FOP_PUSH_PEE, (int8_t)pair_index(nodes ? nodes[held] : held, nodes ? nodes[c] : c, pair_kmax));
+                            held = -1;
+                        } else emit(FOP_PUSH_EL, nodes ? nodes[c] : (int8_t)c);
                         if (st_done[f] > 0) emit(FOP_CONV, 0);
                         st_done[f]++;
                     }
+                if (held >= 0) {
+                    if (n_ops + 2 > MAX_OPS) return false;
+                    emit(FOP_PUSH_EL, nodes ? nodes[held] : (int8_t)held);
+                    if (st_done[f] > 0) emit(FOP_CONV, 0);
+                    st_done[f]++;
+                }
                 fin_r = nodes ? nodes[v] : (int8_t)v;
                 if (cstar < 0) fin = FIN_DOT_SD;
                 else if (st_done[f] == 0) {
@@ -122,16 +145,31 @@ __host__ __device__ inline bool build_program_fast(int k, const int8_t* parent, 
                 --sp;
                 continue;
             }
-            // internal children done: leaves
+            // internal children done: leaves (in pairs when the pair tables exist; the first
+            // leaf / pair carries the scan factor)
             bool first_leaf = true;
+            int held = -1;
             for (int c = 0; c < k; ++c)
                 if (parent[c] == v && nchild[c] == 0) {
+                    if (pair_kmax > 0 && held < 0) { held = c; continue; }
                     if (n_ops + 2 > MAX_OPS) return false;
-                    if (first_leaf) { emit(FOP_PUSH_SEL, nodes ? nodes[c] : (int8_t)c); first_leaf = false; }
+                    if (held >= 0) {
+                        emit(first_leaf ? FOP_PUSH_PSE : FOP_PUSH_PEE,
+                             (int8_t)pair_index(nodes ? nodes[held] : held, nodes ? nodes[c] : c, pair_kmax));
+                        held = -1;
+                    } else if (first_leaf) emit(FOP_PUSH_SEL, nodes ? nodes[c] : (int8_t)c);
                     else emit(FOP_PUSH_EL, nodes ? nodes[c] : (int8_t)c);
+                    first_leaf = false;
                     if (st_done[f] > 0) emit(FOP_CONV, 0);
                     st_done[f]++;
                 }
+            if (held >= 0) {
+                if (n_ops + 2 > MAX_OPS) return false;
+                emit(first_leaf ? FOP_PUSH_SEL : FOP_PUSH_EL, nodes ? nodes[held] : (int8_t)held);
+                first_leaf = false;
+                if (st_done[f] > 0) emit(FOP_CONV, 0);
+                st_done[f]++;
+            }
             if (n_ops + 2 > MAX_OPS) return false;
             if (first_leaf) emit(FOP_SCAN, 0);       // no leaf child: the accumulated product carries the scan
             emit(FOP_ADDD, nodes ? nodes[v] : (int8_t)v);
