@@ -120,12 +120,12 @@ __device__ inline double warp_eval_tree(const ProblemView& pv, const FastTables&
             }
         }
         const int fin = ws->prog.pad;
-        float res2;
-        if (fin == FIN_LSE) res2 = warp_log2sumexp(ws->vec[0] + GUARD, lane) - LOG2_L;
-        else if (fin == FIN_DOT_D) res2 = warp_log2dot(ws->vec[0] + GUARD, ft.D2 + base + (size_t)ws->prog.fin_r * L, lane) - LOG2_L;
-        else if (fin == FIN_DOT_SD) res2 = warp_log2dot(ws->vec[0] + GUARD, ft.SD2 + base + (size_t)ws->prog.fin_r * L, lane);
-        else res2 = warp_log2dot(ws->vec[0] + GUARD,
-                                 ft.HS2 + base * pv.Kmax + ((size_t)ws->prog.fin_r * pv.Kmax + ws->prog.fin_c) * L, lane);
+        const float* tab = nullptr;                  // FIN_LSE: plain log-sum-exp
+        if (fin == FIN_DOT_D) tab = ft.D2 + base + (size_t)ws->prog.fin_r * L;
+        else if (fin == FIN_DOT_SD) tab = ft.SD2 + base + (size_t)ws->prog.fin_r * L;
+        else if (fin == FIN_DOT_HS) tab = ft.HS2 + base * pv.Kmax + ((size_t)ws->prog.fin_r * pv.Kmax + ws->prog.fin_c) * L;
+        float res2 = warp_log2dot(ws->vec[0] + GUARD, tab, lane);
+        if (fin == FIN_LSE || fin == FIN_DOT_D) res2 -= LOG2_L;
         total += (double)res2 * 0.69314718055994530942;
     }
     return total;

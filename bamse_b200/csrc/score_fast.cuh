@@ -84,13 +84,13 @@ __host__ __device__ inline bool build_program_fast(int k, const int8_t* parent, 
     const int n_leaves = prog->n_leaves;
     int root = 0;
     int8_t nchild[KMAX], size[KMAX], order[KMAX];
-    for (int v = 0; v < k; ++v) { nchild[v] = 0; size[v] = 1; if (parent[v] == -1) root = v; }
-    for (int v = 0; v < k; ++v) if (parent[v] >= 0) nchild[parent[v]]++;
+    _Pragma("unroll 1") for (int v = 0; v < k; ++v) { nchild[v] = 0; size[v] = 1; if (parent[v] == -1) root = v; }
+    _Pragma("unroll 1") for (int v = 0; v < k; ++v) if (parent[v] >= 0) nchild[parent[v]]++;
     // subtree sizes: process nodes in decreasing depth order (depth via parent walks)
     int8_t depth[KMAX];
-    for (int v = 0; v < k; ++v) { int d = 0, w = v; while (parent[w] >= 0) { w = parent[w]; ++d; } depth[v] = (int8_t)d; order[v] = (int8_t)v; }
-    for (int i = 1; i < k; ++i) { int8_t o = order[i]; int j = i; while (j > 0 && depth[order[j - 1]] < depth[o]) { order[j] = order[j - 1]; --j; } order[j] = o; }
-    for (int i = 0; i < k; ++i) { const int v = order[i]; if (parent[v] >= 0) size[parent[v]] += size[v]; }
+    _Pragma("unroll 1") for (int v = 0; v < k; ++v) { int d = 0, w = v; _Pragma("unroll 1") while (parent[w] >= 0) { w = parent[w]; ++d; } depth[v] = (int8_t)d; order[v] = (int8_t)v; }
+    _Pragma("unroll 1") for (int i = 1; i < k; ++i) { int8_t o = order[i]; int j = i; _Pragma("unroll 1") while (j > 0 && depth[order[j - 1]] < depth[o]) { order[j] = order[j - 1]; --j; } order[j] = o; }
+    _Pragma("unroll 1") for (int i = 0; i < k; ++i) { const int v = order[i]; if (parent[v] >= 0) size[parent[v]] += size[v]; }
 
     // iterative emission.  frame: node, phase; children lists are recomputed by scanning.
     int8_t st_node[KMAX], st_stage[KMAX], st_done[KMAX];
@@ -100,12 +100,12 @@ __host__ __device__ inline bool build_program_fast(int k, const int8_t* parent, 
     auto emit = [&](int8_t op, int8_t arg) { prog->op[n_ops] = op; prog->arg[n_ops] = arg; ++n_ops; };
     if (nchild[root] == 0) { emit(FOP_PUSH_EL, nodes ? nodes[root] : (int8_t)root); }
     else { st_node[0] = (int8_t)root; st_stage[0] = 0; st_done[0] = 0; st_used[0] = 0; sp = 1; }
-    while (sp > 0) {
+    _Pragma("unroll 1") while (sp > 0) {
         const int f = sp - 1, v = st_node[f];
         if (st_stage[f] == 0) {
             // next unevaluated internal child with the largest subtree
             int best = -1;
-            for (int c = 0; c < k; ++c)
+            _Pragma("unroll 1") for (int c = 0; c < k; ++c)
                 if (parent[c] == v && nchild[c] > 0 && !((st_used[f] >> c) & 1) && (best < 0 || size[c] > size[best])) best = c;
             if (best >= 0) {
                 st_used[f] |= (uint16_t)(1u << best);
@@ -117,7 +117,7 @@ __host__ __device__ inline bool build_program_fast(int k, const int8_t* parent, 
                 // the root: its first leaf child (if any) is folded in by the HS table, the scan and
                 // D[root] by the SD / HS / D tables -- one convolution and one scan fewer
                 int cstar = -1, held = -1;                    // held: a leaf waiting for a partner
-                for (int c = 0; c < k; ++c)
+                _Pragma("unroll 1") for (int c = 0; c < k; ++c)
                     if (parent[c] == v && nchild[c] == 0) {
                         if (cstar < 0) { cstar = c; continue; }
                         if (pair_kmax > 0 && held < 0) { held = c; continue; }
@@ -149,7 +149,7 @@ __host__ __device__ inline bool build_program_fast(int k, const int8_t* parent, 
             // leaf / pair carries the scan factor)
             bool first_leaf = true;
             int held = -1;
-            for (int c = 0; c < k; ++c)
+            _Pragma("unroll 1") for (int c = 0; c < k; ++c)
                 if (parent[c] == v && nchild[c] == 0) {
                     if (pair_kmax > 0 && held < 0) { held = c; continue; }
                     if (n_ops + 2 > MAX_OPS) return false;
@@ -270,12 +270,14 @@ __device__ inline float warp_log2sumexp(const float* __restrict__ v, int lane) {
 }
 
 // log2(sum_x 2^(v[x] + tab[x])), v in shared memory, tab a table row in global memory
+// (tab == nullptr: plain log2sumexp of v) -- one code path for every way a sample is finished
 __device__ inline float warp_log2dot(const float* __restrict__ v, const float* __restrict__ tab, int lane) {
     float x[16];
 #pragma unroll
     for (int t = 0; t < 4; ++t) {
         const float4 q = reinterpret_cast<const float4*>(v)[lane + 32 * t];
-        const float4 d = __ldg(reinterpret_cast<const float4*>(tab) + lane + 32 * t);
+        float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (tab) d = __ldg(reinterpret_cast<const float4*>(tab) + lane + 32 * t);
         x[4 * t] = q.x + d.x; x[4 * t + 1] = q.y + d.y; x[4 * t + 2] = q.z + d.z; x[4 * t + 3] = q.w + d.w;
     }
     float m = x[0];
@@ -308,7 +310,7 @@ __device__ inline void warp_merge_path(const float* __restrict__ a, const float*
     float ai = a[i], an = (i < L - 1) ? a[i + 1] : -CUDART_INF_F;
     float bj = b[j], bn = (j < L - 1) ? b[j + 1] : -CUDART_INF_F;
     uint32_t packed = 0;                                      // two 16-bit j* per word
-#pragma unroll
+#pragma unroll 2
     for (int t = 0; t < 16; ++t) {
         if (t & 1) reinterpret_cast<uint32_t*>(jstar)[(x0 + t) >> 1] = packed | ((uint32_t)j << 16);
         else packed = (uint32_t)j;
@@ -388,29 +390,33 @@ __device__ __forceinline__ void conv_pass_mufu(float* __restrict__ a, const floa
     int jl = max(jmin - hl, 0) & ~3;
     int n4 = (min(jmax + hr, xmax) - jl + 4) >> 2;
     int je = jl + 4 * n4 - 1;
-    chunks += n4;
-    conv_accumulate(a + (x - jl), reinterpret_cast<const float4*>(b + jl), n4, nm2, acc0, acc1, acc2, acc3);
-    // the terms of one output are concave in j: if the edge terms of every lane are below
-    // 2^-THETA of its maximum, everything outside the range is too.  Otherwise extend.
+    // One call site for the accumulation loop (code size): first the guessed range, then -- as long
+    // as some lane's edge term is still above 2^-THETA of its maximum -- extensions to the left,
+    // then to the right.  The terms of one output are concave in j, so sub-threshold edges bound
+    // everything outside the range.
+    int seg_j0 = jl, seg_m4 = n4, phase = 0;
+#pragma unroll 1
     for (;;) {
-        const bool need = (jl > 0) && (((a[x - jl] - mx) + b[jl]) >= -THETA);
-        if (!__any_sync(0xffffffffu, need)) break;
-        const int j2 = max(jl - max(hl, 8), 0) & ~3;
-        const int m4 = (jl - j2) >> 2;
-        chunks += m4;
-        conv_accumulate(a + (x - j2), reinterpret_cast<const float4*>(b + j2), m4, nm2, acc0, acc1, acc2, acc3);
-        hl += jl - j2;
-        jl = j2;
-    }
-    for (;;) {
+        chunks += seg_m4;
+        conv_accumulate(a + (x - seg_j0), reinterpret_cast<const float4*>(b + seg_j0), seg_m4, nm2, acc0, acc1, acc2, acc3);
+        if (phase == 0) {
+            const bool need = (jl > 0) && (((a[x - jl] - mx) + b[jl]) >= -THETA);
+            if (__any_sync(0xffffffffu, need)) {
+                const int j2 = max(jl - max(hl, 8), 0) & ~3;
+                seg_j0 = j2; seg_m4 = (jl - j2) >> 2;
+                hl += jl - j2;
+                jl = j2;
+                continue;
+            }
+            phase = 1;
+        }
         // lanes with x <= je read the -inf guard here, so they never ask for more
         const bool need = ((a[x - je] - mx) + b[je]) >= -THETA;
         if (!__any_sync(0xffffffffu, need) || je >= xmax) break;
-        const int m4 = min((max(hr, 8) + 3) >> 2, ((xmax | 3) - je) >> 2);
-        chunks += m4;
-        conv_accumulate(a + (x - je - 1), reinterpret_cast<const float4*>(b + je + 1), m4, nm2, acc0, acc1, acc2, acc3);
-        hr += 4 * m4;
-        je += 4 * m4;
+        seg_m4 = min((max(hr, 8) + 3) >> 2, ((xmax | 3) - je) >> 2);
+        seg_j0 = je + 1;
+        hr += 4 * seg_m4;
+        je += 4 * seg_m4;
     }
     acc0 = __fadd2_rn(__fadd2_rn(acc0, acc1), __fadd2_rn(acc2, acc3));
     const float s = acc0.x + acc0.y;

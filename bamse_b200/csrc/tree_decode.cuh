@@ -15,15 +15,15 @@ __host__ __device__ inline void decode_tree(int K, uint64_t index, int8_t* paren
     int8_t seq[KMAX];
     int8_t deg[KMAX];
     uint16_t adj[KMAX];  // adjacency bit masks
-    for (int v = 0; v < K; ++v) { deg[v] = 1; adj[v] = 0; }
-    for (int i = 0; i < K - 2; ++i) {
+    _Pragma("unroll 1") for (int v = 0; v < K; ++v) { deg[v] = 1; adj[v] = 0; }
+    _Pragma("unroll 1") for (int i = 0; i < K - 2; ++i) {
         seq[i] = (int8_t)(code % (uint64_t)K);
         code /= (uint64_t)K;
         deg[seq[i]]++;
     }
-    for (int i = 0; i < K - 2; ++i) {
+    _Pragma("unroll 1") for (int i = 0; i < K - 2; ++i) {
         int leaf = 0;
-        while (deg[leaf] != 1) ++leaf;  // smallest label with degree 1
+        _Pragma("unroll 1") while (deg[leaf] != 1) ++leaf;  // smallest label with degree 1
         const int s = seq[i];
         adj[leaf] |= (uint16_t)(1u << s);
         adj[s] |= (uint16_t)(1u << leaf);
@@ -31,20 +31,20 @@ __host__ __device__ inline void decode_tree(int K, uint64_t index, int8_t* paren
         deg[s]--;
     }
     int u = -1, w = -1;
-    for (int v = 0; v < K; ++v)
+    _Pragma("unroll 1") for (int v = 0; v < K; ++v)
         if (deg[v] == 1) { if (u < 0) u = v; else w = v; }
     adj[u] |= (uint16_t)(1u << w);
     adj[w] |= (uint16_t)(1u << u);
     // orient away from the root
-    for (int v = 0; v < K; ++v) parent[v] = -2;
+    _Pragma("unroll 1") for (int v = 0; v < K; ++v) parent[v] = -2;
     parent[root] = -1;
     int8_t stack[KMAX];
     int sp = 0;
     stack[sp++] = (int8_t)root;
-    while (sp > 0) {
+    _Pragma("unroll 1") while (sp > 0) {
         const int n = stack[--sp];
         uint16_t nb = adj[n];
-        while (nb) {
+        _Pragma("unroll 1") while (nb) {
 #ifdef __CUDA_ARCH__
             const int x = __ffs((int)nb) - 1;
 #else
@@ -69,15 +69,15 @@ __host__ __device__ inline void decode_tree(int K, uint64_t index, int8_t* paren
 __host__ __device__ inline bool build_program(int k, const int8_t* parent, const int8_t* nodes,
                                               TreeProgram* prog) {
     int root = -1;
-    for (int v = 0; v < k; ++v) {
+    _Pragma("unroll 1") for (int v = 0; v < k; ++v) {
         if (parent[v] == -1) { if (root >= 0) return false; root = v; }
         else if (parent[v] < 0 || parent[v] >= k || parent[v] == v) return false;
     }
     if (root < 0) return false;
 
     int8_t nchild[KMAX];
-    for (int v = 0; v < k; ++v) nchild[v] = 0;
-    for (int v = 0; v < k; ++v) if (parent[v] >= 0) nchild[parent[v]]++;
+    _Pragma("unroll 1") for (int v = 0; v < k; ++v) nchild[v] = 0;
+    _Pragma("unroll 1") for (int v = 0; v < k; ++v) if (parent[v] >= 0) nchild[parent[v]]++;
 
     // iterative DFS; frame = (node, next child candidate index to scan from)
     int8_t st_node[KMAX], st_next[KMAX], st_seen[KMAX];
@@ -87,7 +87,7 @@ __host__ __device__ inline bool build_program(int k, const int8_t* parent, const
     int n_ops = 0, n_leaves = 0, visited = 0;
     int sp = 0;
     st_node[0] = (int8_t)root; st_next[0] = 0; st_seen[0] = 0; sp = 1;
-    while (sp > 0) {
+    _Pragma("unroll 1") while (sp > 0) {
         const int v = st_node[sp - 1];
         if (nchild[v] == 0) {                         // leaf
             if (n_ops >= MAX_OPS) return false;
@@ -97,7 +97,7 @@ __host__ __device__ inline bool build_program(int k, const int8_t* parent, const
             ++n_leaves; ++visited; --sp;
         } else {
             int c = st_next[sp - 1];
-            while (c < k && parent[c] != v) ++c;
+            _Pragma("unroll 1") while (c < k && parent[c] != v) ++c;
             if (c < k) {                              // descend into next child
                 st_next[sp - 1] = (int8_t)(c + 1);
                 if (sp >= KMAX) return false;         // cycle guard
@@ -107,19 +107,19 @@ __host__ __device__ inline bool build_program(int k, const int8_t* parent, const
             // all children done: fold canon strings / weights
             uint32_t cs[KMAX]; int8_t cl[KMAX]; int nc = 0;
             int32_t w = 1; int run = 1; uint32_t prev = 0; int8_t prevlen = 0;
-            for (int ch = 0; ch < k; ++ch) if (parent[ch] == v) {
+            _Pragma("unroll 1") for (int ch = 0; ch < k; ++ch) if (parent[ch] == v) {
                 w *= weight[ch];
                 if (nc > 0 && canon[ch] == prev && canon_len[ch] == prevlen) ++run;
                 else { w *= run; run = 1; }
                 prev = canon[ch]; prevlen = canon_len[ch];
                 // insertion sort ascending
                 int i = nc++;
-                while (i > 0 && cs[i - 1] > canon[ch]) { cs[i] = cs[i - 1]; cl[i] = cl[i - 1]; --i; }
+                _Pragma("unroll 1") while (i > 0 && cs[i - 1] > canon[ch]) { cs[i] = cs[i - 1]; cl[i] = cl[i - 1]; --i; }
                 cs[i] = canon[ch]; cl[i] = canon_len[ch];
             }
             w *= run;
             uint32_t s = 0; int len = 1;              // leading '[' = 0 bit
-            for (int i = 0; i < nc; ++i) { s |= cs[i] >> len; len += cl[i]; }
+            _Pragma("unroll 1") for (int i = 0; i < nc; ++i) { s |= cs[i] >> len; len += cl[i]; }
             s |= 1u << (31 - len); ++len;             // trailing ']' = 1 bit
             canon[v] = s; canon_len[v] = (int8_t)len; weight[v] = w;
             if (n_ops >= MAX_OPS) return false;
