@@ -522,8 +522,8 @@ static int enumerate_dev(bamse_ctx* ctx, const double* d_const, const double* d_
     ctx->launches++;
     BAMSE_CUDA_TRY(ctx, cudaGetLastError());
     if (topk > 0 && d_out) {
-        launch_merge_topk(ctx->d_cand.as<bamse_record>(), reinterpret_cast<unsigned long long*>(scal + 3), 0, P, topk,
-                          d_out, s);
+        launch_merge_topk(ctx->d_cand.as<bamse_record>(), reinterpret_cast<unsigned long long*>(scal + 3), cand_cap, P,
+                          topk, d_out, s);
         ctx->launches++;
         BAMSE_CUDA_TRY(ctx, cudaGetLastError());
     }
@@ -635,7 +635,7 @@ int bamse_score_topk(bamse_ctx* ctx, const double* clust_const, const double* th
     BAMSE_CUDA_TRY(ctx, cudaMemcpyAsync(recs.data(), ctx->d_records.p, sizeof(bamse_record) * P * ksel, cudaMemcpyDeviceToHost, s));
     BAMSE_CUDA_TRY(ctx, cudaStreamSynchronize(s));
 
-    if (precision == BAMSE_FP32) {
+    if (precision != BAMSE_FP64) {
         // fp64 check-mode re-score of the short list, exact threshold, final ranking
         std::vector<ScoreItem> items;
         std::vector<size_t> where;

@@ -241,7 +241,8 @@ __global__ void __launch_bounds__(512) k_merge_topk(const bamse_record* __restri
     __shared__ bamse_record s_prev;
     __shared__ int s_has[NT / 32];
     const int p = blockIdx.x, t = threadIdx.x, lane = t & 31, w = t >> 5;
-    const unsigned long long n = count ? *count : n_given;
+    // with a device-side count, n_given is the capacity of the bag (appends beyond it were dropped)
+    const unsigned long long n = count ? (*count < n_given ? *count : n_given) : n_given;
     bool have_prev = false;
     bool done = false;
     for (int r = 0; r < topk; ++r) {

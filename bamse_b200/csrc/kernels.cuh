@@ -54,7 +54,7 @@ int enumerate_grid_size(int precision, int device);
 void launch_enumerate(int precision, const ProblemView& pv, const EnumWork& w, int grid, cudaStream_t s);
 void launch_score_items(int precision, const ProblemView& pv, const ScoreItem* d_items, int64_t n,
                         double* d_out, cudaStream_t s);
-// d_bag: n records (n read from d_count when non-NULL) in any order, each tagged with its param;
+// d_bag: n records (min(*d_count, n) when d_count is non-NULL) in any order, each tagged with its param;
 // writes the best topk of every parameter set to d_out [P][topk]
 void launch_merge_topk(const bamse_record* d_bag, const unsigned long long* d_count, unsigned long long n, int P,
                        int topk, bamse_record* d_out, cudaStream_t s);
