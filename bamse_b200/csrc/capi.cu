@@ -461,7 +461,7 @@ static int enumerate_dev(bamse_ctx* ctx, const double* d_const, const double* d_
     }
     const int pi = precision == BAMSE_FP64 ? 1 : (precision == BAMSE_FP32 ? 0 : 2);
     const bool framed = precision == BAMSE_FP32 && ctx->use_framed == 1;
-    if (precision == BAMSE_FP32) ctx->grid[pi] = enumerate_fast_grid_size(ctx->device, topk, framed);
+    if (precision == BAMSE_FP32) ctx->grid[pi] = enumerate_fast_grid_size(ctx->device, topk, framed, ctx->Kmax);
     else if (ctx->grid[pi] == 0) ctx->grid[pi] = enumerate_grid_size(precision, ctx->device);
     const int grid = ctx->grid[pi];
     // work granularity: ~32 chunks per worker (warp for fp32, CTA for the check mode), 1..16 trees

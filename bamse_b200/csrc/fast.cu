@@ -57,9 +57,9 @@ static __device__ __noinline__ void build_tree_program(int K, uint64_t tree, Tre
 }
 
 // ------------------------------------------------------------------ per-warp evaluation
-template <bool FRAMED>
+template <bool FRAMED, int SLOTS = FAST_SLOTS>
 struct alignas(16) WarpSmemT {
-    float vec[FAST_SLOTS][VSTRIDE];
+    float vec[SLOTS][VSTRIDE];       // SLOTS = 2 suffices for K <= 6 (brute-forced), 3 for K <= 12
     uint16_t jstar[L];
     float fa[FRAMED ? FR_A : 4];      // framed-path scratch: 2^(a - frame) of the current segment
     float fb[FRAMED ? FR_SEG : 4];    // framed-path scratch: 2^(b - frame)
@@ -79,7 +79,8 @@ __device__ __forceinline__ W* pin_shared(W* p) {
 
 template <class W>
 __device__ inline void warp_init_guards(W* ws, int lane) {
-    for (int s = 0; s < FAST_SLOTS; ++s) {
+    constexpr int n_slots = (int)(sizeof(ws->vec) / sizeof(ws->vec[0]));
+    for (int s = 0; s < n_slots; ++s) {
         for (int i = lane; i < GUARD; i += 32) ws->vec[s][i] = -CUDART_INF_F;
         if (lane < 4) ws->vec[s][GUARD + L + lane] = -CUDART_INF_F;
     }
@@ -87,8 +88,8 @@ __device__ inline void warp_init_guards(W* ws, int lane) {
 }
 
 // score of the tree whose program sits in ws->prog, summed over samples (fp64), natural log
-template <bool FRAMED>
-__device__ inline double warp_eval_tree(const ProblemView& pv, const FastTables& ft, int p, int c, WarpSmemT<FRAMED>* ws,
+template <bool FRAMED, class WS>
+__device__ inline double warp_eval_tree(const ProblemView& pv, const FastTables& ft, int p, int c, WS* ws,
                                         int lane, unsigned* st_chunks, unsigned* st_convs, unsigned* st_scans) {
     const float add2 = (float)((pv.p0[c] - 6.2383246250395077847550890931236) * 1.4426950408889634074);
     const int n_ops = ws->prog.n_ops;
@@ -200,10 +201,11 @@ __device__ __forceinline__ bool rec_better_f(const bamse_record& a, const bamse_
 // cheap trees (few leaves) simply pulls more, and the tail of the launch is one tree long.
 // Each warp keeps a private top-k list in shared memory and appends it to a flat global bag
 // when its parameter set changes and at the end; k_merge_topk reduces the bag.
-template <bool FRAMED>
-__global__ void __launch_bounds__(FAST_THREADS, FRAMED ? 6 : 7) k_enumerate_fast(ProblemView pv, FastTables ft, EnumWork w) {
+template <bool FRAMED, int SLOTS>
+__global__ void __launch_bounds__(FAST_THREADS, FRAMED ? 6 : (SLOTS == 2 ? 8 : 7))
+k_enumerate_fast(ProblemView pv, FastTables ft, EnumWork w) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    using WS = WarpSmemT<FRAMED>;
+    using WS = WarpSmemT<FRAMED, SLOTS>;
     WS* wsm = reinterpret_cast<WS*>(smem_raw);
     bamse_record* s_top_all = reinterpret_cast<bamse_record*>(smem_raw + sizeof(WS) * FAST_WARPS);
     const int t = threadIdx.x, wid = t >> 5;
@@ -246,7 +248,7 @@ __global__ void __launch_bounds__(FAST_THREADS, FRAMED ? 6 : 7) k_enumerate_fast
             const uint64_t tree = seg.tree_begin + (off + i) * (uint64_t)seg.stride;
             if (lane == 0) build_tree_program(seg.K, tree, &ws->prog, ft.HS2 != nullptr, ft.PSE2 ? pv.Kmax : 0);
             __syncwarp();
-            const double score = warp_eval_tree<FRAMED>(pv, ft, seg.p, seg.c, ws, lane, &st_chunks, &st_convs, &st_scans);
+            const double score = warp_eval_tree<FRAMED, WS>(pv, ft, seg.p, seg.c, ws, lane, &st_chunks, &st_convs, &st_scans);
             st_samples += pv.M;
             if (lane == 0) {
                 const double logscre = log((double)ws->prog.scre);
@@ -307,9 +309,9 @@ __global__ void __launch_bounds__(FAST_THREADS, FRAMED ? 6 : 7) k_enumerate_fast
     }
 }
 
-static size_t fast_smem_bytes(int topk, bool framed = false) {
-    return (framed ? sizeof(WarpSmemT<true>) : sizeof(WarpSmemT<false>)) * FAST_WARPS +
-           sizeof(bamse_record) * FAST_WARPS * (size_t)(topk > 0 ? topk : 1);
+static size_t fast_smem_bytes(int topk, bool framed = false, int slots = FAST_SLOTS) {
+    const size_t per_warp = framed ? sizeof(WarpSmemT<true, 3>) : (slots == 2 ? sizeof(WarpSmemT<false, 2>) : sizeof(WarpSmemT<false, 3>));
+    return per_warp * FAST_WARPS + sizeof(bamse_record) * FAST_WARPS * (size_t)(topk > 0 ? topk : 1);
 }
 
 void launch_tables_hs(const ProblemView& pv, const FastTables& ft, float* HS2, cudaStream_t s) {
@@ -329,15 +331,23 @@ void launch_tables_pairs(const ProblemView& pv, const FastTables& ft, float* PSE
 
 int enumerate_workers(int precision, int grid) { return precision == BAMSE_FP32 ? grid * FAST_WARPS : grid; }
 
-int enumerate_fast_grid_size(int device, int topk, bool framed) {
+// Kmax <= 6 needs two vector slots only -> 8 CTAs (32 warps) per SM instead of 7
+static int fast_slots(int Kmax, bool framed) { return (!framed && Kmax <= 6) ? 2 : 3; }
+
+int enumerate_fast_grid_size(int device, int topk, bool framed, int Kmax) {
     int sms = 148, per_sm = 1;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    const int slots = fast_slots(Kmax, framed);
+    const size_t smax = fast_smem_bytes(BAMSE_TOPK_MAX, framed, slots), sm = fast_smem_bytes(topk, framed, slots);
     if (framed) {
-        cudaFuncSetAttribute(k_enumerate_fast<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_smem_bytes(BAMSE_TOPK_MAX, true));
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_enumerate_fast<true>, FAST_THREADS, fast_smem_bytes(topk, true));
+        cudaFuncSetAttribute(k_enumerate_fast<true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smax);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_enumerate_fast<true, 3>, FAST_THREADS, sm);
+    } else if (slots == 2) {
+        cudaFuncSetAttribute(k_enumerate_fast<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smax);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_enumerate_fast<false, 2>, FAST_THREADS, sm);
     } else {
-        cudaFuncSetAttribute(k_enumerate_fast<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_smem_bytes(BAMSE_TOPK_MAX, false));
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_enumerate_fast<false>, FAST_THREADS, fast_smem_bytes(topk, false));
+        cudaFuncSetAttribute(k_enumerate_fast<false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smax);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_enumerate_fast<false, 3>, FAST_THREADS, sm);
     }
     if (per_sm < 1) per_sm = 1;
     return sms * per_sm;
@@ -345,8 +355,11 @@ int enumerate_fast_grid_size(int device, int topk, bool framed) {
 
 void launch_enumerate_fast(const ProblemView& pv, const FastTables& ft, const EnumWork& w, int grid, bool framed,
                            cudaStream_t s) {
-    if (framed) k_enumerate_fast<true><<<grid, FAST_THREADS, fast_smem_bytes(w.topk, true), s>>>(pv, ft, w);
-    else k_enumerate_fast<false><<<grid, FAST_THREADS, fast_smem_bytes(w.topk, false), s>>>(pv, ft, w);
+    const int slots = fast_slots(pv.Kmax, framed);
+    const size_t sm = fast_smem_bytes(w.topk, framed, slots);
+    if (framed) k_enumerate_fast<true, 3><<<grid, FAST_THREADS, sm, s>>>(pv, ft, w);
+    else if (slots == 2) k_enumerate_fast<false, 2><<<grid, FAST_THREADS, sm, s>>>(pv, ft, w);
+    else k_enumerate_fast<false, 3><<<grid, FAST_THREADS, sm, s>>>(pv, ft, w);
 }
 
 // ---------------------------------------------------------------------- explicit items (fp32)
@@ -366,7 +379,7 @@ __global__ void __launch_bounds__(FAST_THREADS) k_score_items_fast(ProblemView p
     ok = __shfl_sync(0xffffffffu, ok, 0);
     if (!ok) { if (lane == 0) out[idx] = CUDART_NAN; return; }
     unsigned s0 = 0, s1 = 0, s2 = 0;
-    const double score = warp_eval_tree<false>(pv, ft, it.p, it.c, ws, lane, &s0, &s1, &s2);
+    const double score = warp_eval_tree<false, WarpSmem>(pv, ft, it.p, it.c, ws, lane, &s0, &s1, &s2);
     if (lane == 0) out[idx] = score;
 }
 

@@ -64,7 +64,7 @@ struct FastTables;
 void launch_tables_fast(const ProblemView& pv, float* D2, float* EL2, float* SEL2, float* SD2, cudaStream_t s);
 void launch_tables_hs(const ProblemView& pv, const FastTables& ft, float* HS2, cudaStream_t s);
 void launch_tables_pairs(const ProblemView& pv, const FastTables& ft, float* PSE2, float* PEE2, cudaStream_t s);
-int enumerate_fast_grid_size(int device, int topk, bool framed);
+int enumerate_fast_grid_size(int device, int topk, bool framed, int Kmax);
 void launch_enumerate_fast(const ProblemView& pv, const FastTables& ft, const EnumWork& w, int grid, bool framed,
                            cudaStream_t s);
 void launch_score_items_fast(const ProblemView& pv, const FastTables& ft, const ScoreItem* d_items, int64_t n,
