@@ -431,8 +431,16 @@ def main():
                                 "convolution); the kernel exponentiates only the terms within 2^-36 of each "
                                 "output's maximum (log-concavity), so frac can exceed 1; xu_pipe_frac is the "
                                 "XU pipe utilisation of what actually executed"}
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+                tj = json.load(f)
+            if args.config == tj.get("config") and world == 1 and kname.startswith(tj["kernel"].split("<")[0]):
+                traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]     # per launch, from the committed ncu capture
+        except Exception:
+            pass
         roofline = {"bound": bound, "achieved": achieved, "peak": peak, "unit": unit, "frac": achieved / peak,
-                    "traffic": None, "peak_source": peaks["source"], "kernel": kname,
+                    "traffic": traffic, "peak_source": peaks["source"], "kernel": kname,
                     "kernel_ms_per_launch": kern_ms_max, "executed": executed,
                     "hbm": {"algorithmic_bytes_per_launch": int(h2d), "note": "HBM idle: inputs are KBs per launch"}}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
