@@ -172,3 +172,34 @@ def test_errors_are_reported_not_thrown(ctx, shim):
     with pytest.raises(shim.BamseCudaError) as e:
         ctx.score_list(clust, par, nod)
     assert e.value.code == -1
+
+
+def test_index_ranges_beyond_32_bits(ctx, shim):
+    """K = 12 has 12^11 = 7.4e11 labeled rooted trees: a range starting above 2^32 (and one of a
+    K = 9 clustering in the same problem) through the top-k path equals the dense check-mode
+    scores of the same indices."""
+    rng = np.random.default_rng(2026)
+    M, Kmax = 2, 12
+    Ks = [12, 9]
+    var = np.zeros((2, Kmax, M), dtype=np.int64)
+    ref = np.zeros((2, Kmax, M), dtype=np.int64)
+    for c, K in enumerate(Ks):
+        a, b = _random_problem(rng, K, M, 600)
+        var[c, :K], ref[c, :K] = a, b
+    ctx.upload_problem([0.004], Ks, var, ref)
+    begin = np.array([(1 << 33) + 12345, 9 ** 8 - 700], dtype=np.uint64)
+    n = [900, 700]
+    end = begin + np.array(n, dtype=np.uint64)
+    const = np.array([[0.0, 25.0]])
+    rec, par, cnt = ctx.score_topk(const, None, begin, end, topk=10, precision=shim.FP32)
+    assert cnt[0] == 10 and ctx.last_eval_count == sum(n)
+    full = []
+    for c in range(2):
+        s, w = ctx.score_range(0, c, int(begin[c]), n[c], shim.FP64)
+        full += [(-(s[i] + w[i] + const[0, c]), c, int(begin[c]) + i) for i in range(n[c])]
+    full.sort()
+    for j in range(10):
+        assert (int(rec[0, j]["clust"]), int(rec[0, j]["tree"])) == full[j][1:], j
+        assert rec[0, j]["total"] == pytest.approx(-full[j][0], rel=1e-10)
+        K = Ks[full[j][1]]
+        assert [int(x) for x in par[0, j, :K]] == orc.decode_tree(K, full[j][2])
