@@ -51,8 +51,10 @@ def algorithmic_ops_per_eval(K, M, L=512):
 
 # ------------------------------------------------------------------------------------------
 class ClockSampler(object):
-    """samples nvidia-smi clocks / throttle reasons during the timed region."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+    """samples nvidia-smi clocks / throttle reasons; start() early (nvidia-smi needs ~0.3 s to
+    produce its first row), then mark the timed regions with begin()/end(): only rows whose
+    timestamp falls inside a marked region are summarised."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
@@ -60,11 +62,13 @@ class ClockSampler(object):
         self.index = index
         self.rows = []
         self.proc = None
+        self.windows = []
+        self._t0 = None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "25"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -73,33 +77,52 @@ class ClockSampler(object):
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.time(), line.strip()))
+
+    def begin(self):
+        self._t0 = time.time()
+
+    def end(self):
+        if self._t0 is not None:
+            self.windows.append((self._t0, time.time()))
+            self._t0 = None
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.06)                     # let the last rows of the region arrive
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons, power = [], [], set(), []
+        sm, mx, reasons, power, sm_all = [], [], set(), [], []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for t_arrival, r in self.rows:
             f = [x.strip() for x in r.split(",")]
-            if len(f) < 7:
+            if len(f) < 8:
                 continue
             try:
-                sm.append(float(f[0]))
-                mx.append(float(f[1]))
-                power.append(float(f[2]))
+                # rows are stamped by nvidia-smi; parse its local-time stamp, fall back to arrival time
+                try:
+                    ts = time.mktime(time.strptime(f[0][:19], "%Y/%m/%d %H:%M:%S")) + float("0" + f[0][19:])
+                except Exception:
+                    ts = t_arrival
+                c, m, pw = float(f[1]), float(f[2]), float(f[3])
             except ValueError:
                 continue
-            for n, v in zip(names, f[3:7]):
+            sm_all.append(c)
+            if not any(lo - 0.03 <= ts <= hi + 0.03 for lo, hi in self.windows):
+                continue
+            sm.append(c)
+            mx.append(m)
+            power.append(pw)
+            for n, v in zip(names, f[4:8]):
                 if v.lower().startswith("active"):
                     reasons.add(n)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+                "power_w_max": max(power) if power else None, "samples": len(sm), "samples_total": len(sm_all),
+                "reasons": sorted(reasons), "regions": "resident + e2e timed regions"}
 
 
 # ------------------------------------------------------------------------------------------
@@ -228,7 +251,7 @@ def config_dict(args, work, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--config", default="c2", choices=["c1", "c2", "c3", "c4", "c5"])
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
@@ -341,22 +364,23 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     for _ in range(args.warmup):
         step_resident()
     barrier()
     ctx.kernel_time(reset=True)
     ctx.kernel_stats(reset=True)
     launches0 = ctx.launch_count
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler.begin()
     ev0.record()
     for _ in range(args.steps):
         step_resident()
     ev1.record()
     barrier()
-    clocks = sampler.stop() if rank == 0 else None
+    sampler.end()
     ms = ev0.elapsed_time(ev1)
     kern_ms, kern_n = ctx.kernel_time(reset=True)
     stats = ctx.kernel_stats(reset=True)
@@ -392,11 +416,14 @@ def main():
         step_e2e()
     barrier()
     e2e_steps = args.steps
+    sampler.begin()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         e2e_rec = step_e2e()
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    sampler.end()
+    clocks = sampler.stop() if rank == 0 else None
     te2e = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(te2e, op=dist.ReduceOp.MAX)
@@ -428,7 +455,7 @@ def main():
                         "conv_terms_executed_per_launch": stats["conv_terms"] / max(1, kern_n),
                         "conv_terms_algorithmic_per_launch": terms,
                         "note": "achieved/frac use the ALGORITHMIC op count (SURVEY 8d: every term of every "
-                                "convolution); the kernel exponentiates only the terms within 2^-36 of each "
+                                "convolution); the kernel exponentiates only the terms within 2^-30 of each "
                                 "output's maximum (log-concavity), so frac can exceed 1; xu_pipe_frac is the "
                                 "XU pipe utilisation of what actually executed"}
         traffic = None
