@@ -265,8 +265,13 @@ def analyse_clusterings(clusts, top_trees, ctx=None, precision=cuda_shim.FP32, s
     # 4. exhaustive enumeration + global top-k
     if tree_shard is not None:
         ctx.set_shard(*tree_shard)
-    rec, par, cnt = ctx.score_topk(const, thr, None, None, topk=min(max(int(top_trees), 1), cuda_shim.TOPK_MAX),
-                                   precision=precision)
+    # the search only needs the trees that can still qualify: exact sample-level early exit
+    ctx.set_early_exit(True)
+    try:
+        rec, par, cnt = ctx.score_topk(const, thr, None, None, topk=min(max(int(top_trees), 1), cuda_shim.TOPK_MAX),
+                                       precision=precision)
+    finally:
+        ctx.set_early_exit(False)
     out = []
     for j in range(int(cnt[0])):
         c = clusts[int(rec[0, j]['clust'])]

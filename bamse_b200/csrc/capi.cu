@@ -54,6 +54,7 @@ struct bamse_ctx {
     DBuf d_const, d_thr, d_begin, d_end, d_records, d_dense0, d_dense1, d_pb, d_pe;
     int grid[3] = {0, 0, 0};
     int shard_rank = 0, shard_world = 1;
+    int early_exit = 0;      // BAMSE_OPT_EARLY_EXIT
     int use_framed = -1;     // fp32 kernel variant for the resident problem: -1 not probed yet, 0 exponential, 1 framed
     bool probing = false;
     uint64_t problem_sig = 0, probed_sig = 0;   // the variant choice is memoised per problem content
@@ -169,6 +170,23 @@ int bamse_set_shard(bamse_ctx* ctx, int rank, int world) {
 }
 
 int bamse_fast_variant(const bamse_ctx* ctx) { return ctx ? ctx->use_framed : -1; }
+
+int bamse_set_option(bamse_ctx* ctx, int option, int value) {
+    CTX_CHECK(ctx);
+    if (option == BAMSE_OPT_EARLY_EXIT) { ctx->early_exit = value ? 1 : 0; return BAMSE_OK; }
+    return ctx->fail(BAMSE_EINVAL, "bamse_set_option: unknown option %d", option);
+}
+
+int64_t bamse_samples_evaluated(bamse_ctx* ctx, int reset) {
+    if (!ctx || !ctx->d_scalars.p) return 0;
+    cudaSetDevice(ctx->device);
+    uint64_t v = 0;
+    uint64_t* scal = ctx->d_scalars.as<uint64_t>();
+    if (cudaMemcpyAsync(&v, scal + 8, sizeof v, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) return -1;
+    if (reset) cudaMemsetAsync(scal + 8, 0, sizeof v, ctx->stream);
+    cudaStreamSynchronize(ctx->stream);
+    return (int64_t)v;
+}
 
 int64_t bamse_launch_count(const bamse_ctx* ctx) { return ctx ? ctx->launches : 0; }
 int64_t bamse_last_eval_count(const bamse_ctx* ctx) { return ctx ? ctx->last_evals : 0; }
@@ -478,9 +496,9 @@ static int enumerate_dev(bamse_ctx* ctx, const double* d_const, const double* d_
     const uint64_t cand_cap = cand_lists * (uint64_t)(topk > 0 ? topk : 0);
     BAMSE_CUDA_TRY(ctx, ctx->d_segs.ensure(sizeof(Segment) * P * C));
     const bool fresh_scalars = ctx->d_scalars.p == nullptr;
-    BAMSE_CUDA_TRY(ctx, ctx->d_scalars.ensure(sizeof(uint64_t) * 8));
+    BAMSE_CUDA_TRY(ctx, ctx->d_scalars.ensure(sizeof(uint64_t) * 10));
     uint64_t* scal = ctx->d_scalars.as<uint64_t>();
-    BAMSE_CUDA_TRY(ctx, cudaMemsetAsync(scal, 0, sizeof(uint64_t) * (fresh_scalars ? 8 : 4), s));   // stats [4..8) accumulate until read
+    BAMSE_CUDA_TRY(ctx, cudaMemsetAsync(scal, 0, sizeof(uint64_t) * (fresh_scalars ? 10 : 4), s));   // stats [4..8) accumulate until read
     if (topk > 0) BAMSE_CUDA_TRY(ctx, ctx->d_cand.ensure(sizeof(bamse_record) * (size_t)cand_cap));
     EnumWork w;
     if (host_seg) {
@@ -508,6 +526,9 @@ static int enumerate_dev(bamse_ctx* ctx, const double* d_const, const double* d_
     w.dense_score = d_dense_score;
     w.dense_logscre = d_dense_logscre;
     w.stats = reinterpret_cast<unsigned long long*>(scal + 4);
+    w.samples_done = reinterpret_cast<unsigned long long*>(scal + 8);
+    // early exit only where pruned trees cannot matter: top-k enumerations (not dense ranges, not probes)
+    w.early_exit = (ctx->early_exit && !host_seg && !ctx->probing && topk > 0 && precision == BAMSE_FP32) ? 1 : 0;
     std::pair<cudaEvent_t, cudaEvent_t> ev;
     if (!ctx->ev_free.empty()) { ev = ctx->ev_free.back(); ctx->ev_free.pop_back(); }
     else {

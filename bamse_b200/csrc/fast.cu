@@ -88,9 +88,13 @@ __device__ inline void warp_init_guards(W* ws, int lane) {
 }
 
 // score of the tree whose program sits in ws->prog, summed over samples (fp64), natural log
+// `cut`: early-exit bound on the sum over samples (-inf = evaluate everything).  Every per-sample
+// score is <= 0 (a log of an average of products of probabilities <= 1), so once the partial sum is
+// below the cut the tree cannot reach it; *n_done returns the samples actually evaluated.
 template <bool FRAMED, class WS>
 __device__ inline double warp_eval_tree(const ProblemView& pv, const FastTables& ft, int p, int c, WS* ws,
-                                        int lane, unsigned* st_chunks, unsigned* st_convs, unsigned* st_scans) {
+                                        int lane, unsigned* st_chunks, unsigned* st_convs, unsigned* st_scans,
+                                        double cut = (double)-INFINITY, unsigned* n_done = nullptr) {
     const float add2 = (float)((pv.p0[c] - 6.2383246250395077847550890931236) * 1.4426950408889634074);
     const int n_ops = ws->prog.n_ops;
     double total = 0.0;
@@ -128,7 +132,12 @@ __device__ inline double warp_eval_tree(const ProblemView& pv, const FastTables&
         float res2 = warp_log2dot(ws->vec[0] + GUARD, tab, lane);
         if (fin == FIN_LSE || fin == FIN_DOT_D) res2 -= LOG2_L;
         total += (double)res2 * 0.69314718055994530942;
+        if (total < cut) {                           // warp-uniform: res2 is the same in every lane
+            if (n_done) *n_done += m + 1;
+            return -CUDART_INF;
+        }
     }
+    if (n_done) *n_done += pv.M;
     return total;
 }
 
@@ -248,8 +257,18 @@ k_enumerate_fast(ProblemView pv, FastTables ft, EnumWork w) {
             const uint64_t tree = seg.tree_begin + (off + i) * (uint64_t)seg.stride;
             if (lane == 0) build_tree_program(seg.K, tree, &ws->prog, ft.HS2 != nullptr, ft.PSE2 ? pv.Kmax : 0);
             __syncwarp();
-            const double score = warp_eval_tree<FRAMED, WS>(pv, ft, seg.p, seg.c, ws, lane, &st_chunks, &st_convs, &st_scans);
-            st_samples += pv.M;
+            double cut = -CUDART_INF;
+            if (w.early_exit) {
+                // lane 0 knows the warp's k-th best and this tree's log scre; fp32 slack of 1e-3 nats
+                if (lane == 0) {
+                    double c0 = seg.threshold;
+                    if (w.topk > 0 && ntop == w.topk) c0 = fmax(c0, list[w.topk - 1].total - seg.clust_const);
+                    cut = c0 - log((double)ws->prog.scre) - 1e-3 - 1e-6 * fabs(c0);
+                }
+                cut = __shfl_sync(0xffffffffu, cut, 0);
+            }
+            const double score = warp_eval_tree<FRAMED, WS>(pv, ft, seg.p, seg.c, ws, lane, &st_chunks, &st_convs, &st_scans,
+                                                            cut, &st_samples);
             if (lane == 0) {
                 const double logscre = log((double)ws->prog.scre);
                 const double full = score + logscre;
@@ -307,6 +326,7 @@ k_enumerate_fast(ProblemView pv, FastTables ft, EnumWork w) {
         atomicAdd(w.stats + 2, (unsigned long long)st_convs);
         atomicAdd(w.stats + 3, (unsigned long long)st_scans);
     }
+    if (w.samples_done && lane == 0) atomicAdd(w.samples_done, (unsigned long long)st_samples);
 }
 
 static size_t fast_smem_bytes(int topk, bool framed = false, int slots = FAST_SLOTS) {

@@ -41,6 +41,8 @@ struct EnumWork {
     double* dense_score;     // optional [n_trees of segment 0]
     double* dense_logscre;   // optional
     unsigned long long* stats;   // optional [4]: executed MUFU ops (thread level), conv terms, convs, scans
+    unsigned long long* samples_done;   // optional: tree-samples actually evaluated (early exit statistics)
+    int early_exit;              // fp32 kernel: stop a tree once its partial sum over samples cannot reach the cut
 };
 
 void launch_tables(const ProblemView& pv, const double* d_var, const double* d_ref, const double* d_logc,

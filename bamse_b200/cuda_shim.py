@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libbamse_cuda.so")
 FP32 = 0
 FP64 = 1
 FP32_LOGDOMAIN = 2
+OPT_EARLY_EXIT = 1
 KMAX = 12
 TOPK_MAX = 64
 GRID = 512
@@ -56,6 +57,10 @@ def load_library():
     lib.bamse_set_shard.argtypes = [c_p, i32, i32]
     lib.bamse_fast_variant.restype = i32
     lib.bamse_fast_variant.argtypes = [c_p]
+    lib.bamse_set_option.restype = i32
+    lib.bamse_set_option.argtypes = [c_p, i32, i32]
+    lib.bamse_samples_evaluated.restype = i64
+    lib.bamse_samples_evaluated.argtypes = [c_p, i32]
     lib.bamse_launch_count.restype = i64
     lib.bamse_launch_count.argtypes = [c_p]
     lib.bamse_last_eval_count.restype = i64
@@ -85,7 +90,7 @@ def load_library():
 
 
 EXPORTED_SYMBOLS = [
-    "bamse_abi_version", "bamse_create", "bamse_destroy", "bamse_last_error", "bamse_set_stream", "bamse_set_shard", "bamse_fast_variant",
+    "bamse_abi_version", "bamse_create", "bamse_destroy", "bamse_last_error", "bamse_set_stream", "bamse_set_shard", "bamse_fast_variant", "bamse_set_option", "bamse_samples_evaluated",
     "bamse_launch_count", "bamse_last_eval_count", "bamse_decode_tree", "bamse_upload_problem",
     "bamse_score_list", "bamse_score_range", "bamse_score_topk", "bamse_enumerate_topk_dev",
     "bamse_merge_topk_dev", "bamse_kernel_time", "bamse_kernel_stats",
@@ -148,6 +153,13 @@ class Context(object):
     def set_shard(self, rank, world):
         """interleaved multi-GPU sharding of every enumeration of this context."""
         self._check(self._lib.bamse_set_shard(self._h, int(rank), int(world)))
+
+    def set_early_exit(self, on):
+        """BAMSE_OPT_EARLY_EXIT: exact sample-level early exit in fp32 top-k enumerations."""
+        self._check(self._lib.bamse_set_option(self._h, 1, 1 if on else 0))
+
+    def samples_evaluated(self, reset=True):
+        return int(self._lib.bamse_samples_evaluated(self._h, 1 if reset else 0))
 
     @property
     def fast_variant(self):

@@ -79,6 +79,16 @@ int bamse_set_shard(bamse_ctx* ctx, int rank, int world);
  * (MUFU) path only, 1 = with the linear-domain "framed" path, -1 = not decided yet.  Decided by a
  * ~1 ms timing probe on the first enumeration of a problem (BAMSE_FRAMED=0/1 overrides). */
 int bamse_fast_variant(const bamse_ctx* ctx);
+/* Options.  BAMSE_OPT_EARLY_EXIT (default 0): in fp32 top-k enumerations, stop scoring a tree as soon
+ * as its partial sum over samples is below what it needs (the threshold of its clustering / the k-th
+ * best so far).  Exact: every per-sample score is <= 0, so a tree stopped early cannot qualify, and
+ * the returned top-k is identical (it is re-scored in fp64 either way).  This mirrors what the
+ * reference's branch-and-bound does with partial forests (clustering.py:136-138), but with a bound
+ * that never discards a qualifying tree.  Off by default: bench.py's headline scores every sample of
+ * every tree.  bamse_samples_evaluated returns the (tree, sample) evaluations since the last reset. */
+#define BAMSE_OPT_EARLY_EXIT 1
+int bamse_set_option(bamse_ctx* ctx, int option, int value);
+int64_t bamse_samples_evaluated(bamse_ctx* ctx, int reset);
 /* Number of kernels this ctx has launched since creation (for bench.py `gpu_launches`). */
 int64_t bamse_launch_count(const bamse_ctx* ctx);
 

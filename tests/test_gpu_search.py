@@ -251,3 +251,33 @@ def test_cli_end_to_end(tmp_path, monkeypatch, ctx):
     for name in ("tree_number_0_subclones.dot", "tree_number_0_samples.dot", "tree_number_0.txt"):
         assert (tmp_path / name).read_text()
     assert (tmp_path / "tree_number_0_subclones.dot").read_text().startswith("digraph {\nSubcloneA [")
+
+
+def test_early_exit_returns_the_same_topk(ctx, shim):
+    """BAMSE_OPT_EARLY_EXIT: identical records with and without the exact sample-level early exit,
+    while a good share of the (tree, sample) evaluations is skipped."""
+    from bamse_b200 import workloads
+    from bamse_b200.clustering import _pack_problem
+    w = workloads.build("c1", ctx=ctx)
+    clusts = w["clusts"]
+    Ks, var, ref, Kmax = _pack_problem(clusts)
+    ctx.upload_problem([0.001], Ks, var, ref)
+    const = np.array([[c.cluster_prior + c.maxlikelihood for c in clusts]])
+    # thresholds: the best score of each clustering minus 5 nats (what a good greedy candidate gives)
+    thr = np.zeros((1, len(clusts)))
+    for ci, K in enumerate(Ks):
+        s, lw = ctx.score_range(0, ci, 0, int(K) ** (int(K) - 1), shim.FP64)
+        thr[0, ci] = (s + lw).max() - 5.0
+    total_samples = sum(int(K) ** (int(K) - 1) for K in Ks) * var.shape[2]
+    out = {}
+    for on in (False, True):
+        ctx.set_early_exit(on)
+        ctx.samples_evaluated(reset=True)
+        out[on] = (ctx.score_topk(const, thr, topk=6, precision=shim.FP32), ctx.samples_evaluated(reset=True))
+    ctx.set_early_exit(False)
+    (rec0, par0, cnt0), n0 = out[False]
+    (rec1, par1, cnt1), n1 = out[True]
+    assert cnt0[0] == cnt1[0] >= 1
+    assert rec0["tree"].tolist() == rec1["tree"].tolist() and rec0["clust"].tolist() == rec1["clust"].tolist()
+    np.testing.assert_array_equal(rec0["total"], rec1["total"])
+    assert n0 == total_samples and n1 < 0.8 * total_samples
