@@ -281,3 +281,22 @@ def test_early_exit_returns_the_same_topk(ctx, shim):
     assert rec0["tree"].tolist() == rec1["tree"].tolist() and rec0["clust"].tolist() == rec1["clust"].tolist()
     np.testing.assert_array_equal(rec0["total"], rec1["total"])
     assert n0 == total_samples and n1 < 0.8 * total_samples
+
+
+def test_config2_full_size_fp32_equals_check_mode(ctx, shim):
+    """BASELINE config 2 at full size (79 clusterings, 397 530 labeled rooted trees, 10 samples):
+    the fp32 production path (with the exact early exit the CLI driver uses) and a complete fp64
+    check-mode enumeration return identical top-t trees, clusterings and assignments."""
+    from bamse_b200 import workloads
+    from bamse_b200.clustering import analyse_clusterings
+    w32 = workloads.build("c2", ctx=ctx)
+    assert w32["n_evals_per_param"] == 397530
+    t32 = analyse_clusterings(w32["clusts"], 5, ctx=ctx, precision=shim.FP32, solve_fractions=False)
+    w64 = workloads.build("c2", ctx=ctx)
+    t64 = analyse_clusterings(w64["clusts"], 5, ctx=ctx, precision=shim.FP64, solve_fractions=False)
+    assert len(t32) == len(t64) == 5
+    for a, b in zip(t32, t64):
+        assert a["tree"] == b["tree"] and a["clustering_index"] == b["clustering_index"]
+        assert a["assign"].tolist() == b["assign"].tolist()
+        assert a["totalscore"] == pytest.approx(b["totalscore"], rel=1e-10)
+    assert t64[0]["totalscore"] > t64[-1]["totalscore"]
