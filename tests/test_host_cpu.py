@@ -175,3 +175,35 @@ def test_fraction_solver_recovers_planted_fractions():
     As = np.rint(cov * (er + prev * (0.5 - er))).astype(int)
     res = solve4(B, As, cov - As, er, [np.ones(3)] * 2)
     np.testing.assert_allclose(res['s'], x_true, atol=2e-3)
+
+
+def test_workloads_are_reproducible():
+    """the BASELINE.json configurations as work lists: seeded, same clusterings every time."""
+    from bamse_b200 import workloads
+    a = workloads.build("c1")
+    b = workloads.build("c1")
+    assert a["n_evals_per_param"] == b["n_evals_per_param"] == 523
+    assert [c.assign.tolist() for c in a["clusts"]] == [c.assign.tolist() for c in b["clusts"]]
+    assert a["M"] == 3 and a["data"]["As"].shape == (50, 3) and len(a["errs"]) == 1
+    c2 = workloads.build("c2")
+    assert c2["n_evals_per_param"] == 397530 and len(c2["clusts"]) == 79 and c2["M"] == 10
+    assert len(workloads.CONFIGS["c5"]["errs"]) == 64
+
+
+def test_algorithmic_op_count_uses_the_mean_leaf_count():
+    """bench.py's roofline numerator: E[leaves] = K (1 - 1/K)^(K-1) over all labeled rooted trees
+    (SURVEY section 8d), checked by enumeration."""
+    import importlib.util
+    import bamse_oracle as orc
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    for K in range(2, 7):
+        leaves = 0
+        for i in range(K ** (K - 1)):
+            p = orc.decode_tree(K, i)
+            leaves += sum(1 for v in range(K) if v not in p)
+        assert leaves / K ** (K - 1) == pytest.approx(bench.mean_leaves(K), rel=1e-12)
+    n_c, xu, flops = bench.algorithmic_ops_per_eval(7, 10)
+    assert n_c == pytest.approx(10 * (bench.mean_leaves(7) - 1) * 131328)
+    assert xu > n_c and flops > 4 * n_c
