@@ -51,7 +51,7 @@ struct bamse_ctx {
 
     // work buffers
     DBuf d_segs, d_scalars /* total_chunks, total_trees, next_chunk */, d_cand, d_items, d_scores;
-    DBuf d_const, d_thr, d_begin, d_end, d_records, d_dense0, d_dense1, d_pb, d_pe;
+    DBuf d_const, d_thr, d_begin, d_end, d_records, d_dense0, d_dense1, d_pb, d_pe, d_split;
     int grid[3] = {0, 0, 0};
     int shard_rank = 0, shard_world = 1;
     int early_exit = 0;      // BAMSE_OPT_EARLY_EXIT
@@ -148,7 +148,7 @@ void bamse_destroy(bamse_ctx* ctx) {
     DBuf* bufs[] = {&ctx->d_K, &ctx->d_p0, &ctx->d_var, &ctx->d_ref, &ctx->d_logc, &ctx->d_logcf, &ctx->d_log1mcf,
                     &ctx->d_D64, &ctx->d_D32, &ctx->d_D2, &ctx->d_EL2, &ctx->d_SEL2, &ctx->d_SD2, &ctx->d_HS2, &ctx->d_PSE2, &ctx->d_PEE2, &ctx->d_segs, &ctx->d_scalars, &ctx->d_cand, &ctx->d_items,
                     &ctx->d_scores, &ctx->d_const, &ctx->d_thr, &ctx->d_begin, &ctx->d_end, &ctx->d_records,
-                    &ctx->d_dense0, &ctx->d_dense1, &ctx->d_pb, &ctx->d_pe};
+                    &ctx->d_dense0, &ctx->d_dense1, &ctx->d_pb, &ctx->d_pe, &ctx->d_split};
     for (DBuf* b : bufs) b->release();
     for (auto* v : {&ctx->ev_used, &ctx->ev_free})
         for (auto& ev : *v) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
@@ -529,6 +529,20 @@ static int enumerate_dev(bamse_ctx* ctx, const double* d_const, const double* d_
     w.samples_done = reinterpret_cast<unsigned long long*>(scal + 8);
     // early exit only where pruned trees cannot matter: top-k enumerations (not dense ranges, not probes)
     w.early_exit = (ctx->early_exit && !host_seg && !ctx->probing && topk > 0 && precision == BAMSE_FP32) ? 1 : 0;
+    // tail splitting: when a worker gets fewer than ~48 single-tree chunks, issue the last `workers`
+    // trees in 2 (or, below 16 chunks per worker, 4) parts over the samples
+    w.split_ways = 1; w.n_split = 0; w.split_acc = nullptr; w.split_cnt = nullptr;
+    const char* no_split = getenv("BAMSE_SPLIT");      // BAMSE_SPLIT=0 disables (A/B measurements)
+    if (precision == BAMSE_FP32 && chunk == 1 && !ctx->probing && ctx->M >= 4 && trees_upper < (uint64_t)workers * 48 &&
+        !(no_split && atoi(no_split) == 0)) {
+        w.split_ways = (ctx->M >= 8 && trees_upper < (uint64_t)workers * 16) ? 4 : 2;
+        w.n_split = (unsigned long long)workers;
+        const size_t bytes = (sizeof(double) + sizeof(int)) * (size_t)workers;
+        BAMSE_CUDA_TRY(ctx, ctx->d_split.ensure(bytes));
+        BAMSE_CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_split.p, 0, bytes, s));
+        w.split_acc = ctx->d_split.as<double>();
+        w.split_cnt = reinterpret_cast<int*>(ctx->d_split.as<double>() + workers);
+    }
     std::pair<cudaEvent_t, cudaEvent_t> ev;
     if (!ctx->ev_free.empty()) { ev = ctx->ev_free.back(); ctx->ev_free.pop_back(); }
     else {

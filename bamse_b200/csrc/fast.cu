@@ -94,12 +94,15 @@ __device__ inline void warp_init_guards(W* ws, int lane) {
 template <bool FRAMED, class WS>
 __device__ inline double warp_eval_tree(const ProblemView& pv, const FastTables& ft, int p, int c, WS* ws,
                                         int lane, unsigned* st_chunks, unsigned* st_convs, unsigned* st_scans,
-                                        double cut = (double)-INFINITY, unsigned* n_done = nullptr) {
+                                        double cut = (double)-INFINITY, unsigned* n_done = nullptr, int m_begin = 0,
+                                        int m_step = 1) {
     const float add2 = (float)((pv.p0[c] - 6.2383246250395077847550890931236) * 1.4426950408889634074);
     const int n_ops = ws->prog.n_ops;
     double total = 0.0;
-    for (int m = 0; m < pv.M; ++m) {
+    unsigned done = 0;
+    for (int m = m_begin; m < pv.M; m += m_step) {
         const size_t base = pv.table_offset(p, c, m);
+        ++done;
         int sp = 0;                                  // stack position == slot (convolution is in place)
         for (int i = 0; i < n_ops; ++i) {
             const int op = ws->prog.op[i];
@@ -133,11 +136,11 @@ __device__ inline double warp_eval_tree(const ProblemView& pv, const FastTables&
         if (fin == FIN_LSE || fin == FIN_DOT_D) res2 -= LOG2_L;
         total += (double)res2 * 0.69314718055994530942;
         if (total < cut) {                           // warp-uniform: res2 is the same in every lane
-            if (n_done) *n_done += m + 1;
+            if (n_done) *n_done += done;
             return -CUDART_INF;
         }
     }
-    if (n_done) *n_done += pv.M;
+    if (n_done) *n_done += done;
     return total;
 }
 
@@ -238,11 +241,28 @@ k_enumerate_fast(ProblemView pv, FastTables ft, EnumWork w) {
         }
     };
 
+    // Tail splitting: the last n_split single-tree chunks are issued as split_ways items each (every
+    // item takes the samples m = h, h + ways, ...); the parts meet in split_acc / split_cnt and the part
+    // that finishes last ranks the tree.  With few trees per warp (multi-GPU shards of a small
+    // problem) this shortens the tail of the launch from one tree to a fraction of one.
+    const int ways = w.split_ways > 1 ? w.split_ways : 1;
+    const uint64_t n_split = ways > 1 ? (w.n_split < total ? w.n_split : total) : 0;
+    const uint64_t split_from = total - n_split;
+    const uint64_t vtotal = split_from + n_split * (uint64_t)ways;
     for (;;) {
         unsigned long long chunk = 0;
         if (lane == 0) chunk = atomicAdd(w.next_chunk, 1ull);
         chunk = __shfl_sync(0xffffffffu, chunk, 0);
-        if (chunk >= total) break;
+        if (chunk >= vtotal) break;
+        int part = 0, step = 1;
+        uint64_t split_slot = 0;
+        if (chunk >= split_from) {
+            const uint64_t k = chunk - split_from;
+            split_slot = k / (uint64_t)ways;
+            part = (int)(k - split_slot * (uint64_t)ways);
+            step = ways;
+            chunk = split_from + split_slot;
+        }
         int lo = 0, hi = w.n_segs - 1;
         while (lo < hi) {
             const int mid = (lo + hi + 1) >> 1;
@@ -267,8 +287,21 @@ k_enumerate_fast(ProblemView pv, FastTables ft, EnumWork w) {
                 }
                 cut = __shfl_sync(0xffffffffu, cut, 0);
             }
-            const double score = warp_eval_tree<FRAMED, WS>(pv, ft, seg.p, seg.c, ws, lane, &st_chunks, &st_convs, &st_scans,
-                                                            cut, &st_samples);
+            double score = warp_eval_tree<FRAMED, WS>(pv, ft, seg.p, seg.c, ws, lane, &st_chunks, &st_convs, &st_scans,
+                                                      cut, &st_samples, part, step);
+            if (step > 1) {
+                // combine the parts; only the last one to arrive goes on (two or four addends per
+                // tree: the sum does not depend on the arrival order beyond the last bit)
+                int last = 0;
+                if (lane == 0) {
+                    atomicAdd(w.split_acc + split_slot, score);
+                    __threadfence();
+                    last = atomicAdd(w.split_cnt + split_slot, 1) == step - 1;
+                    if (last) score = atomicAdd(w.split_acc + split_slot, 0.0);
+                }
+                last = __shfl_sync(0xffffffffu, last, 0);
+                if (!last) { __syncwarp(); continue; }
+            }
             if (lane == 0) {
                 const double logscre = log((double)ws->prog.scre);
                 const double full = score + logscre;

@@ -43,6 +43,12 @@ struct EnumWork {
     unsigned long long* stats;   // optional [4]: executed MUFU ops (thread level), conv terms, convs, scans
     unsigned long long* samples_done;   // optional: tree-samples actually evaluated (early exit statistics)
     int early_exit;              // fp32 kernel: stop a tree once its partial sum over samples cannot reach the cut
+    // tail splitting (fp32 kernel, chunk == 1): the last `n_split` trees of the launch are issued as
+    // split_ways work items each (samples m = h, h + ways, ...), combined through split_acc/split_cnt
+    int split_ways;              // 1 = off
+    unsigned long long n_split;  // upper bound on the trees issued split (size of the two buffers)
+    double* split_acc;           // [n_split] partial sums (zeroed before launch)
+    int* split_cnt;              // [n_split] finished parts (zeroed before launch)
 };
 
 void launch_tables(const ProblemView& pv, const double* d_var, const double* d_ref, const double* d_logc,

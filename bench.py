@@ -260,6 +260,8 @@ def main():
     ap.add_argument("--ref-items", type=int, default=16, help="work items per step of the reference arm")
     ap.add_argument("--cpu-items", type=int, default=16, help="sample size of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--emulate-shard-of", type=int, default=0,
+                    help="debug: one GPU scores only shard 0 of W (what each rank of a W-GPU run does)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
 
@@ -331,6 +333,9 @@ def main():
     ctx.set_shard(rank, world)
     tb = te = None
     total_evals = work["n_evals_per_param"] * P
+    if args.emulate_shard_of > 1 and world == 1:
+        ctx.set_shard(0, args.emulate_shard_of)
+        total_evals = sum(-(-int(k) ** (int(k) - 1) // args.emulate_shard_of) for k in Ks) * P
     topk = args.topk
 
     # ---- device-resident state for the `value` measurement
