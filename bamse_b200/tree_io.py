@@ -59,64 +59,63 @@ def table_expression(remheight, remwidth, border, orient, tree, node, vafs, colo
 
 def put_sample_in_node(tree, vafs_tr, sample_names, sample_colors, cluster_colors, height=100, width=100, border=2,
                        orient='v'):
-    """one plaintext dot node per sample (reference tree_io.py:61-73)."""
-    out = ''
-    for n, name in enumerate(sample_names):
-        shifted = [-1] + list((np.array(tree) + 1).astype(int))       # virtual germline root 0
-        colors = tuple(["black"] + list(cluster_colors))
-        vafs = [1.0] + list(vafs_tr[n])
-        present = [0] + [x for x in range(1, len(vafs)) if (vafs[x] > 0.04)]
-        for x in range(len(vafs)):
-            if x not in present:
-                shifted[x] = -5
-        body = table_expression(height, width, border, 'v', shifted, 0, vafs, colors)[4:-5]
-        out += name + ' [\n    shape=plaintext\n    xlabel ="' + name + '"\n    label=<\n' + body + '\n  >];'
-    return out
+    """one plaintext dot node per sample (reference tree_io.py:61-73): the subclone tree is hung under
+    a virtual germline node 0; subclones below 4 % prevalence in the sample are cut off."""
+    palette = ("black",) + tuple(cluster_colors)
+    nodes = []
+    for name, row in zip(sample_names, vafs_tr):
+        prevalence = [1.0] + list(row)
+        parents = [-1] + [int(p) + 1 for p in np.array(tree)]
+        for k in range(1, len(prevalence)):
+            if not prevalence[k] > 0.04:
+                parents[k] = -5
+        tiling = table_expression(height, width, border, 'v', parents, 0, prevalence, palette)
+        nodes.append('%s [\n    shape=plaintext\n    xlabel ="%s"\n    label=<\n%s\n  >];' % (name, name, tiling[4:-5]))
+    return ''.join(nodes)
+
+
+_BAR_EMPTY = ('<td FIXEDSIZE="TRUE" HEIGHT="110" WIDTH="%d" cellpadding="0"><table cellspacing="0" cellpadding="0" '
+              'cellborder="0" border="0"><tr><td FIXEDSIZE="TRUE" HEIGHT="%d" WIDTH="%d" > </td></tr>')
+_BAR_FILL = ' <tr><td FIXEDSIZE="TRUE" HEIGHT="%d" WIDTH="%d" bgcolor="%s" > </td></tr>'
 
 
 def chart_plot(subclone_letter, color, percentages, sample_names, sample_colors, num_muts, bar_width=30, border=3):
-    """bar chart node of one subclone (reference tree_io.py:96-115)."""
-    out = ('Subclone' + subclone_letter + ' [\n      shape=plaintext\n      label=<<table FIXEDSIZE="TRUE" HEIGHT="170" WIDTH="'
-           + str(bar_width * len(sample_names) + 60) + '" color="' + color + '" bgcolor="' + color + '" border="'
-           + str(border) + '" cellborder="0" cellspacing="0">\n')
-    out += '<tr><td rowspan ="3">' + subclone_letter + '-' + str(num_muts) + ' </td>\n'
+    """bar chart node of one subclone: one bar per sample, the rounded percentages, the sample names
+    (reference tree_io.py:96-115)."""
+    parts = ['Subclone%s [\n      shape=plaintext\n      label=<<table FIXEDSIZE="TRUE" HEIGHT="170" WIDTH="%d" color="%s" '
+             'bgcolor="%s" border="%d" cellborder="0" cellspacing="0">\n'
+             % (subclone_letter, bar_width * len(sample_names) + 60, color, color, border),
+             '<tr><td rowspan ="3">%s-%d </td>\n' % (subclone_letter, num_muts)]
     for n in range(len(sample_names)):
-        pct = int(100 * percentages[n])
-        if pct < 100:
-            out += ('<td FIXEDSIZE="TRUE" HEIGHT="110" WIDTH="' + str(bar_width)
-                    + '" cellpadding="0"><table cellspacing="0" cellpadding="0" cellborder="0" border="0"><tr><td '
-                    + 'FIXEDSIZE="TRUE" HEIGHT="' + str(100 - pct) + '" WIDTH="' + str(bar_width - 2) + '" > </td></tr>')
-        if pct > 2:
-            out += (' <tr><td FIXEDSIZE="TRUE" HEIGHT="' + str(pct) + '" WIDTH="' + str(bar_width - 2) + '" bgcolor="'
-                    + sample_colors[n] + '" > </td></tr>')
-        out += '</table></td>'
-    out += '</tr><tr>'
-    for x in percentages:
-        out += '<td>' + str(int(np.around(100 * x, 0))) + '</td>'
-    out += '</tr><tr>'
-    for x in sample_names:
-        out += '<td>' + x + '</td>'
-    return out + '</tr></table> \n>]'
+        filled = int(100 * percentages[n])
+        if filled < 100:
+            parts.append(_BAR_EMPTY % (bar_width, 100 - filled, bar_width - 2))
+        if filled > 2:
+            parts.append(_BAR_FILL % (filled, bar_width - 2, sample_colors[n]))
+        parts.append('</table></td>')
+    parts.append('</tr><tr>')
+    parts.extend('<td>%d</td>' % int(np.around(100 * x, 0)) for x in percentages)
+    parts.append('</tr><tr>')
+    parts.extend('<td>%s</td>' % x for x in sample_names)
+    parts.append('</tr></table> \n>]')
+    return ''.join(parts)
 
 
 def write_dot_files(dat, sample_colors, cluster_colors, treeoutfile, samplesoutfile):
     """graphviz files: per-sample tilings and the subclone tree (reference tree_io.py:77-93)."""
-    body = put_sample_in_node(dat['tree'], dat['vaf'].transpose(), dat['sample_names'], sample_colors, cluster_colors,
-                              height=150, width=150)
+    K = len(dat['tree'])
+    per_sample = dat['vaf'].transpose()
     with open(samplesoutfile, 'w') as f:
-        f.write('digraph {\n' + body + '}\n')
-    letters = [chr(65 + x) for x in range(len(dat['tree']))]
-    body = ''
-    for x in range(len(dat['tree'])):
-        n_mut = len([y for y in dat['assign'] if y == x])
-        body += chart_plot(letters[x], cluster_colors[x], dat['vaf'].transpose()[:, x], dat['sample_names'],
-                           sample_colors, n_mut)
-    body += '\n'
-    for x in range(len(dat['tree'])):
-        if not x == dat['root']:
-            body += 'Subclone' + letters[int(dat['tree'][x])] + ' -> Subclone' + letters[x] + '\n'
+        f.write('digraph {\n%s}\n' % put_sample_in_node(dat['tree'], per_sample, dat['sample_names'], sample_colors,
+                                                         cluster_colors, height=150, width=150))
+    letters = [chr(65 + k) for k in range(K)]
+    sizes = [sum(1 for y in dat['assign'] if y == k) for k in range(K)]
+    charts = [chart_plot(letters[k], cluster_colors[k], per_sample[:, k], dat['sample_names'], sample_colors, sizes[k])
+              for k in range(K)]
+    edges = ['Subclone%s -> Subclone%s\n' % (letters[int(dat['tree'][k])], letters[k]) for k in range(K)
+             if not k == dat['root']]
     with open(treeoutfile, 'w') as f:
-        f.write('digraph {\n' + body + '}\n')
+        f.write('digraph {\n%s\n%s}\n' % (''.join(charts), ''.join(edges)))
 
 
 # ------------------------------------------------------------------------------ text report
@@ -153,18 +152,21 @@ def get_ascii_tree(tree, labels):
 
 
 def write_text_output(data, destfile):
-    """text report of the ranked solutions (reference tree_io.py:126-140)."""
+    """text report of the ranked solutions (reference tree_io.py:126-140): parent vector, ASCII tree
+    annotated with the per-sample prevalences, total log score, ML fractions, memberships."""
+    rule = '-' * 64
     with open(destfile, 'w') as f:
-        for i, tree in enumerate(data):
-            f.write('Solution Number ' + str(i + 1) + '\n')
-            f.write('tree = ' + str(tree['tree']) + '\n')
-            depth = get_tree_depth(tree['tree'])
-            pad = max(depth) - np.array(depth) + 1
-            labels = [chr(x + 65) + ' ' * 4 * pad[x] + str(np.around(tree['vaf'][x, :], 2))
-                      for x in range(len(tree['tree']))]
-            f.write(get_ascii_tree(tree['tree'], labels) + '\n')
-            f.write('logscore = ' + str(tree['totalscore']) + '\n')
-            f.write('ML Subclone Fractions = \n' + str(tree['clone_proportions']) + '\n')
-            f.write('Mutations Subclone Membership = ' + str([chr(x + 65) for x in tree['assign']]) + '\n')
-            f.write('----------------------------------------------------------------')
+        for rank, sol in enumerate(data, start=1):
+            parents = sol['tree']
+            depth = np.array(get_tree_depth(parents))
+            indent = depth.max() - depth + 1
+            labels = ['%s%s%s' % (chr(65 + k), ' ' * (4 * int(indent[k])), np.around(sol['vaf'][k, :], 2))
+                      for k in range(len(parents))]
+            f.write('Solution Number %d\n' % rank)
+            f.write('tree = %s\n' % (parents,))
+            f.write('%s\n' % get_ascii_tree(parents, labels))
+            f.write('logscore = %s\n' % (sol['totalscore'],))
+            f.write('ML Subclone Fractions = \n%s\n' % (sol['clone_proportions'],))
+            f.write('Mutations Subclone Membership = %s\n' % ([chr(65 + int(x)) for x in sol['assign']],))
+            f.write(rule)
     return
