@@ -207,3 +207,24 @@ def test_algorithmic_op_count_uses_the_mean_leaf_count():
     n_c, xu, flops = bench.algorithmic_ops_per_eval(7, 10)
     assert n_c == pytest.approx(10 * (bench.mean_leaves(7) - 1) * 131328)
     assert xu > n_c and flops > 4 * n_c
+
+
+def test_committed_bench_lines_follow_the_contract():
+    """the bench lines kept under profiles/ carry every key of the bench.py contract."""
+    import glob
+    import json
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "configs", "bench_c*.json")) +
+                   glob.glob(os.path.join(ROOT, "profiles", "scale", "scale_c2_*.json")))
+    assert len(files) >= 6
+    for fn in files:
+        d = json.load(open(fn))
+        for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                  "vs_baseline", "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline"):
+            assert k in d, (fn, k)
+        assert d["unit"] == "evals/s" and d["higher_is_better"] is True and d["vs_baseline"] is None
+        assert "workload" in d["config"] and "model" not in d["config"]
+        assert set(("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step")) <= set(d["e2e"])
+        assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0
+        assert set(("bound", "achieved", "peak", "unit", "frac", "traffic")) <= set(d["roofline"])
+        assert d["gpu_launches"] > 0 and d["value"] > 0 and d["e2e"]["value"] > 0
+        assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
