@@ -13,6 +13,15 @@ for p in (ROOT, os.path.join(ROOT, "oracle")):
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run with -m gpu on the B200 box)")
+    # a fresh checkout has no libbamse_cuda.so yet (built artefacts are git-ignored): build it once
+    # (nvcc cross-compiles for sm_100a without a GPU) so that the ABI tests can load it
+    lib = os.path.join(ROOT, "bamse_b200", "libbamse_cuda.so")
+    if not os.path.isfile(lib):
+        import shutil
+        import subprocess
+        if shutil.which("nvcc") and shutil.which("make"):
+            subprocess.check_call(["make", "-C", os.path.join(ROOT, "bamse_b200", "csrc"), "-j4"],
+                                  stdout=subprocess.DEVNULL)
 
 
 def load_golden(name):
