@@ -200,7 +200,8 @@ def cpu_reference_rate(work, n_items, cores, seed=0):
     wall = time.perf_counter() - t0
     busy = max(r[1] for r in res)   # slowest worker, excludes process start-up
     n = sum(r[0] for r in res)
-    return dict(value=n / busy, unit=UNIT, cores=len(chunks), kind=kind, wall_s=wall,
+    per_core = statistics.mean(r[0] / r[1] for r in res)     # the reference is single-threaded: its rate on one core
+    return dict(value=n / busy, unit=UNIT, cores=len(chunks), kind=kind, wall_s=wall, per_core=per_core,
                 sample="%d seeded random (clustering, tree) items of %s, %d worker processes" % (n, work["name"], len(chunks)))
 
 
