@@ -300,3 +300,43 @@ def test_config2_full_size_fp32_equals_check_mode(ctx, shim):
         assert a["assign"].tolist() == b["assign"].tolist()
         assert a["totalscore"] == pytest.approx(b["totalscore"], rel=1e-10)
     assert t64[0]["totalscore"] > t64[-1]["totalscore"]
+
+
+def test_config4_shape_index_subranges(ctx, shim):
+    """BASELINE config 4 shape (K = 10: 10^9 labeled rooted trees per clustering, M = 5, 1000
+    mutations): 3 x 300 000-tree index sub-ranges.  Properties at that size: the exact early exit does
+    not change the top-k; splitting the ranges in two and merging gives the same records; and on a
+    20 000-tree sub-range the fp32 path returns what a complete fp64 check-mode pass returns."""
+    from bamse_b200 import multigpu, workloads
+    from bamse_b200.clustering import _pack_problem
+    w = workloads.build("c4", ctx=ctx)
+    clusts = w["clusts"]
+    assert all(c.As.shape == (10, 5) for c in clusts)
+    Ks, var, ref, Kmax = _pack_problem(clusts)
+    ctx.upload_problem([0.001], Ks, var, ref)
+    C = len(clusts)
+    const = np.array([[c.cluster_prior + c.maxlikelihood for c in clusts]])
+    begin = np.array([123456789 + 1000 * c for c in range(C)], dtype=np.uint64)
+    n = 300000
+    end = begin + np.uint64(n)
+    plain, _, cnt = ctx.score_topk(const, None, begin, end, topk=8, precision=shim.FP32)
+    assert cnt[0] == 8 and ctx.last_eval_count == C * n
+    ctx.set_early_exit(True)
+    ctx.samples_evaluated(reset=True)
+    early, _, _ = ctx.score_topk(const, None, begin, end, topk=8, precision=shim.FP32)
+    done = ctx.samples_evaluated(reset=True)
+    ctx.set_early_exit(False)
+    assert early["tree"].tolist() == plain["tree"].tolist() and early["clust"].tolist() == plain["clust"].tolist()
+    np.testing.assert_array_equal(early["total"], plain["total"])
+    assert done <= C * n * 5
+    halves = []
+    for lo, hi in ((begin, begin + np.uint64(n // 2)), (begin + np.uint64(n // 2), end)):
+        halves.append(ctx.score_topk(const, None, lo, hi, topk=8, precision=shim.FP32)[0])
+    merged = multigpu.merge_records(np.stack(halves), 8)
+    assert merged["tree"].tolist() == plain["tree"].tolist()
+    np.testing.assert_allclose(merged["total"], plain["total"], rtol=1e-12)
+    small_end = begin + np.uint64(20000)
+    f32, _, _ = ctx.score_topk(const, None, begin, small_end, topk=5, precision=shim.FP32)
+    f64, _, _ = ctx.score_topk(const, None, begin, small_end, topk=5, precision=shim.FP64)
+    assert f32["tree"].tolist() == f64["tree"].tolist() and f32["clust"].tolist() == f64["clust"].tolist()
+    np.testing.assert_allclose(f32["total"], f64["total"], rtol=1e-10)
