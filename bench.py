@@ -261,6 +261,9 @@ def main():
     ap.add_argument("--ref-items", type=int, default=16, help="work items per step of the reference arm")
     ap.add_argument("--cpu-items", type=int, default=16, help="sample size of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--search-only", action="store_true",
+                    help="not a bench line: run ONE pass of the early-exit search (for configurations whose full\n"
+                         "scoring pass is too long, e.g. c4 = 3e9 trees) and print its own JSON")
     ap.add_argument("--emulate-shard-of", type=int, default=0,
                     help="debug: one GPU scores only shard 0 of W (what each rank of a W-GPU run does)")
     args = ap.parse_args()
@@ -368,6 +371,35 @@ def main():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    if args.search_only:
+        ctx.set_early_exit(True)
+        ctx.samples_evaluated(reset=True)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        step_resident()
+        e1.record()
+        barrier()
+        ts = torch.tensor([e0.elapsed_time(e1), float(ctx.samples_evaluated(reset=True))], dtype=torch.float64, device=dev)
+        if world > 1:
+            tm = ts.clone()
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+            dist.all_reduce(ts, op=dist.ReduceOp.SUM)
+            ts[0] = tm[0]
+        final = d_final.cpu().numpy().view(cuda_shim.RECORD_DTYPE).reshape(P, topk)
+        if rank == 0:
+            print(json.dumps({"not_a_bench_line": "early-exit search, one pass", "config": config_dict(args, work, world),
+                              "n_gpus": world, "seconds": float(ts[0]) / 1e3,
+                              "trees_resolved_per_s": total_evals / (float(ts[0]) / 1e3),
+                              "tree_samples_evaluated_frac": float(ts[1]) / (total_evals * work["M"]),
+                              "top": [{"total": float(final["total"][0, j]), "clust": int(final["clust"][0, j]),
+                                       "tree": int(final["tree"][0, j])} for j in range(topk)]}), flush=True)
+        ctx.close()
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
 
     sampler = ClockSampler(local_rank)
     if rank == 0:
