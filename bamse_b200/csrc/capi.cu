@@ -48,6 +48,12 @@ struct bamse_ctx {
     std::vector<int32_t> K_of_c;
     DBuf d_K, d_p0, d_var, d_ref, d_logc, d_logcf, d_log1mcf, d_D64, d_D32, d_D2, d_EL2, d_SEL2, d_SD2, d_HS2, d_PSE2, d_PEE2;
     bool root_tables = false, pair_tables = false;
+    // program tables (fp32 enumeration): one per K <= PROGTAB_KMAX present in the problem, kept across
+    // uploads while the key (tables present, Kmax of the pair index) is unchanged
+    struct ProgTab { DBuf buf; int root = -1, pair_kmax = -1; };
+    ProgTab progtab[KMAX + 1];
+    DBuf d_progtabs;         // [KMAX + 1] device pointers, NULL = decode in the kernel
+    bool have_progtabs = false;
 
     // work buffers
     DBuf d_segs, d_scalars /* total_chunks, total_trees, next_chunk */, d_cand, d_items, d_scores;
@@ -85,6 +91,8 @@ struct bamse_ctx {
         return v;
     }
 };
+
+constexpr int PROGTAB_KMAX = 8;
 
 static inline bool valid_precision(int p) { return p == BAMSE_FP32 || p == BAMSE_FP64 || p == BAMSE_FP32_LOGDOMAIN; }
 
@@ -150,6 +158,8 @@ void bamse_destroy(bamse_ctx* ctx) {
                     &ctx->d_scores, &ctx->d_const, &ctx->d_thr, &ctx->d_begin, &ctx->d_end, &ctx->d_records,
                     &ctx->d_dense0, &ctx->d_dense1, &ctx->d_pb, &ctx->d_pe, &ctx->d_split};
     for (DBuf* b : bufs) b->release();
+    for (auto& t : ctx->progtab) t.buf.release();
+    ctx->d_progtabs.release();
     for (auto* v : {&ctx->ev_used, &ctx->ev_free})
         for (auto& ev : *v) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -319,6 +329,30 @@ int bamse_upload_problem(bamse_ctx* ctx, int P, const double* err, int C, int M,
     if (ctx->pair_tables) {
         launch_tables_pairs(ctx->view(), ctx->fast(), ctx->d_PSE2.as<float>(), ctx->d_PEE2.as<float>(), s);
         ctx->launches++;
+    }
+    {   // program tables for the small K of this problem (K^(K-1) rows of 64 bytes; K = 8: 134 MB)
+        const char* off = getenv("BAMSE_PROGTAB");          // BAMSE_PROGTAB=0: always decode in the kernel
+        const bool enable = !(off && atoi(off) == 0);
+        const int pair_kmax = ctx->pair_tables ? Kmax : 0;
+        const TreeProgram* ptrs[KMAX + 1];
+        for (int k = 0; k <= KMAX; ++k) ptrs[k] = nullptr;
+        ctx->have_progtabs = false;
+        for (int c = 0; c < C && enable; ++c) {
+            const int K = K_of_c[c];
+            if (K > PROGTAB_KMAX || ptrs[K]) continue;
+            bamse_ctx::ProgTab& t = ctx->progtab[K];
+            const uint64_t n = ipow_u64(K, K - 1);
+            if (!t.buf.p || t.root != (int)ctx->root_tables || t.pair_kmax != pair_kmax) {
+                BAMSE_CUDA_TRY(ctx, t.buf.ensure(sizeof(TreeProgram) * n));
+                launch_build_prog_table(K, n, ctx->root_tables, pair_kmax, t.buf.as<TreeProgram>(), s);
+                ctx->launches++;
+                t.root = (int)ctx->root_tables; t.pair_kmax = pair_kmax;
+            }
+            ptrs[K] = t.buf.as<TreeProgram>();
+            ctx->have_progtabs = true;
+        }
+        BAMSE_CUDA_TRY(ctx, ctx->d_progtabs.ensure(sizeof ptrs));
+        BAMSE_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_progtabs.p, ptrs, sizeof ptrs, cudaMemcpyHostToDevice, s));
     }
     BAMSE_CUDA_TRY(ctx, cudaGetLastError());
     BAMSE_CUDA_TRY(ctx, cudaStreamSynchronize(s));   // host staging vectors die at return
@@ -528,6 +562,7 @@ static int enumerate_dev(bamse_ctx* ctx, const double* d_const, const double* d_
     w.stats = reinterpret_cast<unsigned long long*>(scal + 4);
     w.samples_done = reinterpret_cast<unsigned long long*>(scal + 8);
     // early exit only where pruned trees cannot matter: top-k enumerations (not dense ranges, not probes)
+    w.prog_tabs = (precision == BAMSE_FP32 && ctx->have_progtabs) ? ctx->d_progtabs.as<const TreeProgram*>() : nullptr;
     w.early_exit = (ctx->early_exit && !host_seg && !ctx->probing && topk > 0 && precision == BAMSE_FP32) ? 1 : 0;
     // tail splitting: when a worker gets fewer than ~48 single-tree chunks, issue the last `workers`
     // trees in 2 (or, below 16 chunks per worker, 4) parts over the samples

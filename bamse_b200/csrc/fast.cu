@@ -56,6 +56,24 @@ static __device__ __noinline__ void build_tree_program(int K, uint64_t tree, Tre
     build_program_fast(K, parent, nullptr, prog, root_tables, pair_kmax);
 }
 
+// Program tables.  The program of a tree depends on (K, tree index) and on which tables exist, not on
+// the data, so for small K all K^(K-1) programs are built once, one THREAD per tree, and the
+// enumeration warps fetch 64 bytes instead of running the (serial, one-lane) decoder per tree.
+static_assert(sizeof(TreeProgram) == 64, "program table rows are fetched as 16 words");
+__global__ void __launch_bounds__(128) k_build_prog_table(int K, uint64_t n_trees, bool root_tables, int pair_kmax,
+                                                          TreeProgram* __restrict__ out) {
+    const uint64_t tree = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tree >= n_trees) return;
+    TreeProgram prog;
+    memset(&prog, 0, sizeof prog);
+    build_tree_program(K, tree, &prog, root_tables, pair_kmax);
+    out[tree] = prog;
+}
+
+void launch_build_prog_table(int K, uint64_t n_trees, bool root_tables, int pair_kmax, TreeProgram* out, cudaStream_t s) {
+    k_build_prog_table<<<(unsigned)((n_trees + 127) / 128), 128, 0, s>>>(K, n_trees, root_tables, pair_kmax, out);
+}
+
 // ------------------------------------------------------------------ per-warp evaluation
 template <bool FRAMED, int SLOTS = FAST_SLOTS>
 struct alignas(16) WarpSmemT {
@@ -113,7 +131,7 @@ __device__ inline double warp_eval_tree(const ProblemView& pv, const FastTables&
                 ++sp;
             } else if (op == FOP_PUSH_PSE || op == FOP_PUSH_PEE) {
                 float* dst = ws->vec[sp] + GUARD;
-                const size_t row = (base / ((size_t)pv.Kmax * L)) * n_pairs(pv.Kmax) + (size_t)arg;
+                const size_t row = (((size_t)p * pv.C + c) * pv.M + m) * n_pairs(pv.Kmax) + (size_t)arg;
                 warp_load_vec(dst, (op == FOP_PUSH_PSE ? ft.PSE2 : ft.PEE2) + row * L, lane);
                 ++sp;
             } else if (op == FOP_SCAN) {
@@ -213,8 +231,11 @@ __device__ __forceinline__ bool rec_better_f(const bamse_record& a, const bamse_
 // cheap trees (few leaves) simply pulls more, and the tail of the launch is one tree long.
 // Each warp keeps a private top-k list in shared memory and appends it to a flat global bag
 // when its parameter set changes and at the end; k_merge_topk reduces the bag.
+#ifndef BAMSE_CTAS_2SLOT
+#define BAMSE_CTAS_2SLOT 9      // resident CTAs per SM of the 2-slot instantiation (56 registers, 36 warps)
+#endif
 template <bool FRAMED, int SLOTS>
-__global__ void __launch_bounds__(FAST_THREADS, FRAMED ? 6 : (SLOTS == 2 ? 8 : 7))
+__global__ void __launch_bounds__(FAST_THREADS, FRAMED ? 6 : (SLOTS == 2 ? BAMSE_CTAS_2SLOT : 7))
 k_enumerate_fast(ProblemView pv, FastTables ft, EnumWork w) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     using WS = WarpSmemT<FRAMED, SLOTS>;
@@ -273,9 +294,15 @@ k_enumerate_fast(ProblemView pv, FastTables ft, EnumWork w) {
         const uint64_t off = (chunk - seg.first_chunk) * (uint64_t)w.chunk;
         const uint64_t remain = seg.n_trees - off;
         const int n = remain < (uint64_t)w.chunk ? (int)remain : w.chunk;
+        const TreeProgram* tab = w.prog_tabs ? w.prog_tabs[seg.K] : nullptr;
         for (int i = 0; i < n; ++i) {
             const uint64_t tree = seg.tree_begin + (off + i) * (uint64_t)seg.stride;
-            if (lane == 0) build_tree_program(seg.K, tree, &ws->prog, ft.HS2 != nullptr, ft.PSE2 ? pv.Kmax : 0);
+            if (tab) {
+                if (lane < 16)
+                    reinterpret_cast<uint32_t*>(&ws->prog)[lane] = __ldg(reinterpret_cast<const uint32_t*>(tab + tree) + lane);
+            } else if (lane == 0) {
+                build_tree_program(seg.K, tree, &ws->prog, ft.HS2 != nullptr, ft.PSE2 ? pv.Kmax : 0);
+            }
             __syncwarp();
             double cut = -CUDART_INF;
             if (w.early_exit) {

@@ -49,6 +49,9 @@ struct EnumWork {
     unsigned long long n_split;  // upper bound on the trees issued split (size of the two buffers)
     double* split_acc;           // [n_split] partial sums (zeroed before launch)
     int* split_cnt;              // [n_split] finished parts (zeroed before launch)
+    // fp32 kernel: per-K tables of ready-made evaluation programs, indexed by tree index (device array of
+    // KMAX + 1 device pointers, entry NULL = decode in the kernel); NULL = no tables at all
+    const TreeProgram* const* prog_tabs;
 };
 
 void launch_tables(const ProblemView& pv, const double* d_var, const double* d_ref, const double* d_logc,
@@ -73,6 +76,8 @@ void launch_tables_fast(const ProblemView& pv, float* D2, float* EL2, float* SEL
 void launch_tables_hs(const ProblemView& pv, const FastTables& ft, float* HS2, cudaStream_t s);
 void launch_tables_pairs(const ProblemView& pv, const FastTables& ft, float* PSE2, float* PEE2, cudaStream_t s);
 int enumerate_fast_grid_size(int device, int topk, bool framed, int Kmax);
+// out[i] = evaluation program of tree index i of a K-node clustering, i < n_trees = K^(K-1)
+void launch_build_prog_table(int K, uint64_t n_trees, bool root_tables, int pair_kmax, TreeProgram* out, cudaStream_t s);
 void launch_enumerate_fast(const ProblemView& pv, const FastTables& ft, const EnumWork& w, int grid, bool framed,
                            cudaStream_t s);
 void launch_score_items_fast(const ProblemView& pv, const FastTables& ft, const ScoreItem* d_items, int64_t n,

@@ -306,9 +306,10 @@ __device__ inline void warp_merge_path(const float* __restrict__ a, const float*
         if (sa >= sb) lo = mid + 1; else hi = mid;
     }
     int i = lo, j = x0 - lo;
-    // current and next value on either side (-inf past the right edge: that side cannot advance)
-    float ai = a[i], an = (i < L - 1) ? a[i + 1] : -CUDART_INF_F;
-    float bj = b[j], bn = (j < L - 1) ? b[j + 1] : -CUDART_INF_F;
+    // current and next value on either side; past the right edge both vectors carry four -inf
+    // entries (warp_init_guards), so a side that has run out cannot advance and no index needs a check
+    float ai = a[i], an = a[i + 1];
+    float bj = b[j], bn = b[j + 1];
     uint32_t packed = 0;                                      // two 16-bit j* per word
 #pragma unroll 2
     for (int t = 0; t < 16; ++t) {
@@ -318,7 +319,7 @@ __device__ inline void warp_merge_path(const float* __restrict__ a, const float*
         const bool take_b = (bn - bj) > (an - ai);
         const float* src = take_b ? b : a;
         const int k = (take_b ? j : i) + 2;                   // index of the new "next" value
-        const float nv = (k < L) ? src[k] : -CUDART_INF_F;
+        const float nv = src[k];                              // k <= L + 1: inside the -inf pad
         if (take_b) { ++j; bj = bn; bn = nv; } else { ++i; ai = an; an = nv; }
     }
     __syncwarp();
@@ -345,8 +346,9 @@ static __device__ __noinline__ void warp_logconv_exact_pass(float* __restrict__ 
 __device__ __forceinline__ void conv_accumulate(const float* __restrict__ pa, const float4* __restrict__ pb, int n4,
                                                 const float2 nm2, float2& acc0, float2& acc1, float2& acc2,
                                                 float2& acc3) {
+    const float4* const pend = pb + (n4 & ~1);
 #pragma unroll 1
-    for (int c = n4 >> 1; c > 0; --c) {
+    while (pb != pend) {
         const float4 bv = pb[0], bw = pb[1];
         pb += 2;
         float2 t0 = make_float2(pa[0], pa[-1]), t1 = make_float2(pa[-2], pa[-3]);
@@ -379,9 +381,9 @@ __device__ __forceinline__ void conv_pass_mufu(float* __restrict__ a, const floa
     const int x = x0 + lane;
     const int xmax = x0 + 31;
     const int js = jstar[x];
-    // j* is non-decreasing inside each 16-output walk of the merge path
-    const int jmin = min((int)jstar[x0], (int)jstar[x0 + 16]);
-    const int jmax = max((int)jstar[x0 + 15], (int)jstar[xmax]);
+    // min / max of the lanes' j* in two warp reductions (CREDUX)
+    const int jmin = (int)__reduce_min_sync(0xffffffffu, (unsigned)js);
+    const int jmax = (int)__reduce_max_sync(0xffffffffu, (unsigned)js);
     const float mx = a[x - js] + b[js];
     const float2 nm2 = make_float2(-mx, -mx);
     float2 acc0 = make_float2(0.f, 0.f), acc1 = acc0, acc2 = acc0, acc3 = acc0;
@@ -394,25 +396,30 @@ __device__ __forceinline__ void conv_pass_mufu(float* __restrict__ a, const floa
     // as some lane's edge term is still above 2^-THETA of its maximum -- extensions to the left,
     // then to the right.  The terms of one output are concave in j, so sub-threshold edges bound
     // everything outside the range.
-    int seg_j0 = jl, seg_m4 = n4, phase = 0;
+    int seg_j0 = jl, seg_m4 = n4;
+    bool left_open = jl > 0;                                   // warp-uniform
 #pragma unroll 1
     for (;;) {
         chunks += seg_m4;
         conv_accumulate(a + (x - seg_j0), reinterpret_cast<const float4*>(b + seg_j0), seg_m4, nm2, acc0, acc1, acc2, acc3);
-        if (phase == 0) {
-            const bool need = (jl > 0) && (((a[x - jl] - mx) + b[jl]) >= -THETA);
-            if (__any_sync(0xffffffffu, need)) {
+        // both edge terms at once: most passes need no extension and leave after ONE vote.  Lanes with
+        // x <= je read the -inf guard on the right, so they never ask for more there.
+        const float er = (a[x - je] - mx) + b[je];
+        const float el = (a[x - jl] - mx) + b[jl];
+        const bool need_r = (je < xmax) && er >= -THETA;
+        const bool need_l = left_open && el >= -THETA;
+        if (!__any_sync(0xffffffffu, need_l || need_r)) break;
+        if (left_open) {
+            if (__any_sync(0xffffffffu, need_l)) {
                 const int j2 = max(jl - max(hl, 8), 0) & ~3;
                 seg_j0 = j2; seg_m4 = (jl - j2) >> 2;
                 hl += jl - j2;
                 jl = j2;
+                left_open = jl > 0;
                 continue;
             }
-            phase = 1;
+            left_open = false;                                 // the left edge is settled for good
         }
-        // lanes with x <= je read the -inf guard here, so they never ask for more
-        const bool need = ((a[x - je] - mx) + b[je]) >= -THETA;
-        if (!__any_sync(0xffffffffu, need) || je >= xmax) break;
         seg_m4 = min((max(hr, 8) + 3) >> 2, ((xmax | 3) - je) >> 2);
         seg_j0 = je + 1;
         hr += 4 * seg_m4;
@@ -568,11 +575,22 @@ __device__ inline int warp_logconv(float* __restrict__ a, const float* __restric
     warp_merge_path(a, b, jstar, lane);
     int chunks = 0;
     int hl = 8, hr = 8;                                       // window half-widths, adapted block to block
+    // keep the two vector bases in registers across the passes (ptxas otherwise rebuilds them from
+    // the warp base and the stack position several times per pass)
+    unsigned sa = (unsigned)__cvta_generic_to_shared(a), sb = (unsigned)__cvta_generic_to_shared(b);
+    asm volatile("" : "+r"(sa), "+r"(sb));
+    a = reinterpret_cast<float*>(__cvta_shared_to_generic(sa));
+    b = reinterpret_cast<const float*>(__cvta_shared_to_generic(sb));
+    if (FRAMED) {
 #pragma unroll 1
-    for (int q = L / FR_B - 1; q >= 0; --q) {
-        if (FRAMED && conv_block_framed(a, b, jstar, fa, fb, q, lane, hl, hr, chunks)) continue;
+        for (int q = L / FR_B - 1; q >= 0; --q) {
+            if (conv_block_framed(a, b, jstar, fa, fb, q, lane, hl, hr, chunks)) continue;
 #pragma unroll 1
-        for (int h = 1; h >= 0; --h) conv_pass_mufu(a, b, jstar, 2 * q + h, lane, hl, hr, chunks);
+            for (int h = 1; h >= 0; --h) conv_pass_mufu(a, b, jstar, 2 * q + h, lane, hl, hr, chunks);
+        }
+    } else {
+#pragma unroll 1
+        for (int pass = L / 32 - 1; pass >= 0; --pass) conv_pass_mufu(a, b, jstar, pass, lane, hl, hr, chunks);
     }
     __syncwarp();
     return chunks;

@@ -9,7 +9,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libbamse_cuda.so")
+# BAMSE_CUDA_LIB: load another build of the library (A/B measurements of kernel variants)
+LIB_PATH = os.environ.get("BAMSE_CUDA_LIB") or os.path.join(_HERE, "libbamse_cuda.so")
 
 FP32 = 0
 FP64 = 1

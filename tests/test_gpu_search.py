@@ -340,3 +340,40 @@ def test_config4_shape_index_subranges(ctx, shim):
     f64, _, _ = ctx.score_topk(const, None, begin, small_end, topk=5, precision=shim.FP64)
     assert f32["tree"].tolist() == f64["tree"].tolist() and f32["clust"].tolist() == f64["clust"].tolist()
     np.testing.assert_allclose(f32["total"], f64["total"], rtol=1e-10)
+
+
+def test_program_tables_equal_in_kernel_decoding(ctx, shim, monkeypatch):
+    """The fp32 enumeration fetches ready-made evaluation programs for K <= 8 instead of decoding the
+    tree index in the kernel: both routes must give bit-identical scores, log scre and top-k, for whole
+    small search spaces, a mixed-K problem and a K = 8 sub-range (K = 9 always decodes in the kernel)."""
+    rng = np.random.default_rng(2024)
+
+    def problem(Ks, M, cov):
+        Kmax = max(Ks)
+        As = np.zeros((len(Ks), Kmax, M), np.int64)
+        Bs = np.zeros_like(As)
+        for ci, K in enumerate(Ks):
+            frac = np.sort(rng.dirichlet(np.ones(K + 1))[:K])[::-1]
+            cm = np.clip(np.cumsum(frac[::-1])[::-1][:, None] * rng.uniform(0.6, 1.0, size=(K, M)), 0, 1)
+            As[ci, :K] = rng.binomial(cov, cm * 0.497 + 0.003)
+            Bs[ci, :K] = cov - As[ci, :K]
+        return As, Bs
+
+    for Ks, M, cov, ranges in [([3, 4, 5, 6, 2, 1], 3, 900, None), ([7], 2, 400, [(0, 0, 30000), (0, 7 ** 6 - 5000, 5000)]),
+                               ([8, 5], 2, 2500, [(0, 8 ** 7 - 3000, 3000), (0, 12345, 2000), (1, 0, 625)])]:
+        As, Bs = problem(Ks, M, cov)
+        got = {}
+        monkeypatch.setenv("BAMSE_FRAMED", "1" if Ks == [7] else "0")     # both kernel instantiations
+        for mode in ("0", "1"):
+            monkeypatch.setenv("BAMSE_PROGTAB", mode)
+            ctx.upload_problem([0.003], Ks, As, Bs)
+            rs = ranges or [(c, 0, K ** max(K - 1, 0)) for c, K in enumerate(Ks)]
+            dense = [ctx.score_range(0, c, b, n, shim.FP32) for c, b, n in rs]
+            top = ctx.score_topk(np.zeros((1, len(Ks))), topk=6, precision=shim.FP32)
+            got[mode] = (dense, top)
+        monkeypatch.delenv("BAMSE_PROGTAB")
+        monkeypatch.delenv("BAMSE_FRAMED")
+        for (s0, l0), (s1, l1) in zip(got["0"][0], got["1"][0]):
+            assert np.array_equal(s0, s1) and np.array_equal(l0, l1)
+        assert got["0"][1][0].tobytes() == got["1"][1][0].tobytes()
+        assert np.array_equal(got["0"][1][1], got["1"][1][1])
