@@ -305,22 +305,24 @@ __device__ inline void warp_merge_path(const float* __restrict__ a, const float*
         const float sb = b[x0 - mid] - b[x0 - mid - 1];       // gain of b's last taken step
         if (sa >= sb) lo = mid + 1; else hi = mid;
     }
-    int i = lo, j = x0 - lo;
-    // current and next value on either side; past the right edge both vectors carry four -inf
-    // entries (warp_init_guards), so a side that has run out cannot advance and no index needs a check
-    float ai = a[i], an = a[i + 1];
-    float bj = b[j], bn = b[j + 1];
+    // state per side: the next value and the slope towards it; one load, one subtraction and a
+    // handful of predicated moves per step
+    int j = x0 - lo;
+    const float* pa2 = a + lo + 2;
+    const float* pb2 = b + j + 2;
+    float an = a[lo + 1], bn = b[j + 1];
+    float da = an - a[lo], db = bn - b[j];
     uint32_t packed = 0;                                      // two 16-bit j* per word
 #pragma unroll 2
     for (int t = 0; t < 16; ++t) {
         if (t & 1) reinterpret_cast<uint32_t*>(jstar)[(x0 + t) >> 1] = packed | ((uint32_t)j << 16);
         else packed = (uint32_t)j;
-        // advance along the larger slope (ties and NaNs go to a); one load per step
-        const bool take_b = (bn - bj) > (an - ai);
-        const float* src = take_b ? b : a;
-        const int k = (take_b ? j : i) + 2;                   // index of the new "next" value
-        const float nv = src[k];                              // k <= L + 1: inside the -inf pad
-        if (take_b) { ++j; bj = bn; bn = nv; } else { ++i; ai = an; an = nv; }
+        // advance along the larger slope (ties and NaNs go to a); past the right edge both vectors
+        // carry four -inf entries (warp_init_guards), so a side that has run out cannot advance
+        const bool take_b = db > da;
+        const float nv = *(take_b ? pb2 : pa2);
+        const float d = nv - (take_b ? bn : an);
+        if (take_b) { ++j; db = d; bn = nv; ++pb2; } else { da = d; an = nv; ++pa2; }
     }
     __syncwarp();
 }
