@@ -57,7 +57,7 @@ struct bamse_ctx {
 
     // work buffers
     DBuf d_segs, d_scalars /* total_chunks, total_trees, next_chunk */, d_cand, d_items, d_scores;
-    DBuf d_const, d_thr, d_begin, d_end, d_records, d_dense0, d_dense1, d_pb, d_pe, d_split;
+    DBuf d_const, d_thr, d_begin, d_end, d_records, d_dense0, d_dense1, d_split, d_lists;
     int grid[3] = {0, 0, 0};
     int shard_rank = 0, shard_world = 1;
     int early_exit = 0;      // BAMSE_OPT_EARLY_EXIT
@@ -156,7 +156,7 @@ void bamse_destroy(bamse_ctx* ctx) {
     DBuf* bufs[] = {&ctx->d_K, &ctx->d_p0, &ctx->d_var, &ctx->d_ref, &ctx->d_logc, &ctx->d_logcf, &ctx->d_log1mcf,
                     &ctx->d_D64, &ctx->d_D32, &ctx->d_D2, &ctx->d_EL2, &ctx->d_SEL2, &ctx->d_SD2, &ctx->d_HS2, &ctx->d_PSE2, &ctx->d_PEE2, &ctx->d_segs, &ctx->d_scalars, &ctx->d_cand, &ctx->d_items,
                     &ctx->d_scores, &ctx->d_const, &ctx->d_thr, &ctx->d_begin, &ctx->d_end, &ctx->d_records,
-                    &ctx->d_dense0, &ctx->d_dense1, &ctx->d_pb, &ctx->d_pe, &ctx->d_split};
+                    &ctx->d_dense0, &ctx->d_dense1, &ctx->d_split, &ctx->d_lists};
     for (DBuf* b : bufs) b->release();
     for (auto& t : ctx->progtab) t.buf.release();
     ctx->d_progtabs.release();
@@ -447,8 +447,9 @@ static int enumerate_dev(bamse_ctx* ctx, const double* d_const, const double* d_
 // The fp32 kernel has two instantiations: the exponential path only (lean: 7 CTAs/SM), and one that
 // also carries the linear-domain "framed" path (6 CTAs/SM), which wins when the tables are flat
 // (low coverage: most terms of a convolution matter) and loses on sharply peaked tables.  Which one
-// is faster is a property of the data, so it is measured once per problem on <= 8192 trees of the
-// sample of 8 192 - 40 000 trees (a few ms; only for problems of >= 50 000 trees) and remembered.  BAMSE_FRAMED=0/1 in the environment overrides.
+// is faster is a property of the data, so it is measured once per problem on an interleaved sample of
+// 8 192 - 40 000 trees (a few ms; only for problems of >= 50 000 trees) and remembered.
+// BAMSE_FRAMED=0/1 in the environment overrides.
 static int probe_fast_variant(bamse_ctx* ctx) {
     if (const char* f = getenv("BAMSE_FRAMED")) { ctx->use_framed = atoi(f) ? 1 : 0; return BAMSE_OK; }
     const int P = ctx->P, C = ctx->C;
@@ -457,27 +458,25 @@ static int probe_fast_variant(bamse_ctx* ctx) {
     total *= (uint64_t)P;
     // small problems: a probe would cost more than it can save -- exponential instantiation
     if (total < 50000) { ctx->use_framed = 0; return BAMSE_OK; }
-    // sample: the first `quota` trees of every clustering, total/8 but 8 192 .. 40 000 trees in all --
-    // enough to fill every warp slot of the GPU several times (a shorter run measures latency, not
-    // throughput) while both timed runs together cost at most a quarter of one full enumeration
+    // sample: every W-th tree index of every clustering (interleaved like a shard, so every tree shape and
+    // every root takes part: the low indices alone are the star-like trees around node 0), total/8 but
+    // 8 192 .. 40 000 trees in all -- enough to fill every warp slot of the GPU several times (a shorter run
+    // measures latency, not throughput) while both timed runs together cost at most a quarter of one full
+    // enumeration.  W is kept coprime to every K <= 12: index = root + K * code, so a stride that shares a
+    // factor with K would visit only some of the roots.
     const uint64_t sample = std::min<uint64_t>(40000, std::max<uint64_t>(8192, total / 8));
-    const uint64_t quota = std::max<uint64_t>(16, sample / ((uint64_t)P * C) + 1);
-    std::vector<uint64_t> b(C, 0), e(C);
-    for (int c = 0; c < C; ++c) e[c] = std::min<uint64_t>(ipow_u64(ctx->K_of_c[c], ctx->K_of_c[c] - 1), quota);
-    BAMSE_CUDA_TRY(ctx, ctx->d_pb.ensure(sizeof(uint64_t) * C));
-    BAMSE_CUDA_TRY(ctx, ctx->d_pe.ensure(sizeof(uint64_t) * C));
-    BAMSE_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_pb.p, b.data(), sizeof(uint64_t) * C, cudaMemcpyHostToDevice, ctx->stream));
-    BAMSE_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_pe.p, e.data(), sizeof(uint64_t) * C, cudaMemcpyHostToDevice, ctx->stream));
-    BAMSE_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    uint64_t W = std::max<uint64_t>(1, total / sample);
+    while (W > 1 && (W % 2 == 0 || W % 3 == 0 || W % 5 == 0 || W % 7 == 0 || W % 11 == 0)) --W;
+    if (W > 0x7fffffffull) W = 0x7fffffffull;        // Segment::stride is 32-bit (2^31 - 1 is prime)
     const int save_rank = ctx->shard_rank, save_world = ctx->shard_world;
-    ctx->shard_rank = 0; ctx->shard_world = 1;
+    ctx->shard_rank = 0; ctx->shard_world = (int)W;
     ctx->probing = true;
     float best_ms = 0.f;
     int best = 0, rc = BAMSE_OK;
     for (int v = 0; v < 2 && rc == BAMSE_OK; ++v) {
         ctx->use_framed = v;
-        rc = enumerate_dev(ctx, nullptr, nullptr, ctx->d_pb.as<uint64_t>(), ctx->d_pe.as<uint64_t>(), 0, BAMSE_FP32, 0.0,
-                           0.0, nullptr, nullptr, nullptr, nullptr);
+        rc = enumerate_dev(ctx, nullptr, nullptr, nullptr, nullptr, 0, BAMSE_FP32, 0.0, 0.0, nullptr, nullptr, nullptr,
+                           nullptr);
         if (rc) break;
         if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) { rc = ctx->fail(BAMSE_ECUDA, "probe: stream sync failed"); break; }
         auto ev = ctx->ev_used.back();
@@ -562,6 +561,11 @@ static int enumerate_dev(bamse_ctx* ctx, const double* d_const, const double* d_
     w.stats = reinterpret_cast<unsigned long long*>(scal + 4);
     w.samples_done = reinterpret_cast<unsigned long long*>(scal + 8);
     // early exit only where pruned trees cannot matter: top-k enumerations (not dense ranges, not probes)
+    w.lists = nullptr;
+    if (precision == BAMSE_FP32) {
+        BAMSE_CUDA_TRY(ctx, ctx->d_lists.ensure(sizeof(bamse_record) * (size_t)workers * (size_t)(topk > 0 ? topk : 1)));
+        w.lists = ctx->d_lists.as<bamse_record>();
+    }
     w.prog_tabs = (precision == BAMSE_FP32 && ctx->have_progtabs) ? ctx->d_progtabs.as<const TreeProgram*>() : nullptr;
     w.early_exit = (ctx->early_exit && !host_seg && !ctx->probing && topk > 0 && precision == BAMSE_FP32) ? 1 : 0;
     // tail splitting: when a worker gets fewer than ~48 single-tree chunks, issue the last `workers`

@@ -84,7 +84,7 @@ struct alignas(16) WarpSmemT {
     TreeProgram prog;
 };
 using WarpSmem = WarpSmemT<false>;
-// dynamic shared memory: FAST_WARPS x WarpSmem, then FAST_WARPS x topk bamse_records
+// dynamic shared memory: FAST_WARPS x WarpSmem
 
 // Keeps the warp's shared-memory base in a register: without the opaque move ptxas
 // rematerialises it from S2R tid / cta-id several times per convolution pass.
@@ -219,6 +219,15 @@ __global__ void __launch_bounds__(FAST_THREADS) k_tables_pairs(ProblemView pv, F
     for (int t = 0; t < 16; ++t) out[lane + 32 * t] = a[lane + 32 * t];
 }
 
+// a record written by another warp of the CTA (global memory, read after the barrier): bypass L1
+__device__ __forceinline__ bamse_record load_record_cg(const bamse_record* p) {
+    static_assert(sizeof(bamse_record) == 32, "two 16-byte loads");
+    union { int4 q[2]; bamse_record r; } u;
+    u.q[0] = __ldcg(reinterpret_cast<const int4*>(p));
+    u.q[1] = __ldcg(reinterpret_cast<const int4*>(p) + 1);
+    return u.r;
+}
+
 __device__ __forceinline__ bool rec_better_f(const bamse_record& a, const bamse_record& b) {
     if (a.total != b.total) return a.total > b.total;
     if (a.clust != b.clust) return a.clust < b.clust;
@@ -229,10 +238,10 @@ __device__ __forceinline__ bool rec_better_f(const bamse_record& a, const bamse_
 // Persistent warps: every warp pulls small chunks of consecutive tree indices from one global
 // counter and scores them on its own -- no block-level barrier anywhere, so a warp that drew
 // cheap trees (few leaves) simply pulls more, and the tail of the launch is one tree long.
-// Each warp keeps a private top-k list in shared memory and appends it to a flat global bag
+// Each warp keeps a private top-k list (global memory, EnumWork::lists) and appends it to a flat global bag
 // when its parameter set changes and at the end; k_merge_topk reduces the bag.
 #ifndef BAMSE_CTAS_2SLOT
-#define BAMSE_CTAS_2SLOT 9      // resident CTAs per SM of the 2-slot instantiation (56 registers, 36 warps)
+#define BAMSE_CTAS_2SLOT 10     // resident CTAs per SM of the 2-slot instantiation (48 registers, 40 warps, 22.7 KB each)
 #endif
 template <bool FRAMED, int SLOTS>
 __global__ void __launch_bounds__(FAST_THREADS, FRAMED ? 6 : (SLOTS == 2 ? BAMSE_CTAS_2SLOT : 7))
@@ -240,13 +249,13 @@ k_enumerate_fast(ProblemView pv, FastTables ft, EnumWork w) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     using WS = WarpSmemT<FRAMED, SLOTS>;
     WS* wsm = reinterpret_cast<WS*>(smem_raw);
-    bamse_record* s_top_all = reinterpret_cast<bamse_record*>(smem_raw + sizeof(WS) * FAST_WARPS);
     const int t = threadIdx.x, wid = t >> 5;
     int lane = t & 31;
     asm volatile("" : "+r"(lane));
     WS* ws = pin_shared(wsm + wid);
     const int kcap = w.topk > 0 ? w.topk : 1;
-    bamse_record* list = s_top_all + wid * kcap;
+    bamse_record* const cta_lists = w.lists + (size_t)blockIdx.x * FAST_WARPS * kcap;
+    bamse_record* list = cta_lists + wid * kcap;
     warp_init_guards(ws, lane);
     int ntop = 0;                                    // meaningful in lane 0
     int cur_p = -1;
@@ -370,9 +379,10 @@ k_enumerate_fast(ProblemView pv, FastTables ft, EnumWork w) {
                 int best = -1;
                 for (int i = 0; i < FAST_WARPS; ++i)
                     if (pos[i] < s_ntop[i] &&
-                        (best < 0 || rec_better_f(s_top_all[i * kcap + pos[i]], s_top_all[best * kcap + pos[best]])))
+                        (best < 0 || rec_better_f(load_record_cg(cta_lists + i * kcap + pos[i]),
+                                                  load_record_cg(cta_lists + best * kcap + pos[best]))))
                         best = i;
-                if (base + r < w.cand_cap) w.cand[base + r] = s_top_all[best * kcap + pos[best]];
+                if (base + r < w.cand_cap) w.cand[base + r] = load_record_cg(cta_lists + best * kcap + pos[best]);
                 ++pos[best];
             }
         }
@@ -391,7 +401,8 @@ k_enumerate_fast(ProblemView pv, FastTables ft, EnumWork w) {
 
 static size_t fast_smem_bytes(int topk, bool framed = false, int slots = FAST_SLOTS) {
     const size_t per_warp = framed ? sizeof(WarpSmemT<true, 3>) : (slots == 2 ? sizeof(WarpSmemT<false, 2>) : sizeof(WarpSmemT<false, 3>));
-    return per_warp * FAST_WARPS + sizeof(bamse_record) * FAST_WARPS * (size_t)(topk > 0 ? topk : 1);
+    (void)topk;                                      // the top-k lists live in global memory (EnumWork::lists)
+    return per_warp * FAST_WARPS;
 }
 
 void launch_tables_hs(const ProblemView& pv, const FastTables& ft, float* HS2, cudaStream_t s) {
@@ -411,7 +422,7 @@ void launch_tables_pairs(const ProblemView& pv, const FastTables& ft, float* PSE
 
 int enumerate_workers(int precision, int grid) { return precision == BAMSE_FP32 ? grid * FAST_WARPS : grid; }
 
-// Kmax <= 6 needs two vector slots only -> 8 CTAs (32 warps) per SM instead of 7
+// Kmax <= 6 needs two vector slots only -> 10 CTAs (40 warps) per SM instead of 7
 static int fast_slots(int Kmax, bool framed) { return (!framed && Kmax <= 6) ? 2 : 3; }
 
 int enumerate_fast_grid_size(int device, int topk, bool framed, int Kmax) {

@@ -52,6 +52,9 @@ struct EnumWork {
     // fp32 kernel: per-K tables of ready-made evaluation programs, indexed by tree index (device array of
     // KMAX + 1 device pointers, entry NULL = decode in the kernel); NULL = no tables at all
     const TreeProgram* const* prog_tabs;
+    // fp32 kernel: the workers' private top-k lists, [workers][max(topk, 1)] records in global memory
+    // (touched once per tree by one lane; keeping them out of shared memory buys a resident CTA per SM)
+    bamse_record* lists;
 };
 
 void launch_tables(const ProblemView& pv, const double* d_var, const double* d_ref, const double* d_logc,
