@@ -23,7 +23,10 @@ constexpr int FAST_THREADS = FAST_WARPS * 32;
 constexpr int GUARD = 36;                           // -inf floats in front of every vector (a[x-j], j <= xmax+3)
 constexpr int VSTRIDE = GUARD + L + 4;              // floats per vector slot (4 trailing -inf: b[j], j <= 514)
 constexpr int FAST_SLOTS = 3;                       // max live vectors with the in-place convolution (brute-forced, K <= 12)
-constexpr float THETA = 30.0f;                      // window threshold in bits: terms below 2^-30 of an output's
+#ifndef BAMSE_THETA
+#define BAMSE_THETA 30.0f
+#endif
+constexpr float THETA = BAMSE_THETA;                      // window threshold in bits: terms below 2^-30 of an output's
                                                     // maximum are dropped (<= 512 of them, decaying: < 2^-22 relative)
 constexpr float LOG2_L = 9.0f;                      // log2(512)
 // framed (linear-domain) path of the convolution
@@ -444,6 +447,134 @@ __device__ __forceinline__ void conv_pass_mufu(float* __restrict__ a, const floa
     hr = max(4, hr - (hr >> 2));
 }
 
+// ---- two passes at once: each half-warp takes one 32-output pass, every lane two adjacent outputs ----
+// acc += sum over n4 chunks of 4 consecutive j (from the 4-aligned j0) of 2^((a[x-j] - mx0) + b[j]) in .x
+// and 2^((a[x+1-j] - mx1) + b[j]) in .y; x even, pa = &a[x - j0] (8-byte aligned), pb = &b[j0].  The two
+// outputs of a lane share every loaded element: 2 LDS.64 + 1 LDS.128 per 8 terms instead of 8 LDS.32 +
+// 2 LDS.128.  n4 may differ between the half-warps (each runs its own window).
+__device__ __forceinline__ void conv_accumulate_pair(const float* __restrict__ pa, const float4* __restrict__ pb,
+                                                     int n4, const float2 nm, float2& acc0, float2& acc1,
+                                                     float2& acc2, float2& acc3) {
+    if (n4 <= 0) return;
+    float2 q0 = *reinterpret_cast<const float2*>(pa);         // (a[p], a[p+1]), p = x - j0
+    const float4* const pend = pb + (n4 & ~1);
+#pragma unroll 1
+    while (pb != pend) {
+        const float4 bv = pb[0], bw = pb[1];
+        pb += 2;
+        const float2 q1 = *reinterpret_cast<const float2*>(pa - 2), q2 = *reinterpret_cast<const float2*>(pa - 4);
+        const float2 q3 = *reinterpret_cast<const float2*>(pa - 6), q4 = *reinterpret_cast<const float2*>(pa - 8);
+        pa -= 8;
+        // j0 + k, k = 0..7: the pair (a[p-k], a[p-k+1]) is q_{k/2} for even k, (q_{(k+1)/2}.y, q_{(k-1)/2}.x) for odd k
+        float2 t0 = __fadd2_rn(__fadd2_rn(q0, nm), make_float2(bv.x, bv.x));
+        float2 t1 = __fadd2_rn(__fadd2_rn(make_float2(q1.y, q0.x), nm), make_float2(bv.y, bv.y));
+        float2 t2 = __fadd2_rn(__fadd2_rn(q1, nm), make_float2(bv.z, bv.z));
+        float2 t3 = __fadd2_rn(__fadd2_rn(make_float2(q2.y, q1.x), nm), make_float2(bv.w, bv.w));
+        acc0 = __fadd2_rn(acc0, make_float2(ex2f(t0.x), ex2f(t0.y)));
+        acc1 = __fadd2_rn(acc1, make_float2(ex2f(t1.x), ex2f(t1.y)));
+        acc2 = __fadd2_rn(acc2, make_float2(ex2f(t2.x), ex2f(t2.y)));
+        acc3 = __fadd2_rn(acc3, make_float2(ex2f(t3.x), ex2f(t3.y)));
+        t0 = __fadd2_rn(__fadd2_rn(q2, nm), make_float2(bw.x, bw.x));
+        t1 = __fadd2_rn(__fadd2_rn(make_float2(q3.y, q2.x), nm), make_float2(bw.y, bw.y));
+        t2 = __fadd2_rn(__fadd2_rn(q3, nm), make_float2(bw.z, bw.z));
+        t3 = __fadd2_rn(__fadd2_rn(make_float2(q4.y, q3.x), nm), make_float2(bw.w, bw.w));
+        acc0 = __fadd2_rn(acc0, make_float2(ex2f(t0.x), ex2f(t0.y)));
+        acc1 = __fadd2_rn(acc1, make_float2(ex2f(t1.x), ex2f(t1.y)));
+        acc2 = __fadd2_rn(acc2, make_float2(ex2f(t2.x), ex2f(t2.y)));
+        acc3 = __fadd2_rn(acc3, make_float2(ex2f(t3.x), ex2f(t3.y)));
+        q0 = q4;
+    }
+    if (n4 & 1) {
+        const float4 bv = pb[0];
+        const float2 q1 = *reinterpret_cast<const float2*>(pa - 2), q2 = *reinterpret_cast<const float2*>(pa - 4);
+        const float2 t0 = __fadd2_rn(__fadd2_rn(q0, nm), make_float2(bv.x, bv.x));
+        const float2 t1 = __fadd2_rn(__fadd2_rn(make_float2(q1.y, q0.x), nm), make_float2(bv.y, bv.y));
+        const float2 t2 = __fadd2_rn(__fadd2_rn(q1, nm), make_float2(bv.z, bv.z));
+        const float2 t3 = __fadd2_rn(__fadd2_rn(make_float2(q2.y, q1.x), nm), make_float2(bv.w, bv.w));
+        acc0 = __fadd2_rn(acc0, make_float2(ex2f(t0.x), ex2f(t0.y)));
+        acc1 = __fadd2_rn(acc1, make_float2(ex2f(t1.x), ex2f(t1.y)));
+        acc2 = __fadd2_rn(acc2, make_float2(ex2f(t2.x), ex2f(t2.y)));
+        acc3 = __fadd2_rn(acc3, make_float2(ex2f(t3.x), ex2f(t3.y)));
+    }
+}
+
+// Passes 2q+1 (lanes 16..31) and 2q (lanes 0..15) together: outputs 64q .. 64q+63, lane (h, m) owns
+// x = 64q + 32h + 2m and x + 1.  Each half-warp keeps its own j-window (jl, je and the extension state
+// are uniform inside a half), so nothing is summed that the 32-output pass would not sum; the
+// bookkeeping instructions are shared by both passes.  In place: both halves have finished reading
+// before anything is written.
+__device__ __forceinline__ void conv_pass_pair(float* __restrict__ a, const float* __restrict__ b,
+                                               const uint16_t* __restrict__ jstar, int q, int lane, int& hl, int& hr,
+                                               int& chunks) {
+    const int x0 = 64 * q + (lane & 16) * 2;                  // first output of this half's pass
+    const int x = x0 + 2 * (lane & 15);
+    const int xmax = x0 + 31;
+    const uint32_t jpair = reinterpret_cast<const uint32_t*>(jstar)[x >> 1];
+    const int js0 = (int)(jpair & 0xffffu), js1 = (int)(jpair >> 16);
+    // j* is non-decreasing inside each 16-output walk of the merge path
+    const int jmin = min((int)jstar[x0], (int)jstar[x0 + 16]);
+    const int jmax = max((int)jstar[x0 + 15], (int)jstar[xmax]);
+    const float mx0 = a[x - js0] + b[js0];
+    const float mx1 = a[x + 1 - js1] + b[js1];
+    const float2 nm = make_float2(-mx0, -mx1);
+    float2 acc0 = make_float2(0.f, 0.f), acc1 = acc0, acc2 = acc0, acc3 = acc0;
+    int jl = max(jmin - hl, 0) & ~3;
+    int n4 = (min(jmax + hr, xmax) - jl + 4) >> 2;
+    int je = jl + 4 * n4 - 1;
+    int seg_j0 = jl, seg_m4 = n4;
+    bool left_open = jl > 0;                                   // uniform inside a half
+    const unsigned half_mask = (lane & 16) ? 0xffff0000u : 0x0000ffffu;
+    int grow_l = 0, grow_r = 0;
+#pragma unroll 1
+    for (;;) {
+        chunks += seg_m4;
+        conv_accumulate_pair(a + (x - seg_j0), reinterpret_cast<const float4*>(b + seg_j0), seg_m4, nm, acc0, acc1, acc2, acc3);
+        // edge terms of both outputs on both sides; lanes whose index runs below 0 read the -inf guard
+        const float2 al = *reinterpret_cast<const float2*>(a + (x - jl));             // x - jl is even
+        const float bl = b[jl], br = b[je];
+        const float ar0 = a[x - je], ar1 = a[x + 1 - je];
+        const bool need_l = left_open && (((al.x - mx0) + bl) >= -THETA || ((al.y - mx1) + bl) >= -THETA);
+        const bool need_r = (je < xmax) && (((ar0 - mx0) + br) >= -THETA || ((ar1 - mx1) + br) >= -THETA);
+        const unsigned vote_l = __ballot_sync(0xffffffffu, need_l), vote_r = __ballot_sync(0xffffffffu, need_r);
+        if ((vote_l | vote_r) == 0) break;
+        seg_m4 = 0;                                            // a half that is done idles through the other's extension
+        if (left_open) {
+            if (vote_l & half_mask) {
+                const int j2 = max(jl - max(hl + grow_l, 8), 0) & ~3;
+                seg_j0 = j2; seg_m4 = (jl - j2) >> 2;
+                grow_l += jl - j2;
+                jl = j2;
+                left_open = jl > 0;
+                continue;
+            }
+            left_open = false;                                 // this half's left edge is settled for good
+        }
+        if (vote_r & half_mask) {
+            seg_m4 = min((max(hr + grow_r, 8) + 3) >> 2, ((xmax | 3) - je) >> 2);
+            seg_j0 = je + 1;
+            grow_r += 4 * seg_m4;
+            je += 4 * seg_m4;
+        }
+    }
+    acc0 = __fadd2_rn(__fadd2_rn(acc0, acc1), __fadd2_rn(acc2, acc3));
+    const bool bad = !(acc0.x >= 0.7f && acc0.x <= 2048.f && acc0.y >= 0.7f && acc0.y <= 2048.f);
+    if (__any_sync(0xffffffffu, bad)) {
+        warp_logconv_exact_pass(a, b, 2 * q + 1, lane);
+        warp_logconv_exact_pass(a, b, 2 * q, lane);
+    } else {
+        __syncwarp();                                         // every lane has finished reading a[64q .. 64q+63]
+        *reinterpret_cast<float2*>(a + x) = make_float2(mx0 + lg2f(acc0.x) - LOG2_L, mx1 + lg2f(acc0.y) - LOG2_L);
+    }
+    // window half-widths: grown by the larger extension of the two halves, then allowed to shrink again
+#ifndef BAMSE_HALF_ADAPT
+    grow_l = max(grow_l, __shfl_xor_sync(0xffffffffu, grow_l, 16));
+    grow_r = max(grow_r, __shfl_xor_sync(0xffffffffu, grow_r, 16));
+#endif
+    hl += grow_l; hr += grow_r;
+    hl = max(4, hl - (hl >> 2));
+    hr = max(4, hr - (hr >> 2));
+}
+
 // One block of the LINEAR-DOMAIN ("framed") path: outputs 64*q .. 64*q+63, two per lane, in place.
 // Inside a block M_x is close to linear in x.  After removing a common tilt s (a multiple of 1/64, so
 // s * index is exact) and the centre output's maximising factors (ca, cb), every factor that matters
@@ -592,7 +723,8 @@ __device__ inline int warp_logconv(float* __restrict__ a, const float* __restric
         }
     } else {
 #pragma unroll 1
-        for (int pass = L / 32 - 1; pass >= 0; --pass) conv_pass_mufu(a, b, jstar, pass, lane, hl, hr, chunks);
+        for (int q = L / 64 - 1; q >= 0; --q) conv_pass_pair(a, b, jstar, q, lane, hl, hr, chunks);
+        chunks += __shfl_xor_sync(0xffffffffu, chunks, 16);   // 4-term chunks of both passes (per output lane)
     }
     __syncwarp();
     return chunks;
