@@ -23,11 +23,12 @@ constexpr int FAST_THREADS = FAST_WARPS * 32;
 constexpr int GUARD = 36;                           // -inf floats in front of every vector (a[x-j], j <= xmax+3)
 constexpr int VSTRIDE = GUARD + L + 4;              // floats per vector slot (4 trailing -inf: b[j], j <= 514)
 constexpr int FAST_SLOTS = 3;                       // max live vectors with the in-place convolution (brute-forced, K <= 12)
-#ifndef BAMSE_THETA
-#define BAMSE_THETA 30.0f
-#endif
-constexpr float THETA = BAMSE_THETA;                      // window threshold in bits: terms below 2^-30 of an output's
-                                                    // maximum are dropped (<= 512 of them, decaying: < 2^-22 relative)
+constexpr float THETA = 26.0f;                      // window threshold in bits: terms below 2^-26 of an output's
+                                                    // maximum are dropped.  They decay at least geometrically
+                                                    // (concavity) with the ratio of the last step inside the
+                                                    // window, <= 2^(-26/512): at most 4e-7 relative in the worst
+                                                    // case, ~3e-8 on peaked data -- below the rounding of the fp32
+                                                    // log values themselves
 constexpr float LOG2_L = 9.0f;                      // log2(512)
 // framed (linear-domain) path of the convolution
 constexpr int FR_B = 64;                            // outputs per framed block (2 per lane)
@@ -566,10 +567,8 @@ __device__ __forceinline__ void conv_pass_pair(float* __restrict__ a, const floa
         *reinterpret_cast<float2*>(a + x) = make_float2(mx0 + lg2f(acc0.x) - LOG2_L, mx1 + lg2f(acc0.y) - LOG2_L);
     }
     // window half-widths: grown by the larger extension of the two halves, then allowed to shrink again
-#ifndef BAMSE_HALF_ADAPT
     grow_l = max(grow_l, __shfl_xor_sync(0xffffffffu, grow_l, 16));
     grow_r = max(grow_r, __shfl_xor_sync(0xffffffffu, grow_r, 16));
-#endif
     hl += grow_l; hr += grow_r;
     hl = max(4, hl - (hl >> 2));
     hr = max(4, hr - (hr >> 2));

@@ -523,7 +523,7 @@ def main():
                         "conv_terms_executed_per_launch": stats["conv_terms"] / max(1, kern_n),
                         "conv_terms_algorithmic_per_launch": terms,
                         "note": "achieved/frac use the ALGORITHMIC op count (SURVEY 8d: every term of every "
-                                "convolution); the kernel exponentiates only the terms within 2^-30 of each "
+                                "convolution); the kernel exponentiates only the terms within 2^-26 of each "
                                 "output's maximum (log-concavity), so frac can exceed 1; xu_pipe_frac is the "
                                 "XU pipe utilisation of what actually executed"}
         traffic = None
