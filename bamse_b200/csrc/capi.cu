@@ -94,6 +94,19 @@ struct bamse_ctx {
 
 constexpr int PROGTAB_KMAX = 8;
 
+// A C++ exception (std::bad_alloc of a staging vector, in practice) must not cross the C ABI: the entry
+// points that allocate host memory are function-try-blocks that end here.
+static int on_exception(bamse_ctx* ctx, const char* fn) noexcept {
+    int code = BAMSE_EINTERNAL;
+    const char* what = "unexpected C++ exception";
+    try { throw; }
+    catch (const std::bad_alloc&) { code = BAMSE_ENOMEM; what = "out of host memory"; }
+    catch (const std::exception&) {}
+    catch (...) {}
+    try { if (ctx) ctx->fail(code, "%s: %s", fn, what); } catch (...) {}
+    return code;
+}
+
 static inline bool valid_precision(int p) { return p == BAMSE_FP32 || p == BAMSE_FP64 || p == BAMSE_FP32_LOGDOMAIN; }
 
 #define CTX_CHECK(ctx)                      \
@@ -201,7 +214,7 @@ int64_t bamse_samples_evaluated(bamse_ctx* ctx, int reset) {
 int64_t bamse_launch_count(const bamse_ctx* ctx) { return ctx ? ctx->launches : 0; }
 int64_t bamse_last_eval_count(const bamse_ctx* ctx) { return ctx ? ctx->last_evals : 0; }
 
-int bamse_kernel_time(bamse_ctx* ctx, int reset, double* out_ms, int64_t* out_launches) {
+int bamse_kernel_time(bamse_ctx* ctx, int reset, double* out_ms, int64_t* out_launches) try {
     CTX_CHECK(ctx);
     BAMSE_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     double ms = 0.0;
@@ -217,7 +230,7 @@ int bamse_kernel_time(bamse_ctx* ctx, int reset, double* out_ms, int64_t* out_la
         ctx->ev_used.clear();
     }
     return BAMSE_OK;
-}
+} catch (...) { return on_exception(ctx, "bamse_kernel_time"); }
 
 int bamse_kernel_stats(bamse_ctx* ctx, int reset, uint64_t* out4) {
     CTX_CHECK(ctx);
@@ -239,7 +252,7 @@ int bamse_decode_tree(int K, uint64_t tree_index, int8_t* out_parent) {
 }
 
 int bamse_upload_problem(bamse_ctx* ctx, int P, const double* err, int C, int M, int Kmax, const int32_t* K_of_c,
-                         const int64_t* var_counts, const int64_t* ref_counts) {
+                         const int64_t* var_counts, const int64_t* ref_counts) try {
     CTX_CHECK(ctx);
     ctx->have_problem = false;
     if (P < 1 || C < 1 || M < 1 || M > BAMSE_MMAX || Kmax < 1 || Kmax > KMAX || !err || !K_of_c || !var_counts ||
@@ -369,7 +382,7 @@ int bamse_upload_problem(bamse_ctx* ctx, int P, const double* err, int C, int M,
     }
     ctx->use_framed = (ctx->probed_choice >= 0 && ctx->probed_sig == ctx->problem_sig) ? ctx->probed_choice : -1;
     return BAMSE_OK;
-}
+} catch (...) { return on_exception(ctx, "bamse_upload_problem"); }
 
 // ---- internal: score a host vector of items, results to host ----------------------
 static int score_items_host(bamse_ctx* ctx, const std::vector<ScoreItem>& items, int precision, double* out) {
@@ -404,7 +417,7 @@ static int score_items_host(bamse_ctx* ctx, const std::vector<ScoreItem>& items,
 }
 
 int bamse_score_list(bamse_ctx* ctx, int64_t n_items, const int32_t* item_clust, const int8_t* item_parent,
-                     const int8_t* item_nodes, int precision, double* out_score) {
+                     const int8_t* item_nodes, int precision, double* out_score) try {
     CTX_CHECK(ctx);
     if (!ctx->have_problem) return ctx->fail(BAMSE_ESTATE, "bamse_score_list: no problem uploaded");
     if (n_items < 0 || (n_items > 0 && (!item_clust || !item_parent || !item_nodes || !out_score)))
@@ -438,7 +451,7 @@ int bamse_score_list(bamse_ctx* ctx, int64_t n_items, const int32_t* item_clust,
         for (int p = 0; p < ctx->P; ++p) { it.p = p; items[(size_t)p * n_items + i] = it; }
     }
     return score_items_host(ctx, items, precision, out_score);
-}
+} catch (...) { return on_exception(ctx, "bamse_score_list"); }
 
 static int enumerate_dev(bamse_ctx* ctx, const double* d_const, const double* d_thr, const uint64_t* d_begin,
                          const uint64_t* d_end, int topk, int precision, double slack_abs, double slack_rel,
@@ -605,7 +618,7 @@ static int enumerate_dev(bamse_ctx* ctx, const double* d_const, const double* d_
 }
 
 int bamse_score_range(bamse_ctx* ctx, int p, int c, uint64_t tree_begin, int64_t n, int precision, double* out_score,
-                      double* out_logscre) {
+                      double* out_logscre) try {
     CTX_CHECK(ctx);
     if (!ctx->have_problem) return ctx->fail(BAMSE_ESTATE, "bamse_score_range: no problem uploaded");
     if (p < 0 || p >= ctx->P || c < 0 || c >= ctx->C || n < 0)
@@ -632,11 +645,11 @@ int bamse_score_range(bamse_ctx* ctx, int p, int c, uint64_t tree_begin, int64_t
     if (out_logscre) BAMSE_CUDA_TRY(ctx, cudaMemcpyAsync(out_logscre, ctx->d_dense1.p, sizeof(double) * n, cudaMemcpyDeviceToHost, s));
     BAMSE_CUDA_TRY(ctx, cudaStreamSynchronize(s));
     return BAMSE_OK;
-}
+} catch (...) { return on_exception(ctx, "bamse_score_range"); }
 
 int bamse_enumerate_topk_dev(bamse_ctx* ctx, const double* d_clust_const, const double* d_threshold,
                              const uint64_t* d_tree_begin, const uint64_t* d_tree_end, int topk, int precision,
-                             double slack, bamse_record* d_out_records) {
+                             double slack, bamse_record* d_out_records) try {
     CTX_CHECK(ctx);
     if (!ctx->have_problem) return ctx->fail(BAMSE_ESTATE, "bamse_enumerate_topk_dev: no problem uploaded");
     if (topk < 1 || topk > BAMSE_TOPK_MAX || !d_out_records)
@@ -647,10 +660,10 @@ int bamse_enumerate_topk_dev(bamse_ctx* ctx, const double* d_clust_const, const 
     ctx->last_evals = -1;
     return enumerate_dev(ctx, d_clust_const, d_threshold, d_tree_begin, d_tree_end, topk, precision, slack, 0.0,
                          d_out_records, nullptr, nullptr, nullptr);
-}
+} catch (...) { return on_exception(ctx, "bamse_enumerate_topk_dev"); }
 
 int bamse_merge_topk_dev(bamse_ctx* ctx, const bamse_record* d_lists, int n_lists, int P, int topk,
-                         bamse_record* d_out_records) {
+                         bamse_record* d_out_records) try {
     CTX_CHECK(ctx);
     if (!d_lists || !d_out_records || n_lists < 1 || P < 1 || topk < 1 || topk > BAMSE_TOPK_MAX)
         return ctx->fail(BAMSE_EINVAL, "bamse_merge_topk_dev: bad arguments");
@@ -658,11 +671,11 @@ int bamse_merge_topk_dev(bamse_ctx* ctx, const bamse_record* d_lists, int n_list
     ctx->launches++;
     BAMSE_CUDA_TRY(ctx, cudaGetLastError());
     return BAMSE_OK;
-}
+} catch (...) { return on_exception(ctx, "bamse_merge_topk_dev"); }
 
 int bamse_score_topk(bamse_ctx* ctx, const double* clust_const, const double* threshold, const uint64_t* tree_begin,
                      const uint64_t* tree_end, int topk, int precision, bamse_record* out_records, int8_t* out_parent,
-                     int32_t* out_count) {
+                     int32_t* out_count) try {
     CTX_CHECK(ctx);
     if (!ctx->have_problem) return ctx->fail(BAMSE_ESTATE, "bamse_score_topk: no problem uploaded");
     if (!clust_const || !out_records || topk < 1 || topk > BAMSE_TOPK_MAX)
@@ -768,6 +781,6 @@ int bamse_score_topk(bamse_ctx* ctx, const double* clust_const, const double* th
         if (out_count) out_count[p] = cnt;
     }
     return BAMSE_OK;
-}
+} catch (...) { return on_exception(ctx, "bamse_score_topk"); }
 
 }  // extern "C"

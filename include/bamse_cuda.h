@@ -43,7 +43,8 @@ extern "C" {
 #define BAMSE_ENODEV (-2)   /* no CUDA device / not sm_100                               */
 #define BAMSE_ECUDA (-3)    /* CUDA runtime error (message has the cudaError string)     */
 #define BAMSE_ESTATE (-4)   /* call order (e.g. scoring before a problem is uploaded)    */
-#define BAMSE_ENOMEM (-5)
+#define BAMSE_ENOMEM (-5)   /* device or host allocation failed                         */
+#define BAMSE_EINTERNAL (-6) /* unexpected internal error (a C++ exception was caught)    */
 
 #define BAMSE_FP32 0        /* production: fp32 arithmetic, fp64 accumulation over samples */
 #define BAMSE_FP64 1        /* check mode: everything in fp64, reference operation order  */
