@@ -259,7 +259,7 @@ def main():
     ap.add_argument("--precision", default="fp32", choices=["fp32", "fp64"])
     ap.add_argument("--topk", type=int, default=5)
     ap.add_argument("--ref-items", type=int, default=16, help="work items per step of the reference arm")
-    ap.add_argument("--cpu-items", type=int, default=16, help="sample size of the cpu_baseline leg")
+    ap.add_argument("--cpu-items", type=int, default=48, help="sample size of the cpu_baseline leg (about 10 s on 16 cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--search-only", action="store_true",
                     help="not a bench line: run ONE pass of the early-exit search (for configurations whose full\n"
