@@ -171,3 +171,26 @@ def test_per_sample_scores_are_not_positive():
             tree = list(orc.decode_tree(K, int(rng.integers(0, K ** (K - 1)))))
             s = orc.tree_score_samples(tree, D, orc.prior_const(K))
             assert np.all(s <= 1e-12)
+
+
+def test_window_statistics_of_a_32_output_pass():
+    """What a half-warp pass exponentiates: the union of its 32 outputs' windows (one common j-range), against
+    the outputs' own windows and against windows aligned per lane to the lane's own j* (DESIGN.md section 8,
+    item 1).  own <= aligned <= union; on peaked data the union is ~1.3x the own windows."""
+    _, _, pairs, _ = _messages(6, 16000, seed=21, n_trees=8)
+    cut = THETA_BITS * math.log(2.0)
+    own, union, aligned = [], [], []
+    for a, b in pairs[:12]:
+        T = _terms(a, b)
+        mx, js = T.max(axis=1), T.argmax(axis=1)
+        inside = T >= (mx[:, None] - cut)
+        lo = inside.argmax(axis=1)
+        hi = L - 1 - inside[:, ::-1].argmax(axis=1)
+        own.append((hi - lo + 1).mean())
+        for x0 in range(0, L, 32):
+            s = slice(x0, x0 + 32)
+            union.append(hi[s].max() - lo[s].min() + 1)
+            aligned.append((js[s] - lo[s]).max() + (hi[s] - js[s]).max() + 1)
+    own, union, aligned = np.mean(own), np.mean(union), np.mean(aligned)
+    assert own <= aligned <= union
+    assert 1.1 < union / own < 2.0
