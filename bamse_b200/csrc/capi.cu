@@ -457,7 +457,7 @@ static int enumerate_dev(bamse_ctx* ctx, const double* d_const, const double* d_
                          const uint64_t* d_end, int topk, int precision, double slack_abs, double slack_rel,
                          bamse_record* d_out, double* d_dense_score, double* d_dense_logscre, const Segment* host_seg);
 
-// The fp32 kernel has two instantiations: the exponential path only (lean: 7 CTAs/SM), and one that
+// The fp32 kernel has two instantiations: the exponential path only (lean: 10 or 7 CTAs/SM), and one that
 // also carries the linear-domain "framed" path (6 CTAs/SM), which wins when the tables are flat
 // (low coverage: most terms of a convolution matter) and loses on sharply peaked tables.  Which one
 // is faster is a property of the data, so it is measured once per problem on an interleaved sample of

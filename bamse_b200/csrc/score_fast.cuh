@@ -8,7 +8,8 @@
 //     per-output max-shift M_x costs O(L) per convolution instead of an O(L^2) max pass;
 //   * windowing: the terms of one output are concave in j, so the ones within THETA bits
 //     of M_x form a contiguous window around j*; only those are exponentiated (MUFU.EX2),
-//     32 consecutive outputs at a time over the union of their windows.
+//     32 consecutive outputs at a time over the union of their windows (one such pass per
+//     half-warp, two adjacent outputs per lane: conv_pass_pair).
 //
 // Results equal the reference's my_convolve (clustering.py:365-370) up to fp32 rounding:
 // dropped terms are below 2^-THETA of the output they belong to.
@@ -379,7 +380,9 @@ __device__ __forceinline__ void conv_accumulate(const float* __restrict__ pa, co
     }
 }
 
-// One pass of the exponential path: outputs 32*pass .. 32*pass+31, lane = output, in place.
+// One pass of the exponential path: outputs 32*pass .. 32*pass+31, lane = output, in place.  Used by the
+// framed instantiation for the blocks that do not fit a frame; the exponential-only instantiations
+// run conv_pass_pair (two passes per step).
 __device__ __forceinline__ void conv_pass_mufu(float* __restrict__ a, const float* __restrict__ b,
                                                const uint16_t* __restrict__ jstar, int pass, int lane, int& hl, int& hr,
                                                int& chunks) {
