@@ -34,7 +34,18 @@ def build_parser():
     parser.add_argument('--device', default=0, type=int, help='CUDA device ordinal (B200)')
     parser.add_argument('--check', action='store_true', help='score everything in the fp64 check mode')
     parser.add_argument('--seed', default=None, type=int, help='seed numpy/sklearn RNG for reproducible KMeans restarts')
+    parser.add_argument('--tree-budget', default=2e11, type=float,
+                        help='refuse to start when the clusterings to analyse span more labeled rooted trees than '
+                             'this (the search is exhaustive: K^(K-1) trees per K-cluster clustering; default 2e11)')
     return parser
+
+
+def _fmt_duration(sec):
+    if sec < 120:
+        return "%.0f s" % sec
+    if sec < 7200:
+        return "%.0f min" % (sec / 60.0)
+    return "%.1f h" % (sec / 3600.0)
 
 
 def read_input(path):
@@ -70,7 +81,16 @@ def main(argv=None):
     clusts, pf = candidate_clusterings(X_As, X_Bs, max_clusts, n_trees, err, ctx=ctx, verbose=True)
     if any(int(c.As.shape[0]) > cuda_shim.KMAX for c in clusts):
         raise SystemExit("bamse: more than %d clusters is not supported by the CUDA scorer" % cuda_shim.KMAX)
-    print('analysing %d clusterings on the GPU' % len(clusts))
+    # The reference prunes with a heuristic branch-and-bound; this scorer searches all K^(K-1) labeled rooted
+    # trees of every clustering exactly.  Say what that means before starting (K = 11: 2.6e10, K = 12: 7.4e11).
+    n_trees_total = sum(int(c.As.shape[0]) ** (int(c.As.shape[0]) - 1) for c in clusts)
+    rate = 2.0e7                                    # full-scoring trees/s of one B200 on config 2; the early exit
+    print('analysing %d clusterings on the GPU: %.3g labeled rooted trees, at most ~%s at %.0e trees/s/GPU '
+          '(typically 5-10x less with the exact early exit)'
+          % (len(clusts), n_trees_total, _fmt_duration(n_trees_total / rate), rate))
+    if n_trees_total > args.tree_budget:
+        raise SystemExit("bamse: %.3g trees exceed --tree-budget %.3g (clusterings with K >= 11 take hours per "
+                         "clustering); lower -nc / -n or raise --tree-budget explicitly" % (n_trees_total, args.tree_budget))
     trees = analyse_clusterings(clusts, top_trees, ctx=ctx,
                                 precision=cuda_shim.FP64 if args.check else cuda_shim.FP32)
     for x in trees:

@@ -12,6 +12,7 @@ candidate's control flow (their scores are batched GPU calls).
 """
 import functools
 import math
+import warnings
 
 import numpy as np
 from scipy.special import gammaln
@@ -177,16 +178,23 @@ class clustering:
         self.trees = [{'tree': tree, 'root': 0}]
         return [{'tree': tree, 'root': 0}]
 
-    def get_trees2(self, candidate_tree, max_trees=cuda_shim.TOPK_MAX):
+    def get_trees2(self, candidate_tree, max_trees=cuda_shim.TOPK_MAX, precision=cuda_shim.FP32):
         """every labeled rooted tree with score + log scre >= the candidate's (the set the
         reference's branch-and-bound, clustering.py:116-148, searches for), found by
-        exhaustive GPU enumeration.  At most `max_trees` (<= 64) best ones are returned."""
+        exhaustive GPU enumeration.  Deviation from the reference: at most `max_trees`
+        (<= cuda_shim.TOPK_MAX = 64) best ones are returned, best first; a warning says when
+        the list was cut (the reference returns every qualifying tree, in search order)."""
+        if not 1 <= int(max_trees) <= cuda_shim.TOPK_MAX:
+            raise ValueError("get_trees2: max_trees must be in [1, %d]" % cuda_shim.TOPK_MAX)
         K = self.As.shape[0]
         cand = list(candidate_tree['tree'])
         thr = self.get_tree_score(cand, list(range(K))) + np.log(canonizeF(cand)['scre'])
         ctx = self._make_resident()
         rec, par, cnt = ctx.score_topk(np.zeros((1, 1)), np.array([[thr]]), topk=int(max_trees),
-                                       precision=cuda_shim.FP32)
+                                       precision=precision)
+        if int(cnt[0]) == int(max_trees):
+            warnings.warn("get_trees2: %d or more trees reach the candidate's score; only the best %d are kept"
+                          % (int(max_trees), int(max_trees)))
         self.trees = []
         for j in range(int(cnt[0])):
             tree = [int(x) for x in par[0, j, :K]]
@@ -263,6 +271,9 @@ def analyse_clusterings(clusts, top_trees, ctx=None, precision=cuda_shim.FP32, s
     thr = np.array([[s[ci] + math.log(canonizeF(cand[ci])['scre']) for ci in range(len(clusts))]])
     const = np.array([[c.cluster_prior + c.maxlikelihood for c in clusts]])
     # 4. exhaustive enumeration + global top-k
+    if int(top_trees) > cuda_shim.TOPK_MAX:
+        warnings.warn("analyse_clusterings: -t %d exceeds the scorer's top-k capacity; returning the best %d"
+                      % (int(top_trees), cuda_shim.TOPK_MAX))
     if tree_shard is not None:
         ctx.set_shard(*tree_shard)
     # the search only needs the trees that can still qualify: exact sample-level early exit
@@ -272,17 +283,22 @@ def analyse_clusterings(clusts, top_trees, ctx=None, precision=cuda_shim.FP32, s
                                        precision=precision)
     finally:
         ctx.set_early_exit(False)
+        if tree_shard is not None:
+            ctx.set_shard(0, 1)          # the context is process-wide: never leave it sharded
     out = []
+    for c in clusts:
+        c.trees = []
     for j in range(int(cnt[0])):
         c = clusts[int(rec[0, j]['clust'])]
         K = c.As.shape[0]
         tree = [int(x) for x in par[0, j, :K]]
-        c.trees = [{'tree': tree, 'root': tree.index(-1), 'score': float(rec[0, j]['score'])}]
-        c.analyse_trees_regular2(solve_fractions=solve_fractions)
-        t = c.trees[0]
-        t['tree_index'] = int(rec[0, j]['tree'])
-        t['clustering_index'] = int(rec[0, j]['clust'])
+        t = {'tree': tree, 'root': tree.index(-1), 'score': float(rec[0, j]['score']),
+             'tree_index': int(rec[0, j]['tree']), 'clustering_index': int(rec[0, j]['clust'])}
+        c.trees.append(t)                # a clustering keeps all of its ranked trees
         out.append(t)
+    for c in clusts:
+        if c.trees:
+            c.analyse_trees_regular2(solve_fractions=solve_fractions)
     for c, cd in zip(clusts, cand):
         c.candidate = cd
     return out

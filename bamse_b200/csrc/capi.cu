@@ -59,8 +59,11 @@ struct bamse_ctx {
     DBuf d_segs, d_scalars /* total_chunks, total_trees, next_chunk */, d_cand, d_items, d_scores;
     DBuf d_const, d_thr, d_begin, d_end, d_records, d_dense0, d_dense1, d_split, d_lists;
     int grid[3] = {0, 0, 0};
+    uint64_t last_cand_cap = 0;   // capacity of the candidate bag of the last enumeration
     int shard_rank = 0, shard_world = 1;
     int early_exit = 0;      // BAMSE_OPT_EARLY_EXIT
+    int last_verified = 1;   // the last bamse_score_topk proved its preselection cut safe (bamse_last_topk_verified)
+    int last_ksel = 0;       // ... and the preselection size it ended with
     int use_framed = -1;     // fp32 kernel variant for the resident problem: -1 not probed yet, 0 exponential, 1 framed
     bool probing = false;
     uint64_t problem_sig = 0, probed_sig = 0;   // the variant choice is memoised per problem content
@@ -93,6 +96,7 @@ struct bamse_ctx {
 };
 
 constexpr int PROGTAB_KMAX = 8;
+constexpr int TOPK_INTERNAL = BAMSE_TOPK_INTERNAL;   // preselection lists may grow to this size (public topk <= BAMSE_TOPK_MAX)
 
 // A C++ exception (std::bad_alloc of a staging vector, in practice) must not cross the C ABI: the entry
 // points that allocate host memory are function-try-blocks that end here.
@@ -212,6 +216,8 @@ int64_t bamse_samples_evaluated(bamse_ctx* ctx, int reset) {
 }
 
 int64_t bamse_launch_count(const bamse_ctx* ctx) { return ctx ? ctx->launches : 0; }
+int bamse_last_topk_verified(const bamse_ctx* ctx) { return ctx ? ctx->last_verified : 0; }
+int bamse_last_topk_preselected(const bamse_ctx* ctx) { return ctx ? ctx->last_ksel : 0; }
 int64_t bamse_last_eval_count(const bamse_ctx* ctx) { return ctx ? ctx->last_evals : 0; }
 
 int bamse_kernel_time(bamse_ctx* ctx, int reset, double* out_ms, int64_t* out_launches) try {
@@ -569,6 +575,7 @@ static int enumerate_dev(bamse_ctx* ctx, const double* d_const, const double* d_
     w.cand = ctx->d_cand.as<bamse_record>();
     w.cand_count = reinterpret_cast<unsigned long long*>(scal + 3);
     w.cand_cap = cand_cap;
+    ctx->last_cand_cap = cand_cap;
     w.dense_score = d_dense_score;
     w.dense_logscre = d_dense_logscre;
     w.stats = reinterpret_cast<unsigned long long*>(scal + 4);
@@ -580,7 +587,7 @@ static int enumerate_dev(bamse_ctx* ctx, const double* d_const, const double* d_
         w.lists = ctx->d_lists.as<bamse_record>();
     }
     w.prog_tabs = (precision == BAMSE_FP32 && ctx->have_progtabs) ? ctx->d_progtabs.as<const TreeProgram*>() : nullptr;
-    w.early_exit = (ctx->early_exit && !host_seg && !ctx->probing && topk > 0 && precision == BAMSE_FP32) ? 1 : 0;
+    w.early_exit = (ctx->early_exit && !host_seg && !ctx->probing && topk > 0) ? 1 : 0;
     // tail splitting: when a worker gets fewer than ~48 single-tree chunks, issue the last `workers`
     // trees in 2 (or, below 16 chunks per worker, 4) parts over the samples
     w.split_ways = 1; w.n_split = 0; w.split_acc = nullptr; w.split_cnt = nullptr;
@@ -707,22 +714,49 @@ int bamse_score_topk(bamse_ctx* ctx, const double* clust_const, const double* th
         BAMSE_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_begin.p, tree_begin, sizeof(uint64_t) * C, cudaMemcpyHostToDevice, s));
         BAMSE_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_end.p, tree_end, sizeof(uint64_t) * C, cudaMemcpyHostToDevice, s));
     }
-    // fp32: over-select with a slack that covers fp32 rounding, then re-score in fp64.
-    const int ksel = precision == BAMSE_FP64 ? topk : std::min(BAMSE_TOPK_MAX, topk + 8);
-    const double slack_abs = precision == BAMSE_FP64 ? 0.0 : 1e-3;
-    const double slack_rel = precision == BAMSE_FP64 ? 1e-12 : 1e-5;
-    BAMSE_CUDA_TRY(ctx, ctx->d_records.ensure(sizeof(bamse_record) * P * ksel));
-    int rc = enumerate_dev(ctx, ctx->d_const.as<double>(), threshold ? ctx->d_thr.as<double>() : nullptr,
-                           tree_begin ? ctx->d_begin.as<uint64_t>() : nullptr,
-                           tree_begin ? ctx->d_end.as<uint64_t>() : nullptr, ksel, precision, slack_abs, slack_rel,
-                           ctx->d_records.as<bamse_record>(), nullptr, nullptr, nullptr);
-    if (rc) return rc;
-    ctx->last_evals = evals;
-    std::vector<bamse_record> recs((size_t)P * ksel);
-    BAMSE_CUDA_TRY(ctx, cudaMemcpyAsync(recs.data(), ctx->d_records.p, sizeof(bamse_record) * P * ksel, cudaMemcpyDeviceToHost, s));
-    BAMSE_CUDA_TRY(ctx, cudaStreamSynchronize(s));
-
-    if (precision != BAMSE_FP64) {
+    // Preselection + verified cut.  The enumeration kernel ranks by ITS OWN arithmetic (fp32, or the check
+    // mode's device-side sums); the returned ranking must be the one of the fp64 check-mode scores of the
+    // list-scoring kernel.  So: select the best `ksel` > topk per parameter set (thresholds relaxed by a slack
+    // that covers the selection arithmetic's error), re-score exactly that short list in fp64, apply the exact
+    // threshold, rank -- and then PROVE that nothing outside the list could belong to the top `topk`: every
+    // unselected tree has a selection total <= the worst selected one, T_last, and an fp64 total of at most
+    // T_last + B with B = rel * max_c |T_last - const[p][c]| + abs (the error bound of the selection
+    // arithmetic on a score of that magnitude; the bound of a tree further down grows slower than its
+    // distance).  The cut is safe when the list was not full (everything that qualified is in it) or when
+    // the topk-th re-scored total exceeds T_last + B; otherwise ksel is doubled and the enumeration repeated
+    // (near-degenerate clusterings: many trees tied within rounding).  At the internal cap the result is
+    // returned best-effort and bamse_last_topk_verified() reports 0.
+    const double sel_rel = precision == BAMSE_FP64 ? 1e-11 : 2e-6;      // error bound of the selection arithmetic:
+    const double sel_abs = precision == BAMSE_FP64 ? 1e-9 : 1e-4;       // relative to |score|, plus absolute
+    const double slack_abs = precision == BAMSE_FP64 ? 1e-9 : 1e-3;     // threshold relaxation (>= the bound)
+    const double slack_rel = precision == BAMSE_FP64 ? 1e-11 : 1e-5;
+    int ksel = std::min(TOPK_INTERNAL, topk + 8);
+    std::vector<bamse_record> recs;
+    ctx->last_verified = 1;
+    for (;;) {
+        BAMSE_CUDA_TRY(ctx, ctx->d_records.ensure(sizeof(bamse_record) * P * ksel));
+        int rc = enumerate_dev(ctx, ctx->d_const.as<double>(), threshold ? ctx->d_thr.as<double>() : nullptr,
+                               tree_begin ? ctx->d_begin.as<uint64_t>() : nullptr,
+                               tree_begin ? ctx->d_end.as<uint64_t>() : nullptr, ksel, precision, slack_abs, slack_rel,
+                               ctx->d_records.as<bamse_record>(), nullptr, nullptr, nullptr);
+        if (rc) return rc;
+        ctx->last_evals = evals;
+        recs.assign((size_t)P * ksel, bamse_record());
+        uint64_t bag[2] = {0, 0};                     // scalars [3] = records appended to the bag
+        BAMSE_CUDA_TRY(ctx, cudaMemcpyAsync(recs.data(), ctx->d_records.p, sizeof(bamse_record) * P * ksel, cudaMemcpyDeviceToHost, s));
+        BAMSE_CUDA_TRY(ctx, cudaMemcpyAsync(bag, ctx->d_scalars.as<uint64_t>() + 3, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+        BAMSE_CUDA_TRY(ctx, cudaStreamSynchronize(s));
+        if (bag[0] > ctx->last_cand_cap)
+            return ctx->fail(BAMSE_EINTERNAL, "bamse_score_topk: candidate bag overflow (%llu records, capacity %llu)",
+                             (unsigned long long)bag[0], (unsigned long long)ctx->last_cand_cap);
+        // worst selected total and list fill per parameter set, before the re-score reorders anything
+        std::vector<double> t_last(P, -INFINITY);
+        std::vector<int> n_sel(P, 0);
+        for (int p = 0; p < P; ++p)
+            for (int j = 0; j < ksel; ++j) {
+                const bamse_record& r = recs[(size_t)p * ksel + j];
+                if (r.clust >= 0) { t_last[p] = r.total; n_sel[p]++; }
+            }
         // fp64 check-mode re-score of the short list, exact threshold, final ranking
         std::vector<ScoreItem> items;
         std::vector<size_t> where;
@@ -754,6 +788,7 @@ int bamse_score_topk(bamse_ctx* ctx, const double* clust_const, const double* th
                 if (!(r.score >= th - 1e-12 * fabs(th))) r.clust = -1;
             }
         }
+        bool verified = true;
         for (int p = 0; p < P; ++p) {
             bamse_record* b = recs.data() + (size_t)p * ksel;
             std::stable_sort(b, b + ksel, [](const bamse_record& x, const bamse_record& y) {
@@ -763,7 +798,17 @@ int bamse_score_topk(bamse_ctx* ctx, const double* clust_const, const double* th
                 if (x.clust != y.clust) return x.clust < y.clust;
                 return x.tree < y.tree;
             });
+            if (n_sel[p] < ksel) continue;            // the list holds every tree that passed the relaxed threshold
+            double spread = 0.0;
+            for (int c = 0; c < C; ++c) spread = std::max(spread, fabs(t_last[p] - clust_const[(size_t)p * C + c]));
+            const double bound = sel_rel * spread + sel_abs;
+            const bamse_record& kth = b[topk - 1];    // ksel > topk here, or ksel == TOPK_INTERNAL
+            if (!(kth.clust >= 0 && kth.total > t_last[p] + bound)) verified = false;
         }
+        ctx->last_ksel = ksel;
+        if (verified) break;
+        if (ksel >= TOPK_INTERNAL) { ctx->last_verified = 0; break; }
+        ksel = std::min(TOPK_INTERNAL, 2 * ksel);
     }
     for (int p = 0; p < P; ++p) {
         int cnt = 0;

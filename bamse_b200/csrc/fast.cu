@@ -343,7 +343,7 @@ k_enumerate_fast(ProblemView pv, FastTables ft, EnumWork w) {
                 const double full = score + logscre;
                 if (w.dense_score) w.dense_score[off + i] = score;
                 if (w.dense_logscre) w.dense_logscre[off + i] = logscre;
-                if (w.topk > 0 && full >= seg.threshold) {
+                if (w.topk > 0 && full >= seg.threshold && full > -CUDART_INF) {   // an early-exited tree is -inf
                     bamse_record r;
                     r.total = full + seg.clust_const; r.score = full; r.clust = seg.c; r.param = seg.p; r.tree = tree;
                     if (!(ntop == w.topk && !rec_better_f(r, list[w.topk - 1]))) {

@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(LD_THREADS) k_enumerate_logdomain(ProblemView 
     __shared__ T scratch[LD_THREADS / 32];
     __shared__ TreeProgram prog;
     __shared__ unsigned long long s_chunk;
-    __shared__ bamse_record s_top[BAMSE_TOPK_MAX];
+    __shared__ bamse_record s_top[BAMSE_TOPK_INTERNAL];
     __shared__ int s_ntop;
     const int t = threadIdx.x;
     if (t == 0) s_ntop = 0;
@@ -152,13 +152,22 @@ __global__ void __launch_bounds__(LD_THREADS) k_enumerate_logdomain(ProblemView 
                 build_program(seg.K, parent, nullptr, &prog);
             }
             __syncthreads();
-            const double score = eval_tree_logdomain<T>(pv, seg.p, seg.c, &prog, pool, scratch);
+            double cut = -CUDART_INF;
+            if (w.early_exit) {
+                // what this tree needs: its clustering's threshold, or the CTA's k-th best so far
+                double c0 = seg.threshold;
+                if (w.topk > 0 && s_ntop == w.topk) c0 = fmax(c0, s_top[w.topk - 1].total - seg.clust_const);
+                cut = c0 - log((double)prog.scre) - 1e-6 - 1e-9 * fabs(c0);
+            }
+            unsigned done = 0;
+            const double score = eval_tree_logdomain<T>(pv, seg.p, seg.c, &prog, pool, scratch, 0, -1, cut, &done);
             if (t == 0) {
+                if (w.samples_done) atomicAdd(w.samples_done, (unsigned long long)done);
                 const double logscre = log((double)prog.scre);
                 const double full = score + logscre;                 // clustering.py:182
                 if (w.dense_score) w.dense_score[off + i] = score;
                 if (w.dense_logscre) w.dense_logscre[off + i] = logscre;
-                if (w.topk > 0 && full >= seg.threshold) {           // clustering.py:146-147
+                if (w.topk > 0 && full >= seg.threshold && full > -CUDART_INF) {   // clustering.py:146-147
                     bamse_record r;
                     r.total = full + seg.clust_const;                // clustering.py:183
                     r.score = full; r.clust = seg.c; r.param = seg.p; r.tree = tree;

@@ -121,7 +121,8 @@ template <> struct TableSel<float> { static __device__ const float* get(const Pr
 template <typename T>
 __device__ double eval_tree_logdomain(const ProblemView& pv, int p, int c, const TreeProgram* prog,
                                       T* pool /* [MAX_STACK][L] */, T* scratch /* [LD_THREADS/32] */,
-                                      int m_begin = 0, int m_end = -1) {
+                                      int m_begin = 0, int m_end = -1, double cut = -CUDART_INF,
+                                      unsigned* n_done = nullptr) {
     const int t = threadIdx.x;
     const T log_len = (T)6.2383246250395077847550890931236;  // log(512)
     const T add = (T)pv.p0[c] - log_len;
@@ -164,6 +165,10 @@ __device__ double eval_tree_logdomain(const ProblemView& pv, int p, int c, const
         }
         const T sm = block_logsumexp(pool + (slots & 15) * L, log_len, scratch);
         total += (double)sm;
+        if (n_done) ++*n_done;
+        // exact early exit (BAMSE_OPT_EARLY_EXIT): every per-sample score is <= 0, so a partial sum below
+        // the cut cannot recover; block-uniform (every thread holds the same total)
+        if (total < cut) return -CUDART_INF;
     }
     return total;
 }

@@ -62,6 +62,10 @@ def load_library():
     lib.bamse_set_option.argtypes = [c_p, i32, i32]
     lib.bamse_samples_evaluated.restype = i64
     lib.bamse_samples_evaluated.argtypes = [c_p, i32]
+    lib.bamse_last_topk_verified.restype = i32
+    lib.bamse_last_topk_verified.argtypes = [c_p]
+    lib.bamse_last_topk_preselected.restype = i32
+    lib.bamse_last_topk_preselected.argtypes = [c_p]
     lib.bamse_launch_count.restype = i64
     lib.bamse_launch_count.argtypes = [c_p]
     lib.bamse_last_eval_count.restype = i64
@@ -92,7 +96,7 @@ def load_library():
 
 EXPORTED_SYMBOLS = [
     "bamse_abi_version", "bamse_create", "bamse_destroy", "bamse_last_error", "bamse_set_stream", "bamse_set_shard", "bamse_fast_variant", "bamse_set_option", "bamse_samples_evaluated",
-    "bamse_launch_count", "bamse_last_eval_count", "bamse_decode_tree", "bamse_upload_problem",
+    "bamse_launch_count", "bamse_last_eval_count", "bamse_last_topk_verified", "bamse_last_topk_preselected", "bamse_decode_tree", "bamse_upload_problem",
     "bamse_score_list", "bamse_score_range", "bamse_score_topk", "bamse_enumerate_topk_dev",
     "bamse_merge_topk_dev", "bamse_kernel_time", "bamse_kernel_stats",
 ]
@@ -236,7 +240,20 @@ class Context(object):
         cnt = np.empty(self.P, dtype=np.int32)
         self._check(self._lib.bamse_score_topk(self._h, _ptr(cc), _ptr(th), _ptr(tb), _ptr(te), int(topk),
                                                int(precision), _ptr(rec), _ptr(par), _ptr(cnt)))
+        if not self.last_topk_verified:
+            import warnings
+            warnings.warn("libbamse_cuda: more than %d trees are tied within rounding of the top-%d cut; the "
+                          "ranking below the ties is best effort" % (self.last_topk_preselected, topk))
         return rec, par, cnt
+
+    @property
+    def last_topk_verified(self):
+        """True when the last score_topk proved its preselection cut safe (identical to a full fp64 ranking)."""
+        return bool(self._lib.bamse_last_topk_verified(self._h))
+
+    @property
+    def last_topk_preselected(self):
+        return int(self._lib.bamse_last_topk_preselected(self._h))
 
     # ---------------------------------------------------------------- device-resident
     def enumerate_topk_dev(self, d_clust_const, d_threshold, d_tree_begin, d_tree_end, topk, precision, slack,

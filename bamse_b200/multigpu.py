@@ -1,4 +1,4 @@
-"""Multi-GPU plumbing: one process (rank) per GPU, trees sharded by index range, one
+"""Multi-GPU plumbing: one process (rank) per GPU, trees sharded by interleaved index, one
 all-gather of each rank's top-k records, identical deterministic merge on every rank.
 
 torch.distributed is used only as the transport (NCCL over NVLink on the GPU box, gloo in
@@ -9,13 +9,17 @@ import numpy as np
 from .cuda_shim import RECORD_DTYPE
 
 
-def shard_ranges(K_of_c, rank, world):
-    """tree-index range [begin, end) of every clustering for `rank` of `world`:
-    rank r takes [T*r/W, T*(r+1)/W) of the T = K^(K-1) labeled rooted trees."""
-    T = [int(k) ** (int(k) - 1) for k in K_of_c]
-    begin = np.array([t * rank // world for t in T], dtype=np.uint64)
-    end = np.array([t * (rank + 1) // world for t in T], dtype=np.uint64)
-    return begin, end
+def shard_size(T, rank, world):
+    """number of tree indices of a T-tree clustering that `rank` of `world` scores under the library's
+    interleaved sharding (bamse_set_shard): indices rank, rank + world, rank + 2 world, ... below T."""
+    T, rank, world = int(T), int(rank), int(world)
+    return (T - rank + world - 1) // world if T > rank else 0
+
+
+def shard_indices(T, rank, world):
+    """the tree indices themselves (tests / small T only).  Interleaving, not contiguous ranges: the high
+    Pruefer digits select the tree shape, so contiguous ranges differ in cost (low indices are star-like)."""
+    return np.arange(int(rank), int(T), int(world), dtype=np.uint64)
 
 
 def merge_records(lists, topk):

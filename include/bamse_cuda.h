@@ -37,6 +37,7 @@ extern "C" {
 #define BAMSE_KMAX 12       /* bamse.py:32          default of -nc; 12^11 fits uint64    */
 #define BAMSE_MMAX 64       /* samples per problem                                       */
 #define BAMSE_TOPK_MAX 64
+#define BAMSE_TOPK_INTERNAL 256 /* bamse_score_topk may preselect up to this many per parameter set  */
 
 #define BAMSE_OK 0
 #define BAMSE_EINVAL (-1)   /* bad argument                                              */
@@ -90,6 +91,13 @@ int bamse_fast_variant(const bamse_ctx* ctx);
 #define BAMSE_OPT_EARLY_EXIT 1
 int bamse_set_option(bamse_ctx* ctx, int option, int value);
 int64_t bamse_samples_evaluated(bamse_ctx* ctx, int reset);
+/* bamse_score_topk selects a short list with the enumeration kernel's arithmetic, re-scores it in fp64 and
+ * then proves that no unselected tree can belong to the top `topk` (growing the short list when the proof
+ * fails, up to BAMSE_TOPK_INTERNAL).  1 = the last call's result is proven identical to a full fp64 ranking;
+ * 0 = the list hit the cap first (hundreds of trees tied within rounding): best effort.
+ * bamse_last_topk_preselected: the preselection size the last call ended with. */
+int bamse_last_topk_verified(const bamse_ctx* ctx);
+int bamse_last_topk_preselected(const bamse_ctx* ctx);
 /* Number of kernels this ctx has launched since creation (for bench.py `gpu_launches`). */
 int64_t bamse_launch_count(const bamse_ctx* ctx);
 
@@ -132,9 +140,11 @@ int bamse_score_range(bamse_ctx* ctx, int p, int c, uint64_t tree_begin, int64_t
  * K_c^(K_c-1)), keeps trees with score + log scre >= threshold[p][c] (NULL = keep all;
  * clustering.py:144-147), ranks by total = score + log scre + clust_const[p][c]
  * (ties: clust asc, tree asc) and returns the best `topk` per p.
- *   precision BAMSE_FP32: candidates are selected in fp32 with a small slack, then
- *   re-scored in fp64 before the exact threshold test and the final ranking, so the
- *   returned totals/scores are fp64 check-mode values.
+ *   In every precision a short list (topk + 8, doubled while the cut cannot be proven safe) is
+ *   selected by the enumeration kernel with a small slack, re-scored by the fp64 list-scoring
+ *   kernel before the exact threshold test and the final ranking: the returned totals/scores
+ *   are fp64 check-mode values and BAMSE_FP32 / BAMSE_FP64 return the same records
+ *   (see bamse_last_topk_verified).
  * out_records [P][topk] (unused slots: clust = -1), out_parent [P][topk][Kmax] parent
  * vectors (padding -2), out_count [P] number of valid records.  Host buffers. */
 int bamse_score_topk(bamse_ctx* ctx, const double* clust_const /* [P][C] */,

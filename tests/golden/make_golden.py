@@ -221,6 +221,95 @@ def gen_search():
     dump("search.json", out)
 
 
+# ------------------------------------------------- 6. tree scores at K = 8 .. 12 (round 2)
+def gen_scores_highk():
+    """reference-produced get_tree_score values where configs 3/4 live (K = 8, 9, 10, 11, 12): random labeled
+    rooted trees + the chain and the star of every K, simdata-like and high-coverage tables, full node sets.
+    One reference eval costs (K + leaves - 1) my_convolve calls per sample (~15 ms each)."""
+    cases = []
+    rng = np.random.default_rng(20261020)
+    n = 0
+    for K in (8, 9, 10, 11, 12):
+        shapes = [random_tree(rng, K) for _ in range(4)]
+        shapes.append([-1] + list(range(K - 1)))            # chain: scans only
+        shapes.append([-1] + [0] * (K - 1))                 # star: K - 2 convolutions
+        # a deep tree with a wide node in the middle
+        shapes.append([-1, 0, 1] + [2] * (K - 3))
+        for rep, tree in enumerate(shapes):
+            M = 3 if K <= 10 else 2
+            cov = int([200, 1000, 30000, 200, 2000, 200, 100000][rep])
+            frac = rng.dirichlet(np.ones(K + 1))[:K]
+            frac = np.sort(frac)[::-1]
+            cm = np.clip(np.cumsum(frac[::-1])[::-1][:, None] * rng.uniform(0.6, 1.0, size=(K, M)), 0, 1)
+            err = float(rng.choice([0.001, 0.003]))
+            As = rng.binomial(cov, cm * (0.5 - err) + err)
+            Bs = cov - As
+            D, P = ref_tables(As, Bs, err, K)
+            t0 = time.time()
+            s = cl.tree_integrate_multisample(np.array(tree), D, P)
+            scre = int(tt.canonizeF(tree)["scre"])
+            cases.append(dict(id="H%d" % n, var=As.tolist(), ref=Bs.tolist(), err=err, K_prior=K, tree=[int(x) for x in tree],
+                              nodes=list(range(K)), per_sample=s.tolist(), total=float(np.sum(s)), scre=scre))
+            print("highk case", n, "K", K, "%.1fs" % (time.time() - t0), flush=True)
+            n += 1
+    dump("tree_scores_highk.json", cases)
+
+
+# ------------------------------------------- 7. search path on bamse.dat and at K = 5 (round 2)
+def _search_case(am, bm, assign, pf, err, spec, extra=None):
+    import contextlib
+    import io
+    t0 = time.time()
+    c = cl.clustering(am, bm, tuple(int(x) for x in assign), pf, err)
+    with contextlib.redirect_stdout(io.StringIO()):
+        c.reorder()
+        cand = c.get_candidate_tree()[0]
+        K = c.As.shape[0]
+        thr = c.get_tree_score(cand["tree"], list(range(K))) + np.log(tt.canonizeF(cand["tree"])["scre"])
+        trees = c.get_trees2(cand)
+    kept = []
+    for t in trees:
+        sc = c.get_tree_score(t["tree"], list(range(K)))
+        scre = int(tt.canonizeF(t["tree"])["scre"])
+        kept.append(dict(tree=[int(x) for x in t["tree"]], root=int(t["root"]), score=float(sc), scre=scre,
+                         totalscore=float(sc + np.log(scre) + c.cluster_prior + c.maxlikelihood)))
+    out = dict(spec=spec, am=np.asarray(am).tolist(), bm=np.asarray(bm).tolist(), assign_in=[int(x) for x in assign],
+               pf=pf.tolist(), order=[int(x) for x in c.order], assign_out=[int(x) for x in c.assign],
+               As=c.As.tolist(), Bs=c.Bs.tolist(), candidate=[int(x) for x in cand["tree"]], threshold=float(thr),
+               kept=kept, cluster_prior=float(c.cluster_prior), maxlikelihood=float(c.maxlikelihood))
+    if extra:
+        out.update(extra)
+    print("search case", spec, "kept", len(kept), "%.1fs" % (time.time() - t0), flush=True)
+    return out
+
+
+def gen_search_big():
+    """(a) the reference's own sample input bamse.dat (80 mutations x 3 samples, coverage 10 000: the hard
+    dynamic-range case) at its KMeans-4 and KMeans-5 clusterings, through reorder -> get_candidate_tree ->
+    get_trees2 exactly as bamse.py:91-98 drives them; (b) one K = 5 simdata case (kept set at K = 5)."""
+    import pickle
+    import pandas as pd
+    from sklearn.cluster import KMeans
+    with open("/root/reference/AllTrees.txt", "rb") as f:
+        T, S = pickle.load(f, encoding="latin1")
+    out = []
+    tab = pd.read_table("/root/reference/bamse.dat")
+    names = ["S1", "S2", "S3"]
+    am = tab[[x + ".var" for x in names]].values
+    bm = tab[[x + ".ref" for x in names]].values
+    pf = cl.part_func(len(tab), 10)
+    Y = (am + 0.0) / (am + bm)
+    for K in (4, 5):
+        labels = KMeans(n_clusters=K, n_init=100, random_state=0).fit(Y).labels_
+        assign = tt.reorder_assignmens(labels)                       # bamse.py:23
+        out.append(_search_case(am, bm, assign, pf, 0.001, dict(source="bamse.dat", K=K, err=0.001)))
+    sp = dict(K=5, M=3, N=60, seed=2026, err=0.003, cov=200)
+    am, bm, assign, true_tree = simdata(sp["K"], sp["M"], sp["N"], sp["seed"], T, coverage=sp["cov"])
+    assign = tt.reorder_assignmens(assign)
+    out.append(_search_case(am, bm, assign, cl.part_func(sp["N"], 6), sp["err"], sp, dict(true_tree=true_tree)))
+    dump("search_big.json", out)
+
+
 def gen_outputs():
     """dot / text files written by the reference's own tree_io on a fixed tree dict.
     asciitree is absent here, so its LeftAligned drawer is supplied by our restatement
@@ -262,4 +351,8 @@ if __name__ == "__main__":
         gen_search()
     if "outputs" in which:
         gen_outputs()
+    if "highk" in which:          # round 2 additions: not in the default list (minutes of reference CPU time)
+        gen_scores_highk()
+    if "search_big" in which:
+        gen_search_big()
     print("done in %.1fs" % (time.time() - t0))

@@ -21,7 +21,7 @@ def header_functions():
     return sorted(set(re.findall(r"\b(bamse_[a-z0-9_]+)\s*\(", text)))
 
 
-def test_library_exports_every_declared_symbol():
+def test_library_exports_every_declared_symbol(built_library):
     lib = cuda_shim.load_library()
     declared = header_functions()
     assert len(declared) >= 14
@@ -37,7 +37,7 @@ def test_record_layout_matches_header():
 
 
 @pytest.mark.skipif(has_cuda(), reason="checks the no-GPU failure mode")
-def test_no_gpu_fails_loudly_no_cpu_fallback():
+def test_no_gpu_fails_loudly_no_cpu_fallback(built_library):
     with pytest.raises(cuda_shim.BamseCudaError) as e:
         cuda_shim.Context(0)
     assert e.value.code == -2 and "no CPU fallback" in str(e.value)
@@ -46,7 +46,7 @@ def test_no_gpu_fails_loudly_no_cpu_fallback():
         c.get_tree_score([-1, 0], [0, 1])
 
 
-def test_host_decoder_is_a_bijection():
+def test_host_decoder_is_a_bijection(built_library):
     import bamse_oracle as orc
     for K in range(1, 7):
         seen = set()

@@ -31,7 +31,6 @@ def _fake_scores(K_of_c, P):
 
 
 def _local_topk(K_of_c, P, rank, world, topk):
-    tb, te = multigpu.shard_ranges(K_of_c, rank, world)
     rec = np.zeros((P, topk), dtype=RECORD_DTYPE)
     rec["clust"] = -1
     for p in range(P):
@@ -39,7 +38,7 @@ def _local_topk(K_of_c, P, rank, world, topk):
         for (pp, c, t, s) in _fake_scores(K_of_c, P):
             if pp != p:
                 continue
-            sel = (t >= tb[c]) & (t < te[c])
+            sel = np.isin(t, multigpu.shard_indices(len(t), rank, world))
             for ti, si in zip(t[sel], s[sel]):
                 rows.append((si + c, si, c, p, ti))
         rows.sort(key=lambda r: (-r[0], r[2], r[4]))
@@ -61,16 +60,19 @@ def _worker(rank, world, port, K_of_c, P, topk, q):
         dist.destroy_process_group()
 
 
-def test_shard_ranges_partition_the_index_space():
-    Ks = [1, 2, 3, 5, 7, 10, 12]
+def test_interleaved_shards_partition_the_index_space():
+    """bamse_set_shard's scheme: rank r takes r, r + W, r + 2W, ...; the shards are disjoint, cover every
+    index once, and their sizes differ by at most one."""
+    Ks = [1, 2, 3, 5, 7]
     for world in (1, 2, 3, 4, 8):
-        cover = [0] * len(Ks)
-        for r in range(world):
-            b, e = multigpu.shard_ranges(Ks, r, world)
-            for c in range(len(Ks)):
-                assert int(b[c]) == cover[c] and int(e[c]) >= int(b[c])
-                cover[c] = int(e[c])
-        assert cover == [k ** (k - 1) for k in Ks]
+        for K in Ks:
+            T = K ** (K - 1)
+            parts = [multigpu.shard_indices(T, r, world) for r in range(world)]
+            assert [len(p) for p in parts] == [multigpu.shard_size(T, r, world) for r in range(world)]
+            allidx = np.concatenate(parts)
+            assert len(allidx) == T and len(np.unique(allidx)) == T
+            assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
+    assert multigpu.shard_size(12 ** 11, 7, 8) == (12 ** 11 - 7 + 7) // 8
 
 
 def test_merge_records_order_and_invalid_slots():

@@ -150,3 +150,39 @@ def test_search_path(golden_search):
         # the best tree overall is always among the reference-kept ones
         best = max(full, key=full.get)
         assert best in kept_ref
+
+
+def test_tree_scores_highk_match_reference():
+    """round 2: reference-produced scores at K = 8 ... 12 (tests/golden/tree_scores_highk.json)."""
+    from conftest import load_golden
+    cases = load_golden("tree_scores_highk.json")
+    assert len(cases) >= 30
+    for case in cases:
+        As = np.array(case["var"])
+        Bs = np.array(case["ref"])
+        K, M = As.shape
+        D = np.array([[orc.distrib(As[k, m], Bs[k, m], case["err"]) for m in range(M)] for k in range(K)])
+        s = orc.tree_score_samples(case["tree"], D[case["nodes"]], orc.prior_const(case["K_prior"]))
+        np.testing.assert_allclose(s, case["per_sample"], rtol=1e-12, atol=0, err_msg=case["id"])
+        assert orc.canon_weight(case["tree"])[1] == case["scre"]
+        assert orc.decode_tree(K, orc.encode_tree(case["tree"])) == case["tree"]
+
+
+def test_search_path_on_bamse_dat_and_k5():
+    """round 2: reorder / candidate / threshold / kept set on the reference's sample input bamse.dat
+    (KMeans-4 and KMeans-5 clusterings) and on a K = 5 simdata input (tests/golden/search_big.json)."""
+    from conftest import load_golden
+    for case in load_golden("search_big.json"):
+        o = orc.OracleClustering(case["am"], case["bm"], case["assign_in"], np.array(case["pf"]), case["spec"]["err"])
+        o.reorder()
+        assert [int(x) for x in o.order] == case["order"]
+        assert o.assign.tolist() == case["assign_out"]
+        np.testing.assert_array_equal(o.As, case["As"])
+        cand = o.get_candidate_tree()
+        assert cand == case["candidate"]
+        thr = o.threshold(cand)
+        assert thr == pytest.approx(case["threshold"], rel=1e-12)
+        for k in case["kept"]:
+            assert o.full_score(k["tree"]) == pytest.approx(k["score"] + math.log(k["scre"]), rel=1e-12)
+            assert o.full_score(k["tree"]) >= thr - 1e-9 * abs(thr)
+            assert o.total_score(k["tree"]) == pytest.approx(k["totalscore"], rel=1e-12)
