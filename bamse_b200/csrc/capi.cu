@@ -12,6 +12,7 @@
 #include "kernels.cuh"
 #include "score_fast.cuh"
 #include "tree_decode.cuh"
+#include "forest_host.h"
 
 using namespace bamse;
 
@@ -46,11 +47,18 @@ struct bamse_ctx {
     bool have_problem = false;
     int P = 0, C = 0, M = 0, Kmax = 0;
     std::vector<int32_t> K_of_c;
-    DBuf d_K, d_p0, d_var, d_ref, d_logc, d_logcf, d_log1mcf, d_D64, d_D32, d_D2, d_EL2, d_SEL2, d_SD2, d_HS2, d_PSE2, d_PEE2;
-    bool root_tables = false, pair_tables = false;
+    DBuf d_K, d_p0, d_var, d_ref, d_logc, d_logcf, d_log1mcf, d_D64, d_D32, d_D2, d_SD2;
+    // sub-forest tables (forest.cuh): message tables FG / FSG, finishing tables FH, per-(p, c) bases, shape LUT,
+    // per-K recipes; geometry (s, sh) per cluster count of the resident problem
+    DBuf d_FG, d_FSG, d_FH, d_tb, d_lut, d_recipe_ptrs;
+    struct Recipes { DBuf buf; int s = -1; };
+    Recipes recipes[KMAX + 1];
+    int geom_s[KMAX + 1] = {0}, geom_sh[KMAX + 1] = {0};
+    int slots_needed = 3;
+    double table_bytes = 0.0;
     // program tables (fp32 enumeration): one per K <= PROGTAB_KMAX present in the problem, kept across
-    // uploads while the key (tables present, Kmax of the pair index) is unchanged
-    struct ProgTab { DBuf buf; int root = -1, pair_kmax = -1; };
+    // uploads while the table geometry of that K is unchanged
+    struct ProgTab { DBuf buf; int s = -1, sh = -1; };
     ProgTab progtab[KMAX + 1];
     DBuf d_progtabs;         // [KMAX + 1] device pointers, NULL = decode in the kernel
     bool have_progtabs = false;
@@ -81,9 +89,10 @@ struct bamse_ctx {
     }
     FastTables fast() const {
         FastTables f;
-        f.D2 = d_D2.as<float>(); f.EL2 = d_EL2.as<float>(); f.SEL2 = d_SEL2.as<float>();
-        f.SD2 = root_tables ? d_SD2.as<float>() : nullptr; f.HS2 = root_tables ? d_HS2.as<float>() : nullptr;
-        f.PSE2 = pair_tables ? d_PSE2.as<float>() : nullptr; f.PEE2 = pair_tables ? d_PEE2.as<float>() : nullptr;
+        f.D2 = d_D2.as<float>(); f.SD2 = d_SD2.as<float>();
+        f.FG = d_FG.as<float>(); f.FSG = d_FSG.as<float>(); f.FH = d_FH.as<float>();
+        f.tb = d_tb.as<TableBase>(); f.lut = d_lut.as<int16_t>();
+        f.recipes = d_recipe_ptrs.as<const ForestRecipe*>();
         return f;
     }
     ProblemView view() const {
@@ -95,7 +104,7 @@ struct bamse_ctx {
     }
 };
 
-constexpr int PROGTAB_KMAX = 8;
+constexpr int PROGTAB_KMAX = 9;      // K = 9: 43 M programs, 2.75 GB
 constexpr int TOPK_INTERNAL = BAMSE_TOPK_INTERNAL;   // preselection lists may grow to this size (public topk <= BAMSE_TOPK_MAX)
 
 // A C++ exception (std::bad_alloc of a staging vector, in practice) must not cross the C ABI: the entry
@@ -171,11 +180,13 @@ void bamse_destroy(bamse_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     DBuf* bufs[] = {&ctx->d_K, &ctx->d_p0, &ctx->d_var, &ctx->d_ref, &ctx->d_logc, &ctx->d_logcf, &ctx->d_log1mcf,
-                    &ctx->d_D64, &ctx->d_D32, &ctx->d_D2, &ctx->d_EL2, &ctx->d_SEL2, &ctx->d_SD2, &ctx->d_HS2, &ctx->d_PSE2, &ctx->d_PEE2, &ctx->d_segs, &ctx->d_scalars, &ctx->d_cand, &ctx->d_items,
+                    &ctx->d_D64, &ctx->d_D32, &ctx->d_D2, &ctx->d_SD2, &ctx->d_FG, &ctx->d_FSG, &ctx->d_FH, &ctx->d_tb, &ctx->d_lut,
+                    &ctx->d_recipe_ptrs, &ctx->d_segs, &ctx->d_scalars, &ctx->d_cand, &ctx->d_items,
                     &ctx->d_scores, &ctx->d_const, &ctx->d_thr, &ctx->d_begin, &ctx->d_end, &ctx->d_records,
                     &ctx->d_dense0, &ctx->d_dense1, &ctx->d_split, &ctx->d_lists};
     for (DBuf* b : bufs) b->release();
     for (auto& t : ctx->progtab) t.buf.release();
+    for (auto& r : ctx->recipes) r.buf.release();
     ctx->d_progtabs.release();
     for (auto* v : {&ctx->ev_used, &ctx->ev_free})
         for (auto& ev : *v) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
@@ -257,6 +268,46 @@ int bamse_decode_tree(int K, uint64_t tree_index, int8_t* out_parent) {
     return BAMSE_OK;
 }
 
+// ---- introspection of the data-independent machinery (tests run these without a GPU) ----------------------
+int bamse_debug_forest_geometry(int K, int32_t* out_s, int32_t* out_sh, int32_t* out_nf, int32_t* out_nfh, int32_t* out_slots) {
+    if (K < 1 || K > KMAX) return BAMSE_EINVAL;
+    int s = 1, sh = 1;
+    if (out_s && *out_s > 0 && out_sh && *out_sh > 0) { s = *out_s; sh = *out_sh; }     // caller-given geometry
+    else default_forest_geometry(K, &s, &sh);
+    if (s > FT_SMAX || sh > s) return BAMSE_EINVAL;
+    const ForestIndex fi = make_forest_index(K, s, sh);
+    if (out_s) *out_s = s;
+    if (out_sh) *out_sh = sh;
+    if (out_nf) *out_nf = fi.nf;
+    if (out_nfh) *out_nfh = fi.nfh;
+    if (out_slots) *out_slots = forest_slots_needed(K, s);
+    return BAMSE_OK;
+}
+
+int bamse_debug_forest_recipes(int K, int s, int32_t* out /* [nf][5]: kind, u, a, b, mask */) try {
+    if (K < 1 || K > KMAX || s < 1 || s > FT_SMAX || !out) return BAMSE_EINVAL;
+    const std::vector<ForestRecipe> rec = make_forest_recipes(make_forest_index(K, s, 1));
+    for (size_t i = 0; i < rec.size(); ++i) {
+        out[5 * i] = rec[i].kind; out[5 * i + 1] = rec[i].u; out[5 * i + 2] = rec[i].a; out[5 * i + 3] = rec[i].b;
+        out[5 * i + 4] = rec[i].mask;
+    }
+    return BAMSE_OK;
+} catch (...) { return on_exception(nullptr, "bamse_debug_forest_recipes"); }
+
+int bamse_debug_program(int k, const int8_t* parent, const int8_t* nodes, int Kc, int s, int sh,
+                        int32_t* out /* [6 + 2 * 20]: n_ops, fin, fin_arg, fin_r, scre, max_sp, ops[20], args[20] */) try {
+    if (k < 1 || k > KMAX || Kc < k || Kc > KMAX || s < 1 || s > FT_SMAX || sh < 1 || sh > s || !parent || !out) return BAMSE_EINVAL;
+    FastProgram prog;
+    memset(&prog, 0, sizeof prog);
+    if (!build_program_forest(k, parent, nodes, make_forest_index(Kc, s, sh), forest_lut().lut.data(), &prog)) return BAMSE_EINVAL;
+    out[0] = prog.n_ops; out[1] = prog.fin; out[2] = prog.fin_arg; out[3] = prog.fin_r; out[4] = prog.scre; out[5] = prog.max_sp;
+    for (int i = 0; i < FAST_MAX_OPS; ++i) {
+        out[6 + i] = i < prog.n_ops ? fast_op(prog, i) : -1;
+        out[6 + FAST_MAX_OPS + i] = i < prog.n_ops ? prog.arg[i] : 0;
+    }
+    return BAMSE_OK;
+} catch (...) { return on_exception(nullptr, "bamse_debug_program"); }
+
 int bamse_upload_problem(bamse_ctx* ctx, int P, const double* err, int C, int M, int Kmax, const int32_t* K_of_c,
                          const int64_t* var_counts, const int64_t* ref_counts) try {
     CTX_CHECK(ctx);
@@ -310,22 +361,91 @@ int bamse_upload_problem(bamse_ctx* ctx, int P, const double* err, int C, int M,
     BAMSE_CUDA_TRY(ctx, ctx->d_D64.ensure(sizeof(double) * nrows * L));
     BAMSE_CUDA_TRY(ctx, ctx->d_D32.ensure(sizeof(float) * nrows * L));
     BAMSE_CUDA_TRY(ctx, ctx->d_D2.ensure(sizeof(float) * nrows * L));
-    BAMSE_CUDA_TRY(ctx, ctx->d_EL2.ensure(sizeof(float) * nrows * L));
-    BAMSE_CUDA_TRY(ctx, ctx->d_SEL2.ensure(sizeof(float) * nrows * L));
-    // root tables: K^2 rows per (p, c, m); skipped (generic root handling) if they would be huge
-    ctx->root_tables = (double)nrows * Kmax * L * sizeof(float) <= 16e9;
-    if (ctx->root_tables) {
-        BAMSE_CUDA_TRY(ctx, ctx->d_SD2.ensure(sizeof(float) * nrows * L));
-        BAMSE_CUDA_TRY(ctx, ctx->d_HS2.ensure(sizeof(float) * nrows * Kmax * L));
+    BAMSE_CUDA_TRY(ctx, ctx->d_SD2.ensure(sizeof(float) * nrows * L));
+    // ---- sub-forest tables: geometry per cluster count, stepped down until everything fits the budget
+    //      (BAMSE_TABLE_GB, default 60 % of the device memory); BAMSE_FOREST_S / BAMSE_FOREST_SH override
+    bool k_present[KMAX + 1] = {false};
+    for (int c = 0; c < C; ++c) k_present[K_of_c[c]] = true;
+    const char* env_s = getenv("BAMSE_FOREST_S");
+    const char* env_sh = getenv("BAMSE_FOREST_SH");
+    for (int K = 1; K <= KMAX; ++K) {
+        if (!k_present[K]) continue;
+        default_forest_geometry(K, &ctx->geom_s[K], &ctx->geom_sh[K]);
+        if (env_s) ctx->geom_s[K] = std::max(1, std::min({atoi(env_s), FT_SMAX, K >= 11 ? 3 : FT_SMAX}));
+        if (env_sh) ctx->geom_sh[K] = std::max(1, atoi(env_sh));
+        while (ctx->geom_s[K] > 1 && make_forest_index(K, ctx->geom_s[K], 1).nf > 65535) --ctx->geom_s[K];   // 16-bit row ids
+        ctx->geom_sh[K] = std::min(ctx->geom_sh[K], ctx->geom_s[K]);
     }
-    // leaf-pair tables: Kmax (Kmax - 1) / 2 rows per (p, c, m), two kinds
-    const size_t npair_rows = (nrows / Kmax) * (size_t)n_pairs(Kmax);
-    ctx->pair_tables = Kmax >= 3 && (double)npair_rows * 2 * L * sizeof(float) <= 16e9;
-    if (ctx->pair_tables) {
-        BAMSE_CUDA_TRY(ctx, ctx->d_PSE2.ensure(sizeof(float) * npair_rows * L));
-        BAMSE_CUDA_TRY(ctx, ctx->d_PEE2.ensure(sizeof(float) * npair_rows * L));
+    double budget = 0.0;
+    {
+        size_t free_b = 0, total_b = 0;
+        BAMSE_CUDA_TRY(ctx, cudaMemGetInfo(&free_b, &total_b));
+        budget = 0.6 * (double)total_b;
+        if (const char* g = getenv("BAMSE_TABLE_GB")) budget = atof(g) * 1e9;
     }
+    std::vector<TableBase> tbs((size_t)P * C);
+    size_t fg_rows = 0, fh_rows = 0;
+    for (;;) {
+        fg_rows = fh_rows = 0;
+        double per_k[KMAX + 1] = {0.0};
+        for (int p = 0; p < P; ++p)
+            for (int c = 0; c < C; ++c) {
+                const int K = K_of_c[c];
+                TableBase& t = tbs[(size_t)p * C + c];
+                t.fi = make_forest_index(K, ctx->geom_s[K], ctx->geom_sh[K]);
+                t.fg_row = (uint32_t)fg_rows; t.fh_row = (uint32_t)fh_rows;
+                const size_t a = (size_t)M * t.fi.nf, b = (size_t)M * K * t.fi.nfh;
+                fg_rows += a; fh_rows += b;
+                per_k[K] += (double)(2 * a + b) * L * sizeof(float);
+            }
+        const double bytes = (double)(2 * fg_rows + fh_rows) * L * sizeof(float);
+        ctx->table_bytes = bytes;
+        if ((bytes <= budget && fg_rows < 0xffffffffull && fh_rows < 0xffffffffull) || (env_s && env_sh)) break;
+        int worst = 0;                                 // step the geometry of the hungriest cluster count down
+        for (int K = 1; K <= KMAX; ++K) if (per_k[K] > per_k[worst]) worst = K;
+        if (!worst || !reduce_forest_geometry(&ctx->geom_s[worst], &ctx->geom_sh[worst])) {
+            bool any = false;
+            for (int K = 1; K <= KMAX && !any; ++K) if (k_present[K]) any = reduce_forest_geometry(&ctx->geom_s[K], &ctx->geom_sh[K]);
+            if (!any) return ctx->fail(BAMSE_ENOMEM, "bamse_upload_problem: the smallest sub-forest tables (%.1f GB) exceed the table budget (%.1f GB)", bytes / 1e9, budget / 1e9);
+        }
+    }
+    ctx->slots_needed = 2;
+    int smax = 1, max_level_rows[FT_SMAX + 2] = {0}, max_fh_items = 0;
+    for (int K = 1; K <= KMAX; ++K) {
+        if (!k_present[K]) continue;
+        const ForestIndex fi = make_forest_index(K, ctx->geom_s[K], ctx->geom_sh[K]);
+        ctx->slots_needed = std::max(ctx->slots_needed, forest_slots_needed(K, fi.s));
+        smax = std::max(smax, fi.s);
+        for (int n = 2; n <= fi.s; ++n) max_level_rows[n] = std::max(max_level_rows[n], fi.base[n + 1] - fi.base[n]);
+        max_fh_items = std::max(max_fh_items, K * fi.nfh);
+    }
+    BAMSE_CUDA_TRY(ctx, ctx->d_FG.ensure(sizeof(float) * fg_rows * L));
+    BAMSE_CUDA_TRY(ctx, ctx->d_FSG.ensure(sizeof(float) * fg_rows * L));
+    BAMSE_CUDA_TRY(ctx, ctx->d_FH.ensure(sizeof(float) * std::max<size_t>(fh_rows, 1) * L));
+    BAMSE_CUDA_TRY(ctx, ctx->d_tb.ensure(sizeof(TableBase) * tbs.size()));
     cudaStream_t s = ctx->stream;
+    BAMSE_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_tb.p, tbs.data(), sizeof(TableBase) * tbs.size(), cudaMemcpyHostToDevice, s));
+    if (!ctx->d_lut.p) {
+        BAMSE_CUDA_TRY(ctx, ctx->d_lut.ensure(sizeof(int16_t) * FT_LUT_SIZE));
+        BAMSE_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_lut.p, forest_lut().lut.data(), sizeof(int16_t) * FT_LUT_SIZE, cudaMemcpyHostToDevice, s));
+    }
+    {
+        const ForestRecipe* rptrs[KMAX + 1];
+        for (int K = 0; K <= KMAX; ++K) {
+            rptrs[K] = nullptr;
+            if (K == 0 || !k_present[K]) continue;
+            bamse_ctx::Recipes& r = ctx->recipes[K];
+            if (!r.buf.p || r.s != ctx->geom_s[K]) {
+                const std::vector<ForestRecipe> rec = make_forest_recipes(make_forest_index(K, ctx->geom_s[K], ctx->geom_sh[K]));
+                BAMSE_CUDA_TRY(ctx, r.buf.ensure(sizeof(ForestRecipe) * rec.size()));
+                BAMSE_CUDA_TRY(ctx, cudaMemcpy(r.buf.p, rec.data(), sizeof(ForestRecipe) * rec.size(), cudaMemcpyHostToDevice));
+                r.s = ctx->geom_s[K];
+            }
+            rptrs[K] = r.buf.as<ForestRecipe>();
+        }
+        BAMSE_CUDA_TRY(ctx, ctx->d_recipe_ptrs.ensure(sizeof rptrs));
+        BAMSE_CUDA_TRY(ctx, cudaMemcpy(ctx->d_recipe_ptrs.p, rptrs, sizeof rptrs, cudaMemcpyHostToDevice));
+    }
     BAMSE_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_K.p, K_of_c, sizeof(int32_t) * C, cudaMemcpyHostToDevice, s));
     BAMSE_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_p0.p, p0.data(), sizeof(double) * C, cudaMemcpyHostToDevice, s));
     BAMSE_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_var.p, var.data(), sizeof(double) * ncnt, cudaMemcpyHostToDevice, s));
@@ -338,22 +458,19 @@ int bamse_upload_problem(bamse_ctx* ctx, int P, const double* err, int C, int M,
     launch_tables(ctx->view(), ctx->d_var.as<double>(), ctx->d_ref.as<double>(), ctx->d_logc.as<double>(),
                   ctx->d_logcf.as<double>(), ctx->d_log1mcf.as<double>(), ctx->d_D64.as<double>(),
                   ctx->d_D32.as<float>(), s);
-    launch_tables_fast(ctx->view(), ctx->d_D2.as<float>(), ctx->d_EL2.as<float>(), ctx->d_SEL2.as<float>(),
-                       ctx->root_tables ? ctx->d_SD2.as<float>() : nullptr, s);
+    launch_tables_fast(ctx->view(), ctx->fast(), ctx->d_D2.as<float>(), ctx->d_FG.as<float>(), ctx->d_FSG.as<float>(),
+                       ctx->d_SD2.as<float>(), s);
     ctx->launches += 2;
-    if (ctx->root_tables) {
-        launch_tables_hs(ctx->view(), ctx->fast(), ctx->d_HS2.as<float>(), s);
+    for (int n = 2; n <= smax; ++n) {
+        launch_forest_level(ctx->view(), ctx->fast(), n, max_level_rows[n], ctx->d_FG.as<float>(), ctx->d_FSG.as<float>(), s);
         ctx->launches++;
     }
-    if (ctx->pair_tables) {
-        launch_tables_pairs(ctx->view(), ctx->fast(), ctx->d_PSE2.as<float>(), ctx->d_PEE2.as<float>(), s);
-        ctx->launches++;
-    }
-    {   // program tables for the small K of this problem (K^(K-1) rows of 64 bytes; K = 8: 134 MB)
+    launch_forest_fh(ctx->view(), ctx->fast(), max_fh_items, ctx->d_FH.as<float>(), s);
+    ctx->launches++;
+    {   // program tables for the small K of this problem (K^(K-1) rows of 64 bytes; K = 9: 2.75 GB)
         const char* off = getenv("BAMSE_PROGTAB");          // BAMSE_PROGTAB=0: always decode in the kernel
         const bool enable = !(off && atoi(off) == 0);
-        const int pair_kmax = ctx->pair_tables ? Kmax : 0;
-        const TreeProgram* ptrs[KMAX + 1];
+        const FastProgram* ptrs[KMAX + 1];
         for (int k = 0; k <= KMAX; ++k) ptrs[k] = nullptr;
         ctx->have_progtabs = false;
         for (int c = 0; c < C && enable; ++c) {
@@ -361,13 +478,14 @@ int bamse_upload_problem(bamse_ctx* ctx, int P, const double* err, int C, int M,
             if (K > PROGTAB_KMAX || ptrs[K]) continue;
             bamse_ctx::ProgTab& t = ctx->progtab[K];
             const uint64_t n = ipow_u64(K, K - 1);
-            if (!t.buf.p || t.root != (int)ctx->root_tables || t.pair_kmax != pair_kmax) {
-                BAMSE_CUDA_TRY(ctx, t.buf.ensure(sizeof(TreeProgram) * n));
-                launch_build_prog_table(K, n, ctx->root_tables, pair_kmax, t.buf.as<TreeProgram>(), s);
+            if (!t.buf.p || t.s != ctx->geom_s[K] || t.sh != ctx->geom_sh[K]) {
+                BAMSE_CUDA_TRY(ctx, t.buf.ensure(sizeof(FastProgram) * n));
+                launch_build_prog_table(make_forest_index(K, ctx->geom_s[K], ctx->geom_sh[K]), n, ctx->d_lut.as<int16_t>(),
+                                        t.buf.as<FastProgram>(), s);
                 ctx->launches++;
-                t.root = (int)ctx->root_tables; t.pair_kmax = pair_kmax;
+                t.s = ctx->geom_s[K]; t.sh = ctx->geom_sh[K];
             }
-            ptrs[K] = t.buf.as<TreeProgram>();
+            ptrs[K] = t.buf.as<FastProgram>();
             ctx->have_progtabs = true;
         }
         BAMSE_CUDA_TRY(ctx, ctx->d_progtabs.ensure(sizeof ptrs));
@@ -531,7 +649,7 @@ static int enumerate_dev(bamse_ctx* ctx, const double* d_const, const double* d_
     }
     const int pi = precision == BAMSE_FP64 ? 1 : (precision == BAMSE_FP32 ? 0 : 2);
     const bool framed = precision == BAMSE_FP32 && ctx->use_framed == 1;
-    if (precision == BAMSE_FP32) ctx->grid[pi] = enumerate_fast_grid_size(ctx->device, topk, framed, ctx->Kmax);
+    if (precision == BAMSE_FP32) ctx->grid[pi] = enumerate_fast_grid_size(ctx->device, topk, framed, ctx->slots_needed);
     else if (ctx->grid[pi] == 0) ctx->grid[pi] = enumerate_grid_size(precision, ctx->device);
     const int grid = ctx->grid[pi];
     // work granularity: ~32 chunks per worker (warp for fp32, CTA for the check mode), 1..16 trees
@@ -586,7 +704,7 @@ static int enumerate_dev(bamse_ctx* ctx, const double* d_const, const double* d_
         BAMSE_CUDA_TRY(ctx, ctx->d_lists.ensure(sizeof(bamse_record) * (size_t)workers * (size_t)(topk > 0 ? topk : 1)));
         w.lists = ctx->d_lists.as<bamse_record>();
     }
-    w.prog_tabs = (precision == BAMSE_FP32 && ctx->have_progtabs) ? ctx->d_progtabs.as<const TreeProgram*>() : nullptr;
+    w.prog_tabs = (precision == BAMSE_FP32 && ctx->have_progtabs) ? ctx->d_progtabs.as<const FastProgram*>() : nullptr;
     w.early_exit = (ctx->early_exit && !host_seg && !ctx->probing && topk > 0) ? 1 : 0;
     // tail splitting: when a worker gets fewer than ~48 single-tree chunks, issue the last `workers`
     // trees in 2 (or, below 16 chunks per worker, 4) parts over the samples
@@ -609,7 +727,7 @@ static int enumerate_dev(bamse_ctx* ctx, const double* d_const, const double* d_
         BAMSE_CUDA_TRY(ctx, cudaEventCreate(&ev.second));
     }
     BAMSE_CUDA_TRY(ctx, cudaEventRecord(ev.first, s));
-    if (precision == BAMSE_FP32) launch_enumerate_fast(ctx->view(), ctx->fast(), w, grid, framed, s);
+    if (precision == BAMSE_FP32) launch_enumerate_fast(ctx->view(), ctx->fast(), w, grid, framed, ctx->slots_needed, s);
     else launch_enumerate(precision, ctx->view(), w, grid, s);
     BAMSE_CUDA_TRY(ctx, cudaEventRecord(ev.second, s));
     ctx->ev_used.push_back(ev);

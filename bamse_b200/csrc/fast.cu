@@ -7,15 +7,22 @@
 namespace bamse {
 
 // ---------------------------------------------------------------- fast tables (fp64 -> fp32 log2)
-// one CTA (256 threads) per table row: EL = logcumsum(D) + p0 - log L, SEL = logcumsum(EL) + p0 - log L
-// computed in fp64 natural logs, stored as fp32 base-2 logs.
-__global__ void __launch_bounds__(LD_THREADS) k_tables_fast(ProblemView pv, float* __restrict__ D2,
-                                                            float* __restrict__ EL2, float* __restrict__ SEL2,
+// one CTA (256 threads) per (p, c, m, k): EL = logcumsum(D) + p0 - log L and SEL = logcumsum(EL) + p0 - log L
+// computed in fp64 natural logs, stored as fp32 base-2 logs in rows k of the FG / FSG blocks (single-node
+// forests), plus D2 and the root table SD2 in the [P][C][M][Kmax] layout.
+__global__ void __launch_bounds__(LD_THREADS) k_tables_fast(ProblemView pv, FastTables ft, float* __restrict__ D2,
+                                                            float* __restrict__ FG, float* __restrict__ FSG,
                                                             float* __restrict__ SD2) {
     __shared__ double v[L];
     __shared__ double scratch[LD_THREADS / 32];
     const int row = blockIdx.x;
+    const int k = row % pv.Kmax;
+    const int m = (row / pv.Kmax) % pv.M;
     const int c = (row / (pv.Kmax * pv.M)) % pv.C;
+    const int p = row / (pv.Kmax * pv.M * pv.C);
+    if (k >= pv.K_of_c[c]) return;
+    const TableBase tb = ft.tb[p * pv.C + c];
+    const size_t frow = (size_t)tb.fg_row + (size_t)m * tb.fi.nf + k;
     const int t = threadIdx.x;
     const double log2e = 1.4426950408889634074;
     const double add = pv.p0[c] - 6.2383246250395077847550890931236;
@@ -25,53 +32,51 @@ __global__ void __launch_bounds__(LD_THREADS) k_tables_fast(ProblemView pv, floa
     D2[(size_t)row * L + t + LD_THREADS] = (float)(v[t + LD_THREADS] * log2e);
     __syncthreads();
     block_logcumsum<double>(v, add, scratch);
-    EL2[(size_t)row * L + t] = (float)(v[t] * log2e);
-    EL2[(size_t)row * L + t + LD_THREADS] = (float)(v[t + LD_THREADS] * log2e);
+    FG[frow * L + t] = (float)(v[t] * log2e);
+    FG[frow * L + t + LD_THREADS] = (float)(v[t + LD_THREADS] * log2e);
     __syncthreads();
     block_logcumsum<double>(v, add, scratch);
-    SEL2[(size_t)row * L + t] = (float)(v[t] * log2e);
-    SEL2[(size_t)row * L + t + LD_THREADS] = (float)(v[t + LD_THREADS] * log2e);
-    if (SD2) {
-        // suffix sums of d: the prefix scan of the reversed table; SD = e^p0 / L^2 * sum_{x>=i} d[x]
-        __syncthreads();
-        v[t] = src[L - 1 - t]; v[t + LD_THREADS] = src[L - 1 - t - LD_THREADS];
-        __syncthreads();
-        block_logcumsum<double>(v, add - 6.2383246250395077847550890931236, scratch);
-        SD2[(size_t)row * L + (L - 1 - t)] = (float)(v[t] * log2e);
-        SD2[(size_t)row * L + (L - 1 - t - LD_THREADS)] = (float)(v[t + LD_THREADS] * log2e);
-    }
+    FSG[frow * L + t] = (float)(v[t] * log2e);
+    FSG[frow * L + t + LD_THREADS] = (float)(v[t + LD_THREADS] * log2e);
+    // suffix sums of d: the prefix scan of the reversed table; SD = e^p0 / L^2 * sum_{x>=i} d[x]
+    __syncthreads();
+    v[t] = src[L - 1 - t]; v[t + LD_THREADS] = src[L - 1 - t - LD_THREADS];
+    __syncthreads();
+    block_logcumsum<double>(v, add - 6.2383246250395077847550890931236, scratch);
+    SD2[(size_t)row * L + (L - 1 - t)] = (float)(v[t] * log2e);
+    SD2[(size_t)row * L + (L - 1 - t - LD_THREADS)] = (float)(v[t + LD_THREADS] * log2e);
 }
 
-void launch_tables_fast(const ProblemView& pv, float* D2, float* EL2, float* SEL2, float* SD2, cudaStream_t s) {
+void launch_tables_fast(const ProblemView& pv, const FastTables& ft, float* D2, float* FG, float* FSG, float* SD2,
+                        cudaStream_t s) {
     const int rows = pv.P * pv.C * pv.M * pv.Kmax;
-    k_tables_fast<<<rows, LD_THREADS, 0, s>>>(pv, D2, EL2, SEL2, SD2);
+    k_tables_fast<<<rows, LD_THREADS, 0, s>>>(pv, ft, D2, FG, FSG, SD2);
 }
 
-// Index -> program: executed by one lane once per tree.  Kept out of line so that its (large, fully
-// unrolled) code does not sit between the hot loops in the instruction cache.
-static __device__ __noinline__ void build_tree_program(int K, uint64_t tree, TreeProgram* prog, bool root_tables,
-                                                       int pair_kmax) {
+// Index -> program: executed by one lane once per tree.  Kept out of line so that its (large) code does not
+// sit between the hot loops in the instruction cache.
+static __device__ __noinline__ void build_tree_program(int K, uint64_t tree, FastProgram* prog, const ForestIndex* fi,
+                                                       const int16_t* lut) {
     int8_t parent[KMAX];
     decode_tree(K, tree, parent);
-    build_program_fast(K, parent, nullptr, prog, root_tables, pair_kmax);
+    build_program_forest(K, parent, nullptr, *fi, lut, prog);
 }
 
-// Program tables.  The program of a tree depends on (K, tree index) and on which tables exist, not on
+// Program tables.  The program of a tree depends on (K, tree index) and on the table geometry (s, sh), not on
 // the data, so for small K all K^(K-1) programs are built once, one THREAD per tree, and the
-// enumeration warps fetch 64 bytes instead of running the (serial, one-lane) decoder per tree.
-static_assert(sizeof(TreeProgram) == 64, "program table rows are fetched as 16 words");
-__global__ void __launch_bounds__(128) k_build_prog_table(int K, uint64_t n_trees, bool root_tables, int pair_kmax,
-                                                          TreeProgram* __restrict__ out) {
+// enumeration warps fetch 64 bytes instead of running the (serial, one-lane) builder per tree.
+__global__ void __launch_bounds__(128) k_build_prog_table(ForestIndex fi, uint64_t n_trees, const int16_t* __restrict__ lut,
+                                                          FastProgram* __restrict__ out) {
     const uint64_t tree = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (tree >= n_trees) return;
-    TreeProgram prog;
+    FastProgram prog;
     memset(&prog, 0, sizeof prog);
-    build_tree_program(K, tree, &prog, root_tables, pair_kmax);
+    build_tree_program(fi.K, tree, &prog, &fi, lut);
     out[tree] = prog;
 }
 
-void launch_build_prog_table(int K, uint64_t n_trees, bool root_tables, int pair_kmax, TreeProgram* out, cudaStream_t s) {
-    k_build_prog_table<<<(unsigned)((n_trees + 127) / 128), 128, 0, s>>>(K, n_trees, root_tables, pair_kmax, out);
+void launch_build_prog_table(const ForestIndex& fi, uint64_t n_trees, const int16_t* d_lut, FastProgram* out, cudaStream_t s) {
+    k_build_prog_table<<<(unsigned)((n_trees + 127) / 128), 128, 0, s>>>(fi, n_trees, d_lut, out);
 }
 
 // ------------------------------------------------------------------ per-warp evaluation
@@ -81,7 +86,7 @@ struct alignas(16) WarpSmemT {
     uint16_t jstar[L];
     float fa[FRAMED ? FR_A : 4];      // framed-path scratch: 2^(a - frame) of the current segment
     float fb[FRAMED ? FR_SEG : 4];    // framed-path scratch: 2^(b - frame)
-    TreeProgram prog;
+    FastProgram prog;
 };
 using WarpSmem = WarpSmemT<false>;
 // dynamic shared memory: FAST_WARPS x WarpSmem
@@ -116,23 +121,22 @@ __device__ inline double warp_eval_tree(const ProblemView& pv, const FastTables&
                                         int m_step = 1) {
     const float add2 = (float)((pv.p0[c] - 6.2383246250395077847550890931236) * 1.4426950408889634074);
     const int n_ops = ws->prog.n_ops;
+    const TableBase* tb = ft.tb + (p * pv.C + c);
+    const uint32_t fg_row = tb->fg_row, fh_row = tb->fh_row;
+    const int nf = tb->fi.nf, nfh = tb->fi.nfh, Kc = tb->fi.K;
     double total = 0.0;
     unsigned done = 0;
     for (int m = m_begin; m < pv.M; m += m_step) {
         const size_t base = pv.table_offset(p, c, m);
+        const size_t frow = (size_t)fg_row + (size_t)m * nf;
         ++done;
         int sp = 0;                                  // stack position == slot (convolution is in place)
         for (int i = 0; i < n_ops; ++i) {
-            const int op = ws->prog.op[i];
+            const int op = fast_op(ws->prog, i);
             const int arg = ws->prog.arg[i];
-            if (op == FOP_PUSH_EL || op == FOP_PUSH_SEL) {
+            if (op == FOP_PUSH_G || op == FOP_PUSH_SG) {
                 float* dst = ws->vec[sp] + GUARD;
-                warp_load_vec(dst, (op == FOP_PUSH_EL ? ft.EL2 : ft.SEL2) + base + (size_t)arg * L, lane);
-                ++sp;
-            } else if (op == FOP_PUSH_PSE || op == FOP_PUSH_PEE) {
-                float* dst = ws->vec[sp] + GUARD;
-                const size_t row = (((size_t)p * pv.C + c) * pv.M + m) * n_pairs(pv.Kmax) + (size_t)arg;
-                warp_load_vec(dst, (op == FOP_PUSH_PSE ? ft.PSE2 : ft.PEE2) + row * L, lane);
+                warp_load_vec(dst, (op == FOP_PUSH_G ? ft.FG : ft.FSG) + (frow + (size_t)arg) * L, lane);
                 ++sp;
             } else if (op == FOP_SCAN) {
                 warp_log2cumsum(ws->vec[sp - 1] + GUARD, add2, lane);
@@ -145,11 +149,12 @@ __device__ inline double warp_eval_tree(const ProblemView& pv, const FastTables&
                 warp_add_table(ws->vec[sp - 1] + GUARD, ft.D2 + base + (size_t)arg * L, lane);
             }
         }
-        const int fin = ws->prog.pad;
+        const int fin = ws->prog.fin;
         const float* tab = nullptr;                  // FIN_LSE: plain log-sum-exp
         if (fin == FIN_DOT_D) tab = ft.D2 + base + (size_t)ws->prog.fin_r * L;
         else if (fin == FIN_DOT_SD) tab = ft.SD2 + base + (size_t)ws->prog.fin_r * L;
-        else if (fin == FIN_DOT_HS) tab = ft.HS2 + base * pv.Kmax + ((size_t)ws->prog.fin_r * pv.Kmax + ws->prog.fin_c) * L;
+        else if (fin == FIN_DOT_FH)
+            tab = ft.FH + ((size_t)fh_row + ((size_t)m * Kc + ws->prog.fin_r) * nfh + ws->prog.fin_arg) * L;
         float res2 = warp_log2dot(ws->vec[0] + GUARD, tab, lane);
         if (fin == FIN_LSE || fin == FIN_DOT_D) res2 -= LOG2_L;
         total += (double)res2 * 0.69314718055994530942;
@@ -162,61 +167,67 @@ __device__ inline double warp_eval_tree(const ProblemView& pv, const FastTables&
     return total;
 }
 
-// HS[r][c][i] = 1/L^2 * sum_j d_r[i+j] * sel_c[j]: the correlation of D[r] with the scanned leaf
-// message of c is the convolution of the REVERSED (still log-concave) D[r] with it, read backwards.
-// One warp per (p, c, m, r, c') with the production convolution.
-__global__ void __launch_bounds__(FAST_THREADS) k_tables_hs(ProblemView pv, FastTables ft, float* __restrict__ HS2) {
+// Message tables, one level (= forests with n nodes) per launch: row <- rows with fewer nodes by its recipe.
+// grid = (ceil(max rows of the level / FAST_WARPS), P * C * M); one warp per row, production convolution.
+__global__ void __launch_bounds__(FAST_THREADS) k_forest_level(ProblemView pv, FastTables ft, int n, float* __restrict__ FG,
+                                                               float* __restrict__ FSG) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int wid = threadIdx.x >> 5;
     int lane = threadIdx.x & 31;
     WarpSmem* ws = pin_shared(reinterpret_cast<WarpSmem*>(smem_raw) + wid);
-    const int64_t idx = (int64_t)blockIdx.x * FAST_WARPS + wid;     // ((pcm * Kmax) + r) * Kmax + c
-    const int Kmax = pv.Kmax;
-    const int64_t n = (int64_t)pv.P * pv.C * pv.M * Kmax * Kmax;
-    if (idx >= n) return;
-    const int cc = (int)(idx % Kmax), r = (int)((idx / Kmax) % Kmax);
-    const int64_t pcm = idx / ((int64_t)Kmax * Kmax);
-    const int c = (int)((pcm / pv.M) % pv.C);
-    if (r == cc || r >= pv.K_of_c[c] || cc >= pv.K_of_c[c]) return;
+    const int pcm = blockIdx.y;
+    const int m = pcm % pv.M, pc = pcm / pv.M, c = pc % pv.C;
+    const TableBase* tb = ft.tb + pc;
+    if (n > tb->fi.s) return;
+    const int i = blockIdx.x * FAST_WARPS + wid;
+    if (i >= tb->fi.base[n + 1] - tb->fi.base[n]) return;
+    const int row = tb->fi.base[n] + i;
+    const ForestRecipe rec = ft.recipes[tb->fi.K][row];
+    const size_t frow = (size_t)tb->fg_row + (size_t)m * tb->fi.nf;
+    const float add2 = (float)((pv.p0[c] - 6.2383246250395077847550890931236) * 1.4426950408889634074);
     warp_init_guards(ws, lane);
     float* a = ws->vec[0] + GUARD;
-    float* b = ws->vec[1] + GUARD;
-    const float* D = ft.D2 + ((size_t)pcm * Kmax + r) * L;
-    for (int t = 0; t < 16; ++t) a[lane + 32 * t] = __ldg(D + (L - 1 - lane - 32 * t));
-    warp_load_vec(b, ft.SEL2 + ((size_t)pcm * Kmax + cc) * L, lane);
-    warp_logconv<false>(a, b, ws->jstar, ws->fa, ws->fb, lane);
-    float* out = HS2 + (size_t)idx * L;
-    for (int t = 0; t < 16; ++t) out[lane + 32 * t] = a[L - 1 - lane - 32 * t] - LOG2_L;
+    if (rec.kind == 1) {                            // one tree: E = D[u] + SG(children forest)
+        warp_load_vec(a, FSG + (frow + rec.b) * L, lane);
+        warp_add_table(a, ft.D2 + pv.table_offset(pc / pv.C, c, m) + (size_t)rec.u * L, lane);
+    } else {                                        // several trees: the first one (*) the rest
+        float* b = ws->vec[1] + GUARD;
+        warp_load_vec(a, FG + (frow + rec.a) * L, lane);
+        warp_load_vec(b, FG + (frow + rec.b) * L, lane);
+        warp_logconv<false>(a, b, ws->jstar, ws->fa, ws->fb, lane);
+    }
+    float4* og = reinterpret_cast<float4*>(FG + (frow + row) * L);
+    for (int t = 0; t < 4; ++t) og[lane + 32 * t] = reinterpret_cast<const float4*>(a)[lane + 32 * t];
+    warp_log2cumsum(a, add2, lane);
+    float4* os = reinterpret_cast<float4*>(FSG + (frow + row) * L);
+    for (int t = 0; t < 4; ++t) os[lane + 32 * t] = reinterpret_cast<const float4*>(a)[lane + 32 * t];
 }
 
-// Leaf-pair tables: PSE[c1,c2] = SEL[c1] (*) EL[c2], PEE[c1,c2] = EL[c1] (*) EL[c2] (both symmetric in
-// the pair), one warp per (p, c, m, pair, kind) with the production convolution.
-__global__ void __launch_bounds__(FAST_THREADS) k_tables_pairs(ProblemView pv, FastTables ft, float* __restrict__ PSE2,
-                                                               float* __restrict__ PEE2) {
+// Finishing tables FH[r][F][i] = 1/L^2 * sum_j d_r[i+j] * sg_F[j]: the correlation of D[r] with the scanned
+// message of F is the convolution of the REVERSED (still log-concave) D[r] with it, read backwards.
+// grid = (ceil(max K * nfh / FAST_WARPS), P * C * M); one warp per (root, forest) with the production convolution.
+__global__ void __launch_bounds__(FAST_THREADS) k_forest_fh(ProblemView pv, FastTables ft, float* __restrict__ FH) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int wid = threadIdx.x >> 5;
     int lane = threadIdx.x & 31;
     WarpSmem* ws = pin_shared(reinterpret_cast<WarpSmem*>(smem_raw) + wid);
-    const int Kmax = pv.Kmax, NP = n_pairs(Kmax);
-    const int64_t idx = (int64_t)blockIdx.x * FAST_WARPS + wid;     // (pcm * NP + pair) * 2 + kind
-    const int64_t n = (int64_t)pv.P * pv.C * pv.M * NP * 2;
-    if (idx >= n) return;
-    const int kind = (int)(idx & 1);
-    const int pair = (int)((idx >> 1) % NP);
-    const int64_t pcm = (idx >> 1) / NP;
-    const int c = (int)((pcm / pv.M) % pv.C);
-    int c1 = 0, rem = pair;                                         // invert the triangular index
-    while (rem >= Kmax - 1 - c1) { rem -= Kmax - 1 - c1; ++c1; }
-    const int c2 = c1 + 1 + rem;
-    if (c2 >= pv.K_of_c[c]) return;
+    const int pcm = blockIdx.y;
+    const int m = pcm % pv.M, pc = pcm / pv.M, c = pc % pv.C;
+    const TableBase* tb = ft.tb + pc;
+    const int K = tb->fi.K, nfh = tb->fi.nfh;
+    const int i = blockIdx.x * FAST_WARPS + wid;
+    if (i >= K * nfh) return;
+    const int r = i / nfh, f = i - r * nfh;
+    if ((ft.recipes[K][f].mask >> r) & 1) return;   // the root is not part of its own children
     warp_init_guards(ws, lane);
     float* a = ws->vec[0] + GUARD;
     float* b = ws->vec[1] + GUARD;
-    warp_load_vec(a, (kind == 0 ? ft.SEL2 : ft.EL2) + ((size_t)pcm * Kmax + c1) * L, lane);
-    warp_load_vec(b, ft.EL2 + ((size_t)pcm * Kmax + c2) * L, lane);
+    const float* D = ft.D2 + pv.table_offset(pc / pv.C, c, m) + (size_t)r * L;
+    for (int t = 0; t < 16; ++t) a[lane + 32 * t] = __ldg(D + (L - 1 - lane - 32 * t));
+    warp_load_vec(b, ft.FSG + ((size_t)tb->fg_row + (size_t)m * tb->fi.nf + f) * L, lane);
     warp_logconv<false>(a, b, ws->jstar, ws->fa, ws->fb, lane);
-    float* out = (kind == 0 ? PSE2 : PEE2) + ((size_t)pcm * NP + pair) * L;
-    for (int t = 0; t < 16; ++t) out[lane + 32 * t] = a[lane + 32 * t];
+    float* out = FH + ((size_t)tb->fh_row + ((size_t)m * K + r) * nfh + f) * L;
+    for (int t = 0; t < 16; ++t) out[lane + 32 * t] = a[L - 1 - lane - 32 * t] - LOG2_L;
 }
 
 // a record written by another warp of the CTA (global memory, read after the barrier): bypass L1
@@ -303,16 +314,17 @@ k_enumerate_fast(ProblemView pv, FastTables ft, EnumWork w) {
         const uint64_t off = (chunk - seg.first_chunk) * (uint64_t)w.chunk;
         const uint64_t remain = seg.n_trees - off;
         const int n = remain < (uint64_t)w.chunk ? (int)remain : w.chunk;
-        const TreeProgram* tab = w.prog_tabs ? w.prog_tabs[seg.K] : nullptr;
+        const FastProgram* tab = w.prog_tabs ? w.prog_tabs[seg.K] : nullptr;
         for (int i = 0; i < n; ++i) {
             const uint64_t tree = seg.tree_begin + (off + i) * (uint64_t)seg.stride;
             if (tab) {
                 if (lane < 16)
                     reinterpret_cast<uint32_t*>(&ws->prog)[lane] = __ldg(reinterpret_cast<const uint32_t*>(tab + tree) + lane);
             } else if (lane == 0) {
-                build_tree_program(seg.K, tree, &ws->prog, ft.HS2 != nullptr, ft.PSE2 ? pv.Kmax : 0);
+                build_tree_program(seg.K, tree, &ws->prog, &ft.tb[seg.p * pv.C + seg.c].fi, ft.lut);
             }
             __syncwarp();
+            if (ws->prog.max_sp > SLOTS) asm volatile("trap;");     // a program this instantiation cannot hold: fail loudly
             double cut = -CUDART_INF;
             if (w.early_exit) {
                 // lane 0 knows the warp's k-th best and this tree's log scre; fp32 slack of 1e-3 nats
@@ -405,30 +417,33 @@ static size_t fast_smem_bytes(int topk, bool framed = false, int slots = FAST_SL
     return per_warp * FAST_WARPS;
 }
 
-void launch_tables_hs(const ProblemView& pv, const FastTables& ft, float* HS2, cudaStream_t s) {
-    const int64_t n = (int64_t)pv.P * pv.C * pv.M * pv.Kmax * pv.Kmax;
+void launch_forest_level(const ProblemView& pv, const FastTables& ft, int n, int max_rows, float* FG, float* FSG,
+                         cudaStream_t s) {
+    if (max_rows <= 0) return;
     const size_t smem = sizeof(WarpSmem) * FAST_WARPS;
-    cudaFuncSetAttribute(k_tables_hs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k_tables_hs<<<(unsigned)((n + FAST_WARPS - 1) / FAST_WARPS), FAST_THREADS, smem, s>>>(pv, ft, HS2);
+    cudaFuncSetAttribute(k_forest_level, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const dim3 grid((unsigned)((max_rows + FAST_WARPS - 1) / FAST_WARPS), (unsigned)(pv.P * pv.C * pv.M));
+    k_forest_level<<<grid, FAST_THREADS, smem, s>>>(pv, ft, n, FG, FSG);
 }
 
-void launch_tables_pairs(const ProblemView& pv, const FastTables& ft, float* PSE2, float* PEE2, cudaStream_t s) {
-    const int64_t n = (int64_t)pv.P * pv.C * pv.M * n_pairs(pv.Kmax) * 2;
-    if (n <= 0) return;
+void launch_forest_fh(const ProblemView& pv, const FastTables& ft, int max_items, float* FH, cudaStream_t s) {
+    if (max_items <= 0) return;
     const size_t smem = sizeof(WarpSmem) * FAST_WARPS;
-    cudaFuncSetAttribute(k_tables_pairs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k_tables_pairs<<<(unsigned)((n + FAST_WARPS - 1) / FAST_WARPS), FAST_THREADS, smem, s>>>(pv, ft, PSE2, PEE2);
+    cudaFuncSetAttribute(k_forest_fh, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const dim3 grid((unsigned)((max_items + FAST_WARPS - 1) / FAST_WARPS), (unsigned)(pv.P * pv.C * pv.M));
+    k_forest_fh<<<grid, FAST_THREADS, smem, s>>>(pv, ft, FH);
 }
 
 int enumerate_workers(int precision, int grid) { return precision == BAMSE_FP32 ? grid * FAST_WARPS : grid; }
 
-// Kmax <= 6 needs two vector slots only -> 10 CTAs (40 warps) per SM instead of 7
-static int fast_slots(int Kmax, bool framed) { return (!framed && Kmax <= 6) ? 2 : 3; }
+// two vector slots suffice when the tables fold every small subtree (forest_slots_needed) -> 10 CTAs (40 warps)
+// per SM instead of 7; the framed instantiation always carries three
+static int fast_slots(int slots_needed, bool framed) { return (!framed && slots_needed <= 2) ? 2 : 3; }
 
-int enumerate_fast_grid_size(int device, int topk, bool framed, int Kmax) {
+int enumerate_fast_grid_size(int device, int topk, bool framed, int slots_needed) {
     int sms = 148, per_sm = 1;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-    const int slots = fast_slots(Kmax, framed);
+    const int slots = fast_slots(slots_needed, framed);
     const size_t smax = fast_smem_bytes(BAMSE_TOPK_MAX, framed, slots), sm = fast_smem_bytes(topk, framed, slots);
     if (framed) {
         cudaFuncSetAttribute(k_enumerate_fast<true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smax);
@@ -445,8 +460,8 @@ int enumerate_fast_grid_size(int device, int topk, bool framed, int Kmax) {
 }
 
 void launch_enumerate_fast(const ProblemView& pv, const FastTables& ft, const EnumWork& w, int grid, bool framed,
-                           cudaStream_t s) {
-    const int slots = fast_slots(pv.Kmax, framed);
+                           int slots_needed, cudaStream_t s) {
+    const int slots = fast_slots(slots_needed, framed);
     const size_t sm = fast_smem_bytes(w.topk, framed, slots);
     if (framed) k_enumerate_fast<true, 3><<<grid, FAST_THREADS, sm, s>>>(pv, ft, w);
     else if (slots == 2) k_enumerate_fast<false, 2><<<grid, FAST_THREADS, sm, s>>>(pv, ft, w);
@@ -466,7 +481,7 @@ __global__ void __launch_bounds__(FAST_THREADS) k_score_items_fast(ProblemView p
     warp_init_guards(ws, lane);
     const ScoreItem it = items[idx];
     int ok = 1;
-    if (lane == 0) ok = build_program_fast(it.k, it.parent, it.nodes, &ws->prog, ft.HS2 != nullptr, ft.PSE2 ? pv.Kmax : 0) ? 1 : 0;
+    if (lane == 0) ok = build_program_forest(it.k, it.parent, it.nodes, ft.tb[it.p * pv.C + it.c].fi, ft.lut, &ws->prog) ? 1 : 0;
     ok = __shfl_sync(0xffffffffu, ok, 0);
     if (!ok) { if (lane == 0) out[idx] = CUDART_NAN; return; }
     unsigned s0 = 0, s1 = 0, s2 = 0;

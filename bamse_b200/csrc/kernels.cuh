@@ -1,6 +1,7 @@
 // Kernel declarations shared between the kernel translation units and the C ABI.
 #pragma once
 #include "common.cuh"
+#include "forest.cuh"
 
 namespace bamse {
 
@@ -51,7 +52,7 @@ struct EnumWork {
     int* split_cnt;              // [n_split] finished parts (zeroed before launch)
     // fp32 kernel: per-K tables of ready-made evaluation programs, indexed by tree index (device array of
     // KMAX + 1 device pointers, entry NULL = decode in the kernel); NULL = no tables at all
-    const TreeProgram* const* prog_tabs;
+    const FastProgram* const* prog_tabs;
     // fp32 kernel: the workers' private top-k lists, [workers][max(topk, 1)] records in global memory
     // (touched once per tree by one lane; keeping them out of shared memory buys a resident CTA per SM)
     bamse_record* lists;
@@ -75,14 +76,18 @@ void launch_merge_topk(const bamse_record* d_bag, const unsigned long long* d_co
 int enumerate_workers(int precision, int grid);
 
 struct FastTables;
-void launch_tables_fast(const ProblemView& pv, float* D2, float* EL2, float* SEL2, float* SD2, cudaStream_t s);
-void launch_tables_hs(const ProblemView& pv, const FastTables& ft, float* HS2, cudaStream_t s);
-void launch_tables_pairs(const ProblemView& pv, const FastTables& ft, float* PSE2, float* PEE2, cudaStream_t s);
-int enumerate_fast_grid_size(int device, int topk, bool framed, int Kmax);
-// out[i] = evaluation program of tree index i of a K-node clustering, i < n_trees = K^(K-1)
-void launch_build_prog_table(int K, uint64_t n_trees, bool root_tables, int pair_kmax, TreeProgram* out, cudaStream_t s);
+void launch_tables_fast(const ProblemView& pv, const FastTables& ft, float* D2, float* FG, float* FSG, float* SD2,
+                        cudaStream_t s);
+// level n of the message tables (max_rows = the largest number of n-node forests of any clustering present)
+void launch_forest_level(const ProblemView& pv, const FastTables& ft, int n, int max_rows, float* FG, float* FSG,
+                         cudaStream_t s);
+// finishing tables (max_items = the largest K * nfh of any clustering present)
+void launch_forest_fh(const ProblemView& pv, const FastTables& ft, int max_items, float* FH, cudaStream_t s);
+int enumerate_fast_grid_size(int device, int topk, bool framed, int slots_needed);
+// out[i] = evaluation program of tree index i of a fi.K-node clustering, i < n_trees = K^(K-1)
+void launch_build_prog_table(const ForestIndex& fi, uint64_t n_trees, const int16_t* d_lut, FastProgram* out, cudaStream_t s);
 void launch_enumerate_fast(const ProblemView& pv, const FastTables& ft, const EnumWork& w, int grid, bool framed,
-                           cudaStream_t s);
+                           int slots_needed, cudaStream_t s);
 void launch_score_items_fast(const ProblemView& pv, const FastTables& ft, const ScoreItem* d_items, int64_t n,
                              double* d_out, cudaStream_t s);
 

@@ -16,6 +16,7 @@
 #pragma once
 #include "common.cuh"
 #include "tree_decode.cuh"
+#include "forest.cuh"
 
 namespace bamse {
 
@@ -38,159 +39,24 @@ constexpr int FR_A = FR_SEG + FR_B;                 // a-window floats of one se
 constexpr float FR_DEV = 50.0f;                     // allowed deviation of M_x from linear inside a block (bits)
 constexpr float FR_MAXR = 30.0f;                    // a factor above 2^FR_MAXR of the centre aborts the frame
 
+// Per (parameter set, clustering): where its sub-forest tables start and how they are indexed (forest.cuh).
+struct TableBase {
+    uint32_t fg_row;     // first row of FG / FSG of (p, c, m = 0); sample m starts fi.nf * m rows later
+    uint32_t fh_row;     // first row of FH of (p, c, m = 0, root 0); (m, r) starts (m * K + r) * fi.nfh rows later
+    ForestIndex fi;
+};
+
 struct FastTables {
-    const float* D2;     // [rows][L] log2 of the binomial tables                (clustering.py:20-24)
-    const float* EL2;    // [rows][L] leaf message  log2cumsum(D) + p0 - log L   (clustering.py:377)
-    const float* SEL2;   // [rows][L] scanned leaf message (a leaf used as the scan factor)
-    // root tables (may be NULL): only the scalar sum_x d_r[x] G[x] is needed at the root, so the
-    // last operation there is a dot product of the folded children message Q with
-    const float* SD2;    // [rows][L]       SD[r][i]    = e^p0 / L^2 * sum_{x>=i} d_r[x]              (no leaf child)
-    const float* HS2;    // [rows][Kmax][L] HS[r][c][i] = 1 / L^2 * sum_j d_r[i+j] * sel_c[j]         (leaf child c)
-    // leaf-pair tables (may be NULL): two leaf siblings fold into one table, indexed by the
-    // triangular pair index of (c1 < c2) among Kmax nodes
-    const float* PSE2;   // [pcm][NP][L]  SEL[c1] (*) EL[c2]   (the pair carries the scan factor)
-    const float* PEE2;   // [pcm][NP][L]  EL[c1]  (*) EL[c2]
+    const float* D2;     // [P][C][M][Kmax][L] log2 of the binomial tables               (clustering.py:20-24)
+    const float* SD2;    // same layout: SD[r][i] = e^p0 / L^2 * sum_{x>=i} d_r[x]       (root without finishing forest)
+    const float* FG;     // message tables, rows of L: G(F) of every forest F with <= s nodes; rows 0..K-1 of a
+                         // block are the leaf messages  log2cumsum(D) + p0 - log L       (clustering.py:377)
+    const float* FSG;    // scanned messages SG(F) = log2cumsum(G(F)) + p0 - log L
+    const float* FH;     // finishing tables FH[r][F][i] = 1 / L^2 * sum_j d_r[i+j] * sg_F[j], forests with <= sh nodes
+    const TableBase* tb; // [P * C]
+    const int16_t* lut;  // forest shape LUT (FT_LUT_SIZE entries)
+    const ForestRecipe* const* recipes;   // [KMAX + 1] device arrays, by cluster count
 };
-
-__host__ __device__ inline int pair_index(int c1, int c2, int Kmax) {      // c1 != c2, both < Kmax
-    const int lo = c1 < c2 ? c1 : c2, hi = c1 < c2 ? c2 : c1;
-    return lo * (2 * Kmax - lo - 1) / 2 + (hi - lo - 1);
-}
-__host__ __device__ inline int n_pairs(int Kmax) { return Kmax * (Kmax - 1) / 2; }
-
-// evaluation program of the fast path (convolution is commutative/associative, so the
-// factor that carries the prefix sum may be any child; a leaf child is preferred because
-// its scanned message is a table)
-enum : int8_t {
-    FOP_PUSH_EL = 0,    // push EL2[arg]
-    FOP_PUSH_SEL = 1,   // push SEL2[arg]
-    FOP_SCAN = 2,       // top = log2cumsum(top) + p0 - log L
-    FOP_CONV = 3,       // b = pop; top = top (*) b   (in place)
-    FOP_ADDD = 4,       // top += D2[arg]
-    FOP_PUSH_PSE = 5,   // push PSE2[arg]   (arg = triangular pair index)
-    FOP_PUSH_PEE = 6,   // push PEE2[arg]
-};
-// how the per-sample scalar is produced from the vector left on the stack (TreeProgram::pad;
-// the root node id is TreeProgram::fin_r, the leaf child of FIN_HS is TreeProgram::fin_c)
-enum : int8_t {
-    FIN_LSE = 0,        // log2sumexp(top) - log2 L                 (trap_int(...)[-1], clustering.py:385)
-    FIN_DOT_D = 1,      // log2 sum 2^(top + D2[r]) - log2 L        root with one (leaf) child
-    FIN_DOT_SD = 2,     // log2 sum 2^(top + SD2[r])                root without leaf children
-    FIN_DOT_HS = 3,     // log2 sum 2^(top + HS2[r][c])             root with leaf child c, top = the other children
-};
-
-// Builds the fast program + canonizeF weight.  Same validity rules as build_program.
-__host__ __device__ inline bool build_program_fast(int k, const int8_t* parent, const int8_t* nodes,
-                                                   TreeProgram* prog, bool root_tables = false,
-                                                   int pair_kmax = 0 /* > 0: leaf-pair tables exist */) {
-    // canon weight / validation through the reference-order builder
-    if (!build_program(k, parent, nodes, prog)) return false;
-    const int32_t scre = prog->scre;
-    const int n_leaves = prog->n_leaves;
-    int root = 0;
-    int8_t nchild[KMAX], size[KMAX], order[KMAX];
-    _Pragma("unroll 1") for (int v = 0; v < k; ++v) { nchild[v] = 0; size[v] = 1; if (parent[v] == -1) root = v; }
-    _Pragma("unroll 1") for (int v = 0; v < k; ++v) if (parent[v] >= 0) nchild[parent[v]]++;
-    // subtree sizes: process nodes in decreasing depth order (depth via parent walks)
-    int8_t depth[KMAX];
-    _Pragma("unroll 1") for (int v = 0; v < k; ++v) { int d = 0, w = v; _Pragma("unroll 1") while (parent[w] >= 0) { w = parent[w]; ++d; } depth[v] = (int8_t)d; order[v] = (int8_t)v; }
-    _Pragma("unroll 1") for (int i = 1; i < k; ++i) { int8_t o = order[i]; int j = i; _Pragma("unroll 1") while (j > 0 && depth[order[j - 1]] < depth[o]) { order[j] = order[j - 1]; --j; } order[j] = o; }
-    _Pragma("unroll 1") for (int i = 0; i < k; ++i) { const int v = order[i]; if (parent[v] >= 0) size[parent[v]] += size[v]; }
-
-    // iterative emission.  frame: node, phase; children lists are recomputed by scanning.
-    int8_t st_node[KMAX], st_stage[KMAX], st_done[KMAX];
-    uint16_t st_used[KMAX];              // internal children already evaluated (bit mask)
-    int n_ops = 0, sp = 0;
-    int8_t fin = FIN_LSE, fin_r = 0, fin_c = 0;
-    auto emit = [&](int8_t op, int8_t arg) { prog->op[n_ops] = op; prog->arg[n_ops] = arg; ++n_ops; };
-    if (nchild[root] == 0) { emit(FOP_PUSH_EL, nodes ? nodes[root] : (int8_t)root); }
-    else { st_node[0] = (int8_t)root; st_stage[0] = 0; st_done[0] = 0; st_used[0] = 0; sp = 1; }
-    _Pragma("unroll 1") while (sp > 0) {
-        const int f = sp - 1, v = st_node[f];
-        if (st_stage[f] == 0) {
-            // next unevaluated internal child with the largest subtree
-            int best = -1;
-            _Pragma("unroll 1") for (int c = 0; c < k; ++c)
-                if (parent[c] == v && nchild[c] > 0 && !((st_used[f] >> c) & 1) && (best < 0 || size[c] > size[best])) best = c;
-            if (best >= 0) {
-                st_used[f] |= (uint16_t)(1u << best);
-                st_stage[f] = 1;                     // after the child returns: fold it
-                st_node[sp] = (int8_t)best; st_stage[sp] = 0; st_done[sp] = 0; st_used[sp] = 0; ++sp;
-                continue;
-            }
-            if (root_tables && f == 0) {
-                // the root: its first leaf child (if any) is folded in by the HS table, the scan and
-                // D[root] by the SD / HS / D tables -- one convolution and one scan fewer
-                int cstar = -1, held = -1;                    // held: a leaf waiting for a partner
-                _Pragma("unroll 1") for (int c = 0; c < k; ++c)
-                    if (parent[c] == v && nchild[c] == 0) {
-                        if (cstar < 0) { cstar = c; continue; }
-                        if (pair_kmax > 0 && held < 0) { held = c; continue; }
-                        if (n_ops + 2 > MAX_OPS) return false;
-                        if (held >= 0) {
-                            emit(FOP_PUSH_PEE, (int8_t)pair_index(nodes ? nodes[held] : held, nodes ? nodes[c] : c, pair_kmax));
-                            held = -1;
-                        } else emit(FOP_PUSH_EL, nodes ? nodes[c] : (int8_t)c);
-                        if (st_done[f] > 0) emit(FOP_CONV, 0);
-                        st_done[f]++;
-                    }
-                if (held >= 0) {
-                    if (n_ops + 2 > MAX_OPS) return false;
-                    emit(FOP_PUSH_EL, nodes ? nodes[held] : (int8_t)held);
-                    if (st_done[f] > 0) emit(FOP_CONV, 0);
-                    st_done[f]++;
-                }
-                fin_r = nodes ? nodes[v] : (int8_t)v;
-                if (cstar < 0) fin = FIN_DOT_SD;
-                else if (st_done[f] == 0) {
-                    if (n_ops + 1 > MAX_OPS) return false;
-                    emit(FOP_PUSH_SEL, nodes ? nodes[cstar] : (int8_t)cstar);
-                    fin = FIN_DOT_D;
-                } else { fin = FIN_DOT_HS; fin_c = nodes ? nodes[cstar] : (int8_t)cstar; }
-                --sp;
-                continue;
-            }
-            // internal children done: leaves (in pairs when the pair tables exist; the first
-            // leaf / pair carries the scan factor)
-            bool first_leaf = true;
-            int held = -1;
-            _Pragma("unroll 1") for (int c = 0; c < k; ++c)
-                if (parent[c] == v && nchild[c] == 0) {
-                    if (pair_kmax > 0 && held < 0) { held = c; continue; }
-                    if (n_ops + 2 > MAX_OPS) return false;
-                    if (held >= 0) {
-                        emit(first_leaf ? FOP_PUSH_PSE : FOP_PUSH_PEE,
-                             (int8_t)pair_index(nodes ? nodes[held] : held, nodes ? nodes[c] : c, pair_kmax));
-                        held = -1;
-                    } else if (first_leaf) emit(FOP_PUSH_SEL, nodes ? nodes[c] : (int8_t)c);
-                    else emit(FOP_PUSH_EL, nodes ? nodes[c] : (int8_t)c);
-                    first_leaf = false;
-                    if (st_done[f] > 0) emit(FOP_CONV, 0);
-                    st_done[f]++;
-                }
-            if (held >= 0) {
-                if (n_ops + 2 > MAX_OPS) return false;
-                emit(first_leaf ? FOP_PUSH_SEL : FOP_PUSH_EL, nodes ? nodes[held] : (int8_t)held);
-                first_leaf = false;
-                if (st_done[f] > 0) emit(FOP_CONV, 0);
-                st_done[f]++;
-            }
-            if (n_ops + 2 > MAX_OPS) return false;
-            if (first_leaf) emit(FOP_SCAN, 0);       // no leaf child: the accumulated product carries the scan
-            emit(FOP_ADDD, nodes ? nodes[v] : (int8_t)v);
-            --sp;
-        } else {
-            // an internal child's message is on the stack
-            if (n_ops + 1 > MAX_OPS) return false;
-            if (st_done[f] > 0) emit(FOP_CONV, 0);
-            st_done[f]++;
-            st_stage[f] = 0;
-        }
-    }
-    prog->n_ops = (int8_t)n_ops; prog->k = (int8_t)k; prog->n_leaves = (int8_t)n_leaves; prog->scre = scre;
-    prog->pad = fin; prog->fin_r = fin_r; prog->fin_c = fin_c;
-    return true;
-}
 
 // ----------------------------------------------------------------------------- warp ops
 __device__ __forceinline__ float ex2f(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }

@@ -121,7 +121,7 @@ template <> struct TableSel<float> { static __device__ const float* get(const Pr
 template <typename T>
 __device__ double eval_tree_logdomain(const ProblemView& pv, int p, int c, const TreeProgram* prog,
                                       T* pool /* [MAX_STACK][L] */, T* scratch /* [LD_THREADS/32] */,
-                                      int m_begin = 0, int m_end = -1, double cut = -CUDART_INF,
+                                      int m_begin = 0, int m_end = -1, double cut = -HUGE_VAL,
                                       unsigned* n_done = nullptr) {
     const int t = threadIdx.x;
     const T log_len = (T)6.2383246250395077847550890931236;  // log(512)

@@ -88,6 +88,12 @@ def load_library():
     lib.bamse_kernel_time.argtypes = [c_p, i32, ctypes.POINTER(dbl), ctypes.POINTER(i64)]
     lib.bamse_kernel_stats.restype = i32
     lib.bamse_kernel_stats.argtypes = [c_p, i32, c_p]
+    lib.bamse_debug_forest_geometry.restype = i32
+    lib.bamse_debug_forest_geometry.argtypes = [i32, c_p, c_p, c_p, c_p, c_p]
+    lib.bamse_debug_forest_recipes.restype = i32
+    lib.bamse_debug_forest_recipes.argtypes = [i32, i32, c_p]
+    lib.bamse_debug_program.restype = i32
+    lib.bamse_debug_program.argtypes = [i32, c_p, c_p, i32, i32, i32, c_p]
     if lib.bamse_abi_version() != 1:
         raise RuntimeError("libbamse_cuda ABI version mismatch")
     _lib = lib
@@ -99,6 +105,7 @@ EXPORTED_SYMBOLS = [
     "bamse_launch_count", "bamse_last_eval_count", "bamse_last_topk_verified", "bamse_last_topk_preselected", "bamse_decode_tree", "bamse_upload_problem",
     "bamse_score_list", "bamse_score_range", "bamse_score_topk", "bamse_enumerate_topk_dev",
     "bamse_merge_topk_dev", "bamse_kernel_time", "bamse_kernel_stats",
+    "bamse_debug_forest_geometry", "bamse_debug_forest_recipes", "bamse_debug_program",
 ]
 
 

@@ -183,6 +183,19 @@ int bamse_kernel_time(bamse_ctx* ctx, int reset, double* out_ms, int64_t* out_la
  *          convolutions, prefix scans }.  For the pipe-utilisation side of the roofline. */
 int bamse_kernel_stats(bamse_ctx* ctx, int reset, uint64_t* out4);
 
+/* ---------------------------------------------------------- introspection (no GPU needed)
+ * The fp32 path memoises sub-forest messages in tables and drives each tree by a small program
+ * (bamse_b200/csrc/forest.cuh).  Both are data independent; these entry points run the HOST instances of
+ * the code the kernels run, so tests can interpret them with the CPU oracle.
+ * bamse_debug_forest_geometry: *s / *sh > 0 on entry = use that geometry, else the default of K is returned;
+ *   out_nf / out_nfh = table rows per (parameter set, clustering, sample) / per root; out_slots = live vectors.
+ * bamse_debug_forest_recipes: out [nf][5] = {kind, root label, row a, row b, node mask} of every table row.
+ * bamse_debug_program: the program of a tree (k nodes, parent vector, optional cluster ids) in a clustering
+ *   of Kc clusters: out = {n_ops, fin, fin_arg, fin_r, scre, max_sp, op[20], arg[20]}. */
+int bamse_debug_forest_geometry(int K, int32_t* s, int32_t* sh, int32_t* out_nf, int32_t* out_nfh, int32_t* out_slots);
+int bamse_debug_forest_recipes(int K, int s, int32_t* out);
+int bamse_debug_program(int k, const int8_t* parent, const int8_t* nodes, int Kc, int s, int sh, int32_t* out);
+
 /* Host helper shared with the oracle's definition: index -> parent vector. */
 int bamse_decode_tree(int K, uint64_t tree_index, int8_t* out_parent /* [K] */);
 
