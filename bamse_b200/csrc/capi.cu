@@ -13,6 +13,7 @@
 #include "score_fast.cuh"
 #include "tree_decode.cuh"
 #include "forest_host.h"
+#include "pairs_host.h"
 
 using namespace bamse;
 
@@ -273,7 +274,7 @@ int bamse_debug_forest_geometry(int K, int32_t* out_s, int32_t* out_sh, int32_t*
     if (K < 1 || K > KMAX) return BAMSE_EINVAL;
     int s = 1, sh = 1;
     if (out_s && *out_s > 0 && out_sh && *out_sh > 0) { s = *out_s; sh = *out_sh; }     // caller-given geometry
-    else default_forest_geometry(K, &s, &sh);
+    else { default_forest_geometry(K, &s, &sh); s = program_forest_s(K, s); if (sh > s) sh = s; }   // what the programs see
     if (s > FT_SMAX || sh > s) return BAMSE_EINVAL;
     const ForestIndex fi = make_forest_index(K, s, sh);
     if (out_s) *out_s = s;
@@ -307,6 +308,32 @@ int bamse_debug_program(int k, const int8_t* parent, const int8_t* nodes, int Kc
     }
     return BAMSE_OK;
 } catch (...) { return on_exception(nullptr, "bamse_debug_program"); }
+
+int bamse_debug_pair_geometry(int K, int32_t* s, int32_t* r, int32_t* out_nf, int32_t* out_nt) {
+    if (K < 1 || K > KMAX || !s || !r) return BAMSE_EINVAL;
+    if (*s <= 0 || *r < 0) { int sh = 1, rr = 0, ss = 1; default_forest_geometry(K, &ss, &sh, &rr); *s = ss; *r = rr; }
+    if (*s > FT_SMAX || *r > PR_RMAX || (*r > 0 && *r - 1 > *s)) return BAMSE_EINVAL;
+    if (out_nf) *out_nf = make_forest_index(K, *s, 1).nf;
+    if (out_nt) *out_nt = (int32_t)make_pair_geom(K, *s, *r).nt;
+    return BAMSE_OK;
+}
+
+int bamse_debug_ctx_recipes(int K, int s, int r, int32_t* out /* [nt][3]: parent context row, FG row of H, marked label */) try {
+    if (K < 1 || K > KMAX || s < 1 || s > FT_SMAX || r < 1 || r > PR_RMAX || r - 1 > s || !out) return BAMSE_EINVAL;
+    const std::vector<CtxRecipe> rec = make_ctx_recipes(make_forest_index(K, s, 1), make_pair_geom(K, s, r));
+    for (size_t i = 0; i < rec.size(); ++i) { out[3 * i] = rec[i].parent_row; out[3 * i + 1] = rec[i].h_row; out[3 * i + 2] = rec[i].v; }
+    return BAMSE_OK;
+} catch (...) { return on_exception(nullptr, "bamse_debug_ctx_recipes"); }
+
+int bamse_debug_classify(int K, const int8_t* parent, int s, int r, int32_t* out /* regular, FG row, context row */) try {
+    if (K < 1 || K > KMAX || s < 1 || s > FT_SMAX || r < 0 || r > PR_RMAX || !parent || !out) return BAMSE_EINVAL;
+    TreeProgram ref;
+    if (!build_program(K, parent, nullptr, &ref)) return BAMSE_EINVAL;
+    uint32_t fg = 0, t = 0;
+    const bool reg = r > 0 && classify_tree(K, parent, make_forest_index(K, s, 1), forest_lut().lut.data(), make_pair_geom(K, s, r), &fg, &t);
+    out[0] = reg ? 1 : 0; out[1] = (int32_t)fg; out[2] = (int32_t)t;
+    return BAMSE_OK;
+} catch (...) { return on_exception(nullptr, "bamse_debug_classify"); }
 
 int bamse_upload_problem(bamse_ctx* ctx, int P, const double* err, int C, int M, int Kmax, const int32_t* K_of_c,
                          const int64_t* var_counts, const int64_t* ref_counts) try {

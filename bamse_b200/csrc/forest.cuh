@@ -28,9 +28,11 @@ constexpr int FT_LUT_SIZE = 8476;          // sum_{n=1..5} (n+1)^n codes
 #ifdef __CUDA_ARCH__
 #define BAMSE_POPC(x) __popc((unsigned)(x))
 #define BAMSE_CTZ(x) (__ffs((int)(x)) - 1)
+#define BAMSE_CLZ(x) __clz((int)(x))
 #else
 #define BAMSE_POPC(x) __builtin_popcount((unsigned)(x))
 #define BAMSE_CTZ(x) __builtin_ctz((unsigned)(x))
+#define BAMSE_CLZ(x) __builtin_clz((unsigned)(x))
 #endif
 
 __host__ __device__ inline int forest_count(int n) {          // (n+1)^(n-1)

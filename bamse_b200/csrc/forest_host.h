@@ -85,16 +85,31 @@ inline std::vector<ForestRecipe> make_forest_recipes(const ForestIndex& fi) {
     return out;
 }
 
-// Default table geometry per cluster count (convolutions per tree and table bytes per
-// (p, c, m) for every (s, sh)); reduce_forest_geometry() steps a choice down when the tables do not fit.
-inline void default_forest_geometry(int K, int* s, int* sh) {
-    if (K <= 2) { *s = 1; *sh = 1; }
-    else if (K <= 5) { *s = K - 2 < 3 ? K - 2 : 3; *sh = *s < 2 ? *s : 2; }
-    else if (K == 6) { *s = 4; *sh = 2; }
-    else if (K <= 10) { *s = 4; *sh = 3; }
-    else { *s = 3; *sh = 2; }                         // K = 11, 12: row ids must stay below 65 536
-    if (*s < 1) *s = 1;
-    if (*sh < 1) *sh = 1;
+// Default table geometry per cluster count: inside tables for forests of <= s nodes, finishing tables of the
+// table-driven programs for forests of <= sh nodes, context tables (pairs.cuh) for contexts of <= r nodes
+// (r = 0: no pair path).  Chosen by counting rows against the trees they serve (brute force over all trees
+// for K <= 8, 30 000 random trees above): regular trees = 100 % up to K = 7, 97.9 % at
+// K = 8, 98.1 % at K = 9, 87.9 % at K = 10.  K >= 11 needs s + r >= 11 (tens of GB per sample): programs only.
+inline void default_forest_geometry(int K, int* s, int* sh, int* r = nullptr) {
+    int rr = 0;
+    if (K <= 1) { *s = 1; *sh = 1; }
+    else if (K == 2) { *s = 1; *sh = 1; rr = 1; }
+    else if (K == 3) { *s = 2; *sh = 1; rr = 1; }
+    else if (K == 4) { *s = 2; *sh = 2; rr = 2; }
+    else if (K == 5) { *s = 3; *sh = 2; rr = 3; }
+    else if (K == 6) { *s = 4; *sh = 2; rr = 3; }
+    else if (K == 7) { *s = 4; *sh = 3; rr = 4; }
+    else if (K == 8) { *s = 5; *sh = 3; rr = 4; }
+    else if (K <= 10) { *s = 5; *sh = 3; rr = 5; }
+    else { *s = 3; *sh = 2; }                         // K = 11, 12
+    if (r) *r = rr;
+}
+
+// The table-driven programs address rows with 16 bits: they see the inside tables up to s_prog <= s nodes (the
+// rows of the smaller forests are a prefix of the table, so both geometries share one table).
+inline int program_forest_s(int K, int s) {
+    while (s > 1 && make_forest_index(K, s, 1).nf > 65535) --s;
+    return s;
 }
 
 inline bool reduce_forest_geometry(int* s, int* sh) {

@@ -94,6 +94,12 @@ def load_library():
     lib.bamse_debug_forest_recipes.argtypes = [i32, i32, c_p]
     lib.bamse_debug_program.restype = i32
     lib.bamse_debug_program.argtypes = [i32, c_p, c_p, i32, i32, i32, c_p]
+    lib.bamse_debug_pair_geometry.restype = i32
+    lib.bamse_debug_pair_geometry.argtypes = [i32, c_p, c_p, c_p, c_p]
+    lib.bamse_debug_ctx_recipes.restype = i32
+    lib.bamse_debug_ctx_recipes.argtypes = [i32, i32, i32, c_p]
+    lib.bamse_debug_classify.restype = i32
+    lib.bamse_debug_classify.argtypes = [i32, c_p, i32, i32, c_p]
     if lib.bamse_abi_version() != 1:
         raise RuntimeError("libbamse_cuda ABI version mismatch")
     _lib = lib
@@ -106,6 +112,7 @@ EXPORTED_SYMBOLS = [
     "bamse_score_list", "bamse_score_range", "bamse_score_topk", "bamse_enumerate_topk_dev",
     "bamse_merge_topk_dev", "bamse_kernel_time", "bamse_kernel_stats",
     "bamse_debug_forest_geometry", "bamse_debug_forest_recipes", "bamse_debug_program",
+    "bamse_debug_pair_geometry", "bamse_debug_ctx_recipes", "bamse_debug_classify",
 ]
 
 

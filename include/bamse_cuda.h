@@ -195,6 +195,16 @@ int bamse_kernel_stats(bamse_ctx* ctx, int reset, uint64_t* out4);
 int bamse_debug_forest_geometry(int K, int32_t* s, int32_t* sh, int32_t* out_nf, int32_t* out_nfh, int32_t* out_slots);
 int bamse_debug_forest_recipes(int K, int s, int32_t* out);
 int bamse_debug_program(int k, const int8_t* parent, const int8_t* nodes, int Kc, int s, int sh, int32_t* out);
+/* Inside x outside pairs (bamse_b200/csrc/pairs.cuh): a tree whose best cut leaves a pack of <= s nodes and a
+ * context of <= r nodes is scored by one dot product of an inside-table row with a context-table row.
+ * bamse_debug_pair_geometry: *s <= 0 on entry = the default (s, r) of K is returned; out_nf / out_nt = inside /
+ *   context rows per (parameter set, clustering, sample).
+ * bamse_debug_ctx_recipes: out [nt][3] = {context row of the marked node's parent (-1: the marked node is the
+ *   root), inside row of the marked node's children forest within the context (-1: none), marked label}.
+ * bamse_debug_classify: the cut of a full tree on K labels: out = {regular (0 / 1), inside row, context row}. */
+int bamse_debug_pair_geometry(int K, int32_t* s, int32_t* r, int32_t* out_nf, int32_t* out_nt);
+int bamse_debug_ctx_recipes(int K, int s, int r, int32_t* out);
+int bamse_debug_classify(int K, const int8_t* parent, int s, int r, int32_t* out);
 
 /* Host helper shared with the oracle's definition: index -> parent vector. */
 int bamse_decode_tree(int K, uint64_t tree_index, int8_t* out_parent /* [K] */);

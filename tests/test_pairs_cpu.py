@@ -1,0 +1,119 @@
+"""CPU tests of the inside x outside factorisation (bamse_b200/csrc/pairs.cuh): context recipes and the cut of
+every tree come out of libbamse_cuda's HOST instances of the code the kernels run (bamse_debug_* entry points,
+no GPU needed); the tables are built here in fp64 with the numpy oracle's operators, and the dot product of the
+two rows a tree is cut into must reproduce the oracle's tree score."""
+import ctypes
+import math
+
+import numpy as np
+import pytest
+from scipy.special import logsumexp
+
+import bamse_oracle as orc
+from bamse_b200 import cuda_shim
+from test_forest_cpu import Tables, _tables, recipes
+
+LOGL = math.log(512)
+
+
+def pair_geometry(lib, K, s=0, r=-1):
+    a, b, nf, nt = ctypes.c_int32(s), ctypes.c_int32(r), ctypes.c_int32(), ctypes.c_int32()
+    assert lib.bamse_debug_pair_geometry(K, ctypes.byref(a), ctypes.byref(b), ctypes.byref(nf), ctypes.byref(nt)) == 0
+    return a.value, b.value, nf.value, nt.value
+
+
+def ctx_recipes(lib, K, s, r, nt):
+    out = np.zeros((nt, 3), dtype=np.int32)
+    assert lib.bamse_debug_ctx_recipes(K, s, r, out.ctypes.data_as(ctypes.c_void_p)) == 0
+    return out
+
+
+def classify(lib, tree, s, r):
+    par = np.asarray(tree, dtype=np.int8)
+    out = np.zeros(3, dtype=np.int32)
+    assert lib.bamse_debug_classify(len(tree), par.ctypes.data_as(ctypes.c_void_p), s, r, out.ctypes.data_as(ctypes.c_void_p)) == 0
+    return bool(out[0]), int(out[1]), int(out[2])
+
+
+class Contexts(object):
+    """numpy build of the context rows T for one sample, following the recipes (rows with fewer nodes first:
+    a recipe's parent row always has a smaller index base, so evaluate lazily with memoisation)."""
+
+    def __init__(self, D, p0, FG, rec):
+        self.D, self.p0, self.FG, self.rec = D, p0, FG, rec
+        self.rows = {}
+
+    def row(self, i):
+        if i in self.rows:
+            return self.rows[i]
+        par, h, v = (int(x) for x in self.rec[i])
+        L = self.D.shape[1]
+        o = np.full(L, -LOGL) if par < 0 else self.row(par)          # outside message at the marked node
+        a = np.logaddexp.accumulate((o + self.D[v])[::-1])[::-1]     # A[y] = sum_{x >= y} O[x] d[x]
+        if h < 0:
+            t = a + self.p0 - LOGL
+        else:
+            g = self.FG[h]
+            t = np.array([logsumexp(g[:L - z] + a[z:]) for z in range(L)]) + self.p0 - 2 * LOGL
+        self.rows[i] = t
+        return t
+
+
+@pytest.mark.parametrize("K,s,r", [(2, 1, 1), (3, 2, 1), (4, 2, 2), (5, 3, 3), (5, 3, 2), (6, 4, 3), (6, 3, 3), (7, 4, 4), (8, 4, 4)])
+def test_pairs_reproduce_the_oracle(built_library, K, s, r):
+    """all trees for K <= 5, a stratified sample above: log sum 2^(FG[pack] + T[context]) == oracle score."""
+    lib = cuda_shim.load_library()
+    s, r, nf, nt = pair_geometry(lib, K, s, r)
+    rec = recipes(lib, K, s, nf)
+    crec = ctx_recipes(lib, K, s, r, nt)
+    assert (crec[:, 0] < np.arange(nt)).all()            # a parent context always sits in an earlier row
+    assert (crec[:, 1] < nf).all()
+    D = _tables(K, 7 * K + s)
+    p0 = orc.prior_const(K)
+    tab = Tables(D, p0, rec, 0)
+    ctxs = Contexts(D, p0, tab.FG, crec)
+    T = K ** (K - 1)
+    idx = range(T) if T <= 700 else list(range(0, T, max(1, T // 200))) + [T - 1]
+    n_reg = 0
+    for i in idx:
+        tree = orc.decode_tree(K, i)
+        reg, fg, t = classify(lib, tree, s, r)
+        if not reg:
+            continue
+        n_reg += 1
+        assert 0 <= fg < nf and 0 <= t < nt
+        want = orc.tree_score_samples(tree, D[:, None, :], p0)[0]
+        got = logsumexp(tab.FG[fg] + ctxs.row(t))
+        assert got == pytest.approx(want, rel=1e-9), (K, s, r, i, tree, fg, t)
+    if (K, s, r) in ((2, 1, 1), (3, 2, 1), (4, 2, 2), (5, 3, 3), (6, 4, 3), (7, 4, 4)):
+        assert n_reg == len(idx)                          # these geometries cut every tree
+    else:
+        assert n_reg > 0.85 * len(idx)
+
+
+@pytest.mark.parametrize("K", [9, 10])
+def test_pair_cuts_for_large_k(built_library, K):
+    """default geometry at K = 9, 10: most random trees are regular, rows are in range, the pack has <= s
+    nodes and the context <= r nodes (checked through the recipes' node counts), extreme shapes included."""
+    lib = cuda_shim.load_library()
+    s, r, nf, nt = pair_geometry(lib, K)
+    assert nf < (1 << 24) and nt < (1 << 24)
+    rec = recipes(lib, K, s, nf)
+    rng = np.random.default_rng(K)
+    trees = [orc.decode_tree(K, int(rng.integers(0, K ** (K - 1)))) for _ in range(600)]
+    trees += [[-1] + list(range(K - 1)), [-1] + [0] * (K - 1), [-1, 0] + [1] * (K - 2), [-1] + [i // 2 for i in range(K - 1)]]
+    n_reg = 0
+    for t in trees:
+        reg, fg, tr = classify(lib, t, s, r)
+        if reg:
+            n_reg += 1
+            n_pack = bin(int(rec[fg][4])).count("1")
+            assert K - r <= n_pack <= s and 0 <= tr < nt
+    assert n_reg > 0.8 * len(trees)
+
+
+def test_default_geometry_is_consistent(built_library):
+    lib = cuda_shim.load_library()
+    for K in range(1, 13):
+        s, r, nf, nt = pair_geometry(lib, K)
+        assert r == 0 or (s + r >= K and r - 1 <= s)
