@@ -54,7 +54,25 @@ struct bamse_ctx {
     DBuf d_FG, d_FSG, d_FH, d_tb, d_lut, d_recipe_ptrs;
     struct Recipes { DBuf buf; int s = -1; };
     Recipes recipes[KMAX + 1];
-    int geom_s[KMAX + 1] = {0}, geom_sh[KMAX + 1] = {0};
+    int geom_s[KMAX + 1] = {0}, geom_sh[KMAX + 1] = {0}, geom_r[KMAX + 1] = {0};
+    // pair path (pairs.cuh), per cluster count: pair table, context map / compact recipes; kept across uploads
+    // while the geometry of that K is unchanged
+    struct PairState {
+        DBuf tab, map, recipes;
+        int s = -1, r = -1;
+        bool has_tab = false;
+        uint32_t nt = 0, lbase[PR_RMAX + 2] = {0};
+        uint64_t n_irregular = 0;
+    };
+    PairState pairs[KMAX + 1];
+    DBuf d_T, d_pk, d_flat, d_flat_meta, d_lists2, d_segs2, d_owner;
+    std::vector<int32_t> owner;          // [P][C] sharding plan (empty: none): -1 split over all ranks, else the owning rank
+    bool k_present[KMAX + 1] = {false};
+    bool interp_ready = false;           // finishing tables + top-level scanned messages of the resident problem built
+    int max_top_rows = 0, max_fh_items = 0, max_level_rows[FT_SMAX + 2] = {0}, max_ctx_rows[PR_RMAX + 2] = {0};
+    int smax = 1, rmax = 0;
+    size_t fh_rows = 0;
+    int grid_pairs = 0;
     int slots_needed = 3;
     double table_bytes = 0.0;
     // program tables (fp32 enumeration): one per K <= PROGTAB_KMAX present in the problem, kept across
@@ -70,6 +88,9 @@ struct bamse_ctx {
     int grid[3] = {0, 0, 0};
     uint64_t last_cand_cap = 0;   // capacity of the candidate bag of the last enumeration
     int shard_rank = 0, shard_world = 1;
+    int plan_rank = 0, plan_world = 1;   // the shard the resident problem's plan / tables were made for
+    int shard_plan = 1;      // BAMSE_OPT_SHARD_PLAN
+    int collect_stats = 0;   // BAMSE_OPT_STATS
     int early_exit = 0;      // BAMSE_OPT_EARLY_EXIT
     int last_verified = 1;   // the last bamse_score_topk proved its preselection cut safe (bamse_last_topk_verified)
     int last_ksel = 0;       // ... and the preselection size it ended with
@@ -77,7 +98,7 @@ struct bamse_ctx {
     bool probing = false;
     uint64_t problem_sig = 0, probed_sig = 0;   // the variant choice is memoised per problem content
     int probed_choice = -1;
-    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_used, ev_free;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_used, ev_build_used, ev_free;
 
     int fail(int code, const char* fmt, ...) {
         char buf[512];
@@ -92,6 +113,7 @@ struct bamse_ctx {
         FastTables f;
         f.D2 = d_D2.as<float>(); f.SD2 = d_SD2.as<float>();
         f.FG = d_FG.as<float>(); f.FSG = d_FSG.as<float>(); f.FH = d_FH.as<float>();
+        f.T = d_T.as<float>(); f.pk = d_pk.as<PairK>();
         f.tb = d_tb.as<TableBase>(); f.lut = d_lut.as<int16_t>();
         f.recipes = d_recipe_ptrs.as<const ForestRecipe*>();
         return f;
@@ -105,7 +127,8 @@ struct bamse_ctx {
     }
 };
 
-constexpr int PROGTAB_KMAX = 9;      // K = 9: 43 M programs, 2.75 GB
+constexpr int PROGTAB_KMAX = 8;      // K = 8: 2 M programs, 134 MB
+constexpr int PAIRTAB_KMAX = 9;      // K = 9: 43 M entries, 344 MB; above, the cut is computed in the kernel
 constexpr int TOPK_INTERNAL = BAMSE_TOPK_INTERNAL;   // preselection lists may grow to this size (public topk <= BAMSE_TOPK_MAX)
 
 // A C++ exception (std::bad_alloc of a staging vector, in practice) must not cross the C ABI: the entry
@@ -128,6 +151,369 @@ static inline bool valid_precision(int p) { return p == BAMSE_FP32 || p == BAMSE
         if (!(ctx)) return BAMSE_EINVAL;    \
         cudaSetDevice((ctx)->device);       \
     } while (0)
+
+
+static bool pairs_enabled() {
+    const char* e = getenv("BAMSE_PAIRS");           // BAMSE_PAIRS=0: table-driven programs only (A/B measurements)
+    return !(e && atoi(e) == 0);
+}
+
+// Pair state of a cluster count for the geometry (geom_s, geom_r): the cut of every tree (pair table for
+// K <= PAIRTAB_KMAX, a marking pass above), the context rows in use closed under the recipes' parent links, the
+// map from the full context index space to compact rows and the compact recipes.  Data independent: built once
+// per ctx and geometry.
+static int ensure_pair_state(bamse_ctx* ctx, int K) {
+    bamse_ctx::PairState& ps = ctx->pairs[K];
+    const int sK = ctx->geom_s[K], rK = ctx->geom_r[K];
+    if (ps.s == sK && ps.r == rK) return BAMSE_OK;
+    ps.s = ps.r = -1;
+    const ForestIndex fi = make_forest_index(K, sK, 1);
+    const PairGeom g = make_pair_geom(K, sK, rK);
+    if (fi.nf >= (1 << 24) || g.nt >= (1u << 24)) return ctx->fail(BAMSE_EINTERNAL, "pair geometry of K=%d exceeds 24-bit row ids", K);
+    cudaStream_t st = ctx->stream;
+    const uint64_t n_trees = ipow_u64(K, K - 1);
+    ps.has_tab = K <= PAIRTAB_KMAX;
+    if (ps.has_tab) BAMSE_CUDA_TRY(ctx, ps.tab.ensure(sizeof(uint64_t) * n_trees));
+    DBuf used;
+    const size_t used_bytes = ((size_t)g.nt + 15) / 8 * 8;
+    cudaError_t e = used.ensure(used_bytes + 8);
+    if (e != cudaSuccess) return ctx->fail(BAMSE_ENOMEM, "pair state: %s", cudaGetErrorString(e));
+    cudaMemsetAsync(used.p, 0, used_bytes + 8, st);
+    unsigned long long* d_nirr = reinterpret_cast<unsigned long long*>(used.as<uint8_t>() + used_bytes);
+    launch_build_pair_table(fi, g, n_trees, ctx->d_lut.as<int16_t>(), ps.has_tab ? ps.tab.as<uint64_t>() : nullptr,
+                            used.as<uint8_t>(), d_nirr, st);
+    ctx->launches++;
+    std::vector<uint8_t> h_used(used_bytes + 8);
+    e = cudaMemcpyAsync(h_used.data(), used.p, used_bytes + 8, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) { used.release(); return ctx->fail(BAMSE_ECUDA, "pair state of K=%d: %s", K, cudaGetErrorString(e)); }
+    unsigned long long n_irr = 0;
+    memcpy(&n_irr, h_used.data() + used_bytes, sizeof n_irr);
+    used.release();
+    const std::vector<CtxRecipe> full = make_ctx_recipes(fi, g);
+    // a row in use needs the context its recipe starts from; parents have fewer nodes, i.e. smaller row ids
+    for (size_t i = g.nt; i-- > 0;)
+        if (h_used[i] && full[i].parent_row >= 0) h_used[(size_t)full[i].parent_row] = 1;
+    std::vector<uint32_t> map(g.nt, 0xffffffffu);
+    std::vector<CtxRecipe> comp;
+    for (int q = 1; q <= PR_RMAX + 1; ++q) {
+        ps.lbase[q] = (uint32_t)comp.size();
+        if (q > rK) continue;
+        for (uint32_t i = g.base[q]; i < g.base[q + 1]; ++i) {
+            if (!h_used[i]) continue;
+            map[i] = (uint32_t)comp.size();
+            CtxRecipe c = full[i];
+            if (c.parent_row >= 0) c.parent_row = (int32_t)map[(size_t)c.parent_row];
+            comp.push_back(c);
+        }
+    }
+    ps.lbase[0] = 0;
+    ps.nt = (uint32_t)comp.size();
+    BAMSE_CUDA_TRY(ctx, ps.map.ensure(sizeof(uint32_t) * std::max<size_t>(map.size(), 1)));
+    BAMSE_CUDA_TRY(ctx, ps.recipes.ensure(sizeof(CtxRecipe) * std::max<size_t>(comp.size(), 1)));
+    BAMSE_CUDA_TRY(ctx, cudaMemcpy(ps.map.p, map.data(), sizeof(uint32_t) * map.size(), cudaMemcpyHostToDevice));
+    BAMSE_CUDA_TRY(ctx, cudaMemcpy(ps.recipes.p, comp.data(), sizeof(CtxRecipe) * comp.size(), cudaMemcpyHostToDevice));
+    if (ps.has_tab) {
+        launch_remap_pair_table(ps.tab.as<uint64_t>(), n_trees, ps.map.as<uint32_t>(), st);
+        ctx->launches++;
+    }
+    BAMSE_CUDA_TRY(ctx, cudaGetLastError());
+    ps.n_irregular = n_irr;
+    ps.s = sK; ps.r = rK;
+    return BAMSE_OK;
+}
+
+// Sharding plan (multi-GPU): which rank scores which (parameter set, clustering).  Tables are per (p, c), so a
+// pair that one rank owns entirely costs its table build once; a pair split over all ranks (interleaved tree
+// indices) costs the build on EVERY rank.  Longest-processing-time assignment of whole pairs, with the j most
+// expensive pairs split instead, j chosen to minimise the estimated makespan (small problems: a few whole pairs
+// per rank; one huge clustering: split).  Costs are in convolution units per sample: table rows that need a
+// convolution count 1, the other rows 0.25, a regular tree 0.004 (one windowed dot product), an irregular tree or
+// a tree of a cluster count without pair path ~1.  Deterministic: every rank computes the same plan.
+static void make_shard_plan(bamse_ctx* ctx) {
+    ctx->owner.clear();
+    ctx->plan_rank = ctx->shard_rank; ctx->plan_world = ctx->shard_world;
+    const int W = ctx->shard_world, P = ctx->P, C = ctx->C;
+    if (W <= 1 || !ctx->shard_plan) return;
+    if (const char* e = getenv("BAMSE_SHARD_PLAN")) if (atoi(e) == 0) return;
+    double build_k[KMAX + 1] = {0.0}, enum_k[KMAX + 1] = {0.0};
+    for (int K = 1; K <= KMAX; ++K) {
+        if (!ctx->k_present[K]) continue;
+        const ForestIndex fi = make_forest_index(K, ctx->geom_s[K], ctx->geom_sh[K]);
+        double conv_rows = 0.0;
+        for (int n = 2; n <= fi.s; ++n) {
+            double trees = 1.0;                       // n^(n-1) single trees among the (n+1)^(n-1) forests
+            for (int i = 0; i < n - 1; ++i) trees *= n;
+            conv_rows += binom_small(K, n) * ((double)forest_count(n) - trees);
+        }
+        const double T = (double)ipow_u64(K, K - 1);
+        if (ctx->geom_r[K] > 0) {
+            build_k[K] = conv_rows + 0.25 * fi.nf + 1.1 * ctx->pairs[K].nt;
+            enum_k[K] = 0.004 * T + 1.2 * (double)ctx->pairs[K].n_irregular;
+        } else {
+            build_k[K] = conv_rows + 0.25 * fi.nf + (double)K * fi.nfh;
+            enum_k[K] = T * (K <= 6 ? 0.1 : 0.25 * (K - 5));
+        }
+    }
+    const int n = P * C;
+    std::vector<int> order(n);
+    for (int i = 0; i < n; ++i) order[i] = i;
+    auto cost = [&](int i) { const int K = ctx->K_of_c[i % C]; return build_k[K] + enum_k[K]; };
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return cost(a) > cost(b); });
+    int best_j = 0;
+    double best_span = -1.0;
+    std::vector<double> load(W);
+    const int j_max = std::min(n, 4 * W + 8);
+    for (int j = 0; j <= j_max; ++j) {
+        double base = 0.0;
+        for (int t = 0; t < j; ++t) { const int K = ctx->K_of_c[order[t] % C]; base += build_k[K] + enum_k[K] / W; }
+        for (int r = 0; r < W; ++r) load[r] = base;
+        for (int t = j; t < n; ++t) {
+            int r_min = 0;
+            for (int r = 1; r < W; ++r) if (load[r] < load[r_min]) r_min = r;
+            load[r_min] += cost(order[t]);
+        }
+        double span = 0.0;
+        for (int r = 0; r < W; ++r) span = std::max(span, load[r]);
+        if (best_span < 0.0 || span < best_span * (1.0 - 1e-9)) { best_span = span; best_j = j; }
+    }
+    ctx->owner.assign(n, -1);
+    for (int r = 0; r < W; ++r) load[r] = 0.0;
+    for (int t = best_j; t < n; ++t) {
+        int r_min = 0;
+        for (int r = 1; r < W; ++r) if (load[r] < load[r_min]) r_min = r;
+        load[r_min] += cost(order[t]);
+        ctx->owner[order[t]] = r_min;
+    }
+}
+
+// Geometry of every cluster count present (stepped down until the tables fit the budget), pair states, table
+// bases, allocations, recipes and program tables of the resident problem.  Host work + data-independent kernels.
+static int plan_tables(bamse_ctx* ctx) {
+    const int P = ctx->P, C = ctx->C, M = ctx->M;
+    const bool* k_present = ctx->k_present;
+    cudaStream_t s = ctx->stream;
+    if (!ctx->d_lut.p) {
+        BAMSE_CUDA_TRY(ctx, ctx->d_lut.ensure(sizeof(int16_t) * FT_LUT_SIZE));
+        BAMSE_CUDA_TRY(ctx, cudaMemcpy(ctx->d_lut.p, forest_lut().lut.data(), sizeof(int16_t) * FT_LUT_SIZE, cudaMemcpyHostToDevice));
+    }
+    // BAMSE_TABLE_GB: table budget (default 60 % of the device memory); BAMSE_FOREST_S / _SH / BAMSE_PAIR_R override
+    const char* env_s = getenv("BAMSE_FOREST_S");
+    const char* env_sh = getenv("BAMSE_FOREST_SH");
+    const char* env_r = getenv("BAMSE_PAIR_R");
+    const bool pairs_on = pairs_enabled();
+    for (int K = 1; K <= KMAX; ++K) {
+        if (!k_present[K]) continue;
+        default_forest_geometry(K, &ctx->geom_s[K], &ctx->geom_sh[K], &ctx->geom_r[K]);
+        if (env_s) ctx->geom_s[K] = std::max(1, std::min(atoi(env_s), FT_SMAX));
+        if (env_sh) ctx->geom_sh[K] = std::max(1, atoi(env_sh));
+        if (env_r) ctx->geom_r[K] = std::max(0, std::min(atoi(env_r), PR_RMAX));
+        int& sK = ctx->geom_s[K];
+        int& rK = ctx->geom_r[K];
+        if (!pairs_on || K < 2 || sK + rK < K || rK - 1 > sK) rK = 0;
+        if (rK > 0 && (make_forest_index(K, sK, 1).nf >= (1 << 24) || make_pair_geom(K, sK, rK).nt >= (1u << 24))) rK = 0;
+        if (rK == 0) sK = program_forest_s(K, sK);     // programs only: nothing above the 16-bit row ids is needed
+        ctx->geom_sh[K] = std::min(ctx->geom_sh[K], program_forest_s(K, sK));
+    }
+    double budget = 0.0;
+    {
+        size_t free_b = 0, total_b = 0;
+        BAMSE_CUDA_TRY(ctx, cudaMemGetInfo(&free_b, &total_b));
+        budget = 0.6 * (double)total_b;
+        if (const char* g = getenv("BAMSE_TABLE_GB")) budget = atof(g) * 1e9;
+    }
+    std::vector<TableBase> tbs((size_t)P * C);
+    size_t fg_rows = 0, fh_rows = 0, t_rows = 0;
+    for (;;) {
+        for (int K = 1; K <= KMAX; ++K)
+            if (k_present[K] && ctx->geom_r[K] > 0) { const int rc = ensure_pair_state(ctx, K); if (rc) return rc; }
+        make_shard_plan(ctx);
+        fg_rows = fh_rows = t_rows = 0;
+        double per_k[KMAX + 1] = {0.0};
+        for (int p = 0; p < P; ++p)
+            for (int c = 0; c < C; ++c) {
+                const int K = ctx->K_of_c[c];
+                TableBase& t = tbs[(size_t)p * C + c];
+                t.fi = make_forest_index(K, ctx->geom_s[K], ctx->geom_sh[K]);
+                t.s_prog = program_forest_s(K, ctx->geom_s[K]);
+                t.mine = ctx->owner.empty() || ctx->owner[(size_t)p * C + c] < 0 || ctx->owner[(size_t)p * C + c] == ctx->shard_rank;
+                t.fg_row = (uint32_t)fg_rows; t.fh_row = (uint32_t)fh_rows; t.t_row = (uint32_t)t_rows;
+                if (!t.mine) continue;
+                const size_t a = (size_t)M * t.fi.nf, b = (size_t)M * K * t.fi.nfh;
+                const size_t tt = ctx->geom_r[K] > 0 ? (size_t)M * ctx->pairs[K].nt : 0;
+                fg_rows += a; fh_rows += b; t_rows += tt;
+                per_k[K] += (double)(2 * a + b + tt) * L * sizeof(float);
+            }
+        const double bytes = (double)(2 * fg_rows + fh_rows + t_rows) * L * sizeof(float);
+        ctx->table_bytes = bytes;
+        if ((bytes <= budget && fg_rows < 0xffffffffull && fh_rows < 0xffffffffull && t_rows < 0xffffffffull) || (env_s && env_sh)) break;
+        int worst = 0;                                 // step the geometry of the hungriest cluster count down
+        for (int K = 1; K <= KMAX; ++K) if (per_k[K] > per_k[worst]) worst = K;
+        bool stepped = false;
+        if (worst && ctx->geom_r[worst] > 0) {         // first give up the pair path of that cluster count
+            ctx->geom_r[worst] = 0;
+            ctx->geom_s[worst] = program_forest_s(worst, ctx->geom_s[worst]);
+            stepped = true;
+        } else if (worst) stepped = reduce_forest_geometry(&ctx->geom_s[worst], &ctx->geom_sh[worst]);
+        if (!stepped) {
+            bool any = false;
+            for (int K = 1; K <= KMAX && !any; ++K)
+                if (k_present[K] && ctx->geom_r[K] == 0) any = reduce_forest_geometry(&ctx->geom_s[K], &ctx->geom_sh[K]);
+            if (!any) return ctx->fail(BAMSE_ENOMEM, "bamse_upload_problem: the smallest tables (%.1f GB) exceed the table budget (%.1f GB)", bytes / 1e9, budget / 1e9);
+        }
+    }
+    ctx->slots_needed = 2;
+    ctx->smax = 1; ctx->rmax = 0; ctx->max_fh_items = 0; ctx->max_top_rows = 0;
+    for (int n = 0; n <= FT_SMAX + 1; ++n) ctx->max_level_rows[n] = 0;
+    for (int q = 0; q <= PR_RMAX + 1; ++q) ctx->max_ctx_rows[q] = 0;
+    for (int K = 1; K <= KMAX; ++K) {
+        if (!k_present[K]) continue;
+        const ForestIndex fi = make_forest_index(K, ctx->geom_s[K], ctx->geom_sh[K]);
+        const int sp = program_forest_s(K, fi.s);
+        ctx->slots_needed = std::max(ctx->slots_needed, forest_slots_needed(K, sp));
+        ctx->smax = std::max(ctx->smax, fi.s);
+        for (int n = 2; n <= fi.s; ++n) ctx->max_level_rows[n] = std::max(ctx->max_level_rows[n], fi.base[n + 1] - fi.base[n]);
+        if (sp == fi.s) ctx->max_top_rows = std::max(ctx->max_top_rows, fi.base[fi.s + 1] - fi.base[fi.s]);
+        ctx->max_fh_items = std::max(ctx->max_fh_items, K * fi.nfh);
+        if (ctx->geom_r[K] > 0) {
+            const bamse_ctx::PairState& ps = ctx->pairs[K];
+            ctx->rmax = std::max(ctx->rmax, ctx->geom_r[K]);
+            for (int q = 1; q <= ctx->geom_r[K]; ++q)
+                ctx->max_ctx_rows[q] = std::max(ctx->max_ctx_rows[q], (int)(ps.lbase[q + 1] - ps.lbase[q]));
+        }
+    }
+    ctx->fh_rows = fh_rows;
+    ctx->interp_ready = false;
+    BAMSE_CUDA_TRY(ctx, ctx->d_FG.ensure(sizeof(float) * std::max<size_t>(fg_rows, 1) * L));
+    BAMSE_CUDA_TRY(ctx, ctx->d_FSG.ensure(sizeof(float) * std::max<size_t>(fg_rows, 1) * L));
+    BAMSE_CUDA_TRY(ctx, ctx->d_T.ensure(sizeof(float) * std::max<size_t>(t_rows, 1) * L));
+    BAMSE_CUDA_TRY(ctx, ctx->d_tb.ensure(sizeof(TableBase) * tbs.size()));
+    BAMSE_CUDA_TRY(ctx, cudaMemcpy(ctx->d_tb.p, tbs.data(), sizeof(TableBase) * tbs.size(), cudaMemcpyHostToDevice));
+    if (!ctx->owner.empty()) {
+        BAMSE_CUDA_TRY(ctx, ctx->d_owner.ensure(sizeof(int32_t) * ctx->owner.size()));
+        BAMSE_CUDA_TRY(ctx, cudaMemcpy(ctx->d_owner.p, ctx->owner.data(), sizeof(int32_t) * ctx->owner.size(), cudaMemcpyHostToDevice));
+    }
+    {
+        const ForestRecipe* rptrs[KMAX + 1];
+        PairK pks[KMAX + 1];
+        memset(pks, 0, sizeof pks);
+        for (int K = 0; K <= KMAX; ++K) {
+            rptrs[K] = nullptr;
+            if (K == 0 || !k_present[K]) continue;
+            bamse_ctx::Recipes& r = ctx->recipes[K];
+            if (!r.buf.p || r.s != ctx->geom_s[K]) {
+                const std::vector<ForestRecipe> rec = make_forest_recipes(make_forest_index(K, ctx->geom_s[K], ctx->geom_sh[K]));
+                BAMSE_CUDA_TRY(ctx, r.buf.ensure(sizeof(ForestRecipe) * rec.size()));
+                BAMSE_CUDA_TRY(ctx, cudaMemcpy(r.buf.p, rec.data(), sizeof(ForestRecipe) * rec.size(), cudaMemcpyHostToDevice));
+                r.s = ctx->geom_s[K];
+            }
+            rptrs[K] = r.buf.as<ForestRecipe>();
+            if (ctx->geom_r[K] > 0) {
+                const bamse_ctx::PairState& ps = ctx->pairs[K];
+                PairK& pk = pks[K];
+                pk.g = make_pair_geom(K, ctx->geom_s[K], ctx->geom_r[K]);
+                pk.nt = ps.nt;
+                for (int q = 0; q <= PR_RMAX + 1; ++q) pk.lbase[q] = ps.lbase[q];
+                pk.map = ps.map.as<uint32_t>();
+                pk.recipes = ps.recipes.as<CtxRecipe>();
+                pk.pair_tab = ps.has_tab ? ps.tab.as<uint64_t>() : nullptr;
+            }
+        }
+        BAMSE_CUDA_TRY(ctx, ctx->d_recipe_ptrs.ensure(sizeof rptrs));
+        BAMSE_CUDA_TRY(ctx, cudaMemcpy(ctx->d_recipe_ptrs.p, rptrs, sizeof rptrs, cudaMemcpyHostToDevice));
+        BAMSE_CUDA_TRY(ctx, ctx->d_pk.ensure(sizeof pks));
+        BAMSE_CUDA_TRY(ctx, cudaMemcpy(ctx->d_pk.p, pks, sizeof pks, cudaMemcpyHostToDevice));
+    }
+    {   // program tables for the small K of this problem (K^(K-1) rows of 64 bytes; K = 8: 134 MB)
+        const char* off = getenv("BAMSE_PROGTAB");          // BAMSE_PROGTAB=0: always decode in the kernel
+        const bool enable = !(off && atoi(off) == 0);
+        const FastProgram* ptrs[KMAX + 1];
+        for (int k = 0; k <= KMAX; ++k) ptrs[k] = nullptr;
+        ctx->have_progtabs = false;
+        for (int c = 0; c < C && enable; ++c) {
+            const int K = ctx->K_of_c[c];
+            if (K > PROGTAB_KMAX || ptrs[K]) continue;
+            // a cluster count whose trees are all regular never runs a program in an enumeration
+            if (ctx->geom_r[K] > 0 && ctx->pairs[K].n_irregular == 0) continue;
+            bamse_ctx::ProgTab& t = ctx->progtab[K];
+            const uint64_t n = ipow_u64(K, K - 1);
+            const int sp = program_forest_s(K, ctx->geom_s[K]);
+            if (!t.buf.p || t.s != sp || t.sh != ctx->geom_sh[K]) {
+                BAMSE_CUDA_TRY(ctx, t.buf.ensure(sizeof(FastProgram) * n));
+                launch_build_prog_table(make_forest_index(K, sp, ctx->geom_sh[K]), n, ctx->d_lut.as<int16_t>(),
+                                        t.buf.as<FastProgram>(), s);
+                ctx->launches++;
+                t.s = sp; t.sh = ctx->geom_sh[K];
+            }
+            ptrs[K] = t.buf.as<FastProgram>();
+            ctx->have_progtabs = true;
+        }
+        BAMSE_CUDA_TRY(ctx, ctx->d_progtabs.ensure(sizeof ptrs));
+        BAMSE_CUDA_TRY(ctx, cudaMemcpy(ctx->d_progtabs.p, ptrs, sizeof ptrs, cudaMemcpyHostToDevice));
+    }
+    return BAMSE_OK;
+}
+
+// Every table of the resident problem from the read counts in device memory: binomial tables, inside tables
+// level by level, context tables level by level.  Asynchronous on the ctx stream.  The finishing tables and
+// the top-level scanned messages, which only the table-driven programs read, follow on demand (ensure_interp).
+static int launch_table_build(bamse_ctx* ctx) {
+    cudaStream_t s = ctx->stream;
+    unsigned long long* stats = nullptr;
+    if (ctx->collect_stats) {
+        const bool fresh = ctx->d_scalars.p == nullptr;
+        BAMSE_CUDA_TRY(ctx, ctx->d_scalars.ensure(sizeof(uint64_t) * 16));
+        if (fresh) BAMSE_CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_scalars.p, 0, sizeof(uint64_t) * 16, s));
+        stats = reinterpret_cast<unsigned long long*>(ctx->d_scalars.as<uint64_t>() + 4);
+    }
+    std::pair<cudaEvent_t, cudaEvent_t> ev;
+    if (!ctx->ev_free.empty()) { ev = ctx->ev_free.back(); ctx->ev_free.pop_back(); }
+    else {
+        BAMSE_CUDA_TRY(ctx, cudaEventCreate(&ev.first));
+        BAMSE_CUDA_TRY(ctx, cudaEventCreate(&ev.second));
+    }
+    BAMSE_CUDA_TRY(ctx, cudaEventRecord(ev.first, s));
+    launch_tables(ctx->view(), ctx->d_var.as<double>(), ctx->d_ref.as<double>(), ctx->d_logc.as<double>(),
+                  ctx->d_logcf.as<double>(), ctx->d_log1mcf.as<double>(), ctx->d_D64.as<double>(),
+                  ctx->d_D32.as<float>(), s);
+    launch_tables_fast(ctx->view(), ctx->fast(), ctx->d_D2.as<float>(), ctx->d_FG.as<float>(), ctx->d_FSG.as<float>(),
+                       ctx->d_SD2.as<float>(), s);
+    ctx->launches += 2;
+    for (int n = 2; n <= ctx->smax; ++n) {
+        launch_forest_level(ctx->view(), ctx->fast(), n, ctx->max_level_rows[n], ctx->d_FG.as<float>(), ctx->d_FSG.as<float>(), 0, stats, s);
+        ctx->launches++;
+    }
+    for (int q = 1; q <= ctx->rmax; ++q) {
+        if (ctx->max_ctx_rows[q] <= 0) continue;
+        launch_ctx_level(ctx->view(), ctx->fast(), q, ctx->max_ctx_rows[q], ctx->d_T.as<float>(), stats, s);
+        ctx->launches++;
+    }
+    BAMSE_CUDA_TRY(ctx, cudaEventRecord(ev.second, s));
+    ctx->ev_build_used.push_back(ev);
+    if (ctx->ev_build_used.size() > 256) {           // nobody is reading the timer: keep the newest only
+        ctx->ev_free.push_back(ctx->ev_build_used.front());
+        ctx->ev_build_used.erase(ctx->ev_build_used.begin());
+    }
+    ctx->interp_ready = false;
+    BAMSE_CUDA_TRY(ctx, cudaGetLastError());
+    return BAMSE_OK;
+}
+
+// What only the table-driven programs read: the scanned messages of the top-level forests and the finishing tables.
+static int ensure_interp(bamse_ctx* ctx) {
+    if (ctx->interp_ready) return BAMSE_OK;
+    cudaStream_t s = ctx->stream;
+    BAMSE_CUDA_TRY(ctx, ctx->d_FH.ensure(sizeof(float) * std::max<size_t>(ctx->fh_rows, 1) * L));
+    if (ctx->max_top_rows > 0) {
+        launch_forest_scan_top(ctx->view(), ctx->fast(), ctx->max_top_rows, ctx->d_FG.as<float>(), ctx->d_FSG.as<float>(), s);
+        ctx->launches++;
+    }
+    launch_forest_fh(ctx->view(), ctx->fast(), ctx->max_fh_items, ctx->d_FH.as<float>(), s);
+    ctx->launches++;
+    BAMSE_CUDA_TRY(ctx, cudaGetLastError());
+    ctx->interp_ready = true;
+    return BAMSE_OK;
+}
 
 extern "C" {
 
@@ -184,12 +570,14 @@ void bamse_destroy(bamse_ctx* ctx) {
                     &ctx->d_D64, &ctx->d_D32, &ctx->d_D2, &ctx->d_SD2, &ctx->d_FG, &ctx->d_FSG, &ctx->d_FH, &ctx->d_tb, &ctx->d_lut,
                     &ctx->d_recipe_ptrs, &ctx->d_segs, &ctx->d_scalars, &ctx->d_cand, &ctx->d_items,
                     &ctx->d_scores, &ctx->d_const, &ctx->d_thr, &ctx->d_begin, &ctx->d_end, &ctx->d_records,
-                    &ctx->d_dense0, &ctx->d_dense1, &ctx->d_split, &ctx->d_lists};
+                    &ctx->d_dense0, &ctx->d_dense1, &ctx->d_split, &ctx->d_lists, &ctx->d_T, &ctx->d_pk, &ctx->d_flat,
+                    &ctx->d_flat_meta, &ctx->d_lists2, &ctx->d_segs2, &ctx->d_owner};
     for (DBuf* b : bufs) b->release();
     for (auto& t : ctx->progtab) t.buf.release();
+    for (auto& t : ctx->pairs) { t.tab.release(); t.map.release(); t.recipes.release(); }
     for (auto& r : ctx->recipes) r.buf.release();
     ctx->d_progtabs.release();
-    for (auto* v : {&ctx->ev_used, &ctx->ev_free})
+    for (auto* v : {&ctx->ev_used, &ctx->ev_build_used, &ctx->ev_free})
         for (auto& ev : *v) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
@@ -205,6 +593,9 @@ int bamse_set_shard(bamse_ctx* ctx, int rank, int world) {
     CTX_CHECK(ctx);
     if (world < 1 || rank < 0 || rank >= world) return ctx->fail(BAMSE_EINVAL, "bamse_set_shard: need 0 <= rank < world");
     ctx->shard_rank = rank; ctx->shard_world = world;
+    // tables exist only for the (parameter set, clustering) pairs the plan gave this rank: a resident problem
+    // that was planned for another shard has to be uploaded again
+    if (ctx->have_problem && !ctx->owner.empty() && (rank != ctx->plan_rank || world != ctx->plan_world)) ctx->have_problem = false;
     return BAMSE_OK;
 }
 
@@ -213,6 +604,8 @@ int bamse_fast_variant(const bamse_ctx* ctx) { return ctx ? ctx->use_framed : -1
 int bamse_set_option(bamse_ctx* ctx, int option, int value) {
     CTX_CHECK(ctx);
     if (option == BAMSE_OPT_EARLY_EXIT) { ctx->early_exit = value ? 1 : 0; return BAMSE_OK; }
+    if (option == BAMSE_OPT_SHARD_PLAN) { ctx->shard_plan = value ? 1 : 0; return BAMSE_OK; }
+    if (option == BAMSE_OPT_STATS) { ctx->collect_stats = value ? 1 : 0; return BAMSE_OK; }
     return ctx->fail(BAMSE_EINVAL, "bamse_set_option: unknown option %d", option);
 }
 
@@ -249,6 +642,24 @@ int bamse_kernel_time(bamse_ctx* ctx, int reset, double* out_ms, int64_t* out_la
     }
     return BAMSE_OK;
 } catch (...) { return on_exception(ctx, "bamse_kernel_time"); }
+
+int bamse_table_time(bamse_ctx* ctx, int reset, double* out_ms, int64_t* out_builds) try {
+    CTX_CHECK(ctx);
+    BAMSE_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    double ms = 0.0;
+    for (auto& ev : ctx->ev_build_used) {
+        float t = 0.f;
+        BAMSE_CUDA_TRY(ctx, cudaEventElapsedTime(&t, ev.first, ev.second));
+        ms += t;
+    }
+    if (out_ms) *out_ms = ms;
+    if (out_builds) *out_builds = (int64_t)ctx->ev_build_used.size();
+    if (reset) {
+        for (auto& ev : ctx->ev_build_used) ctx->ev_free.push_back(ev);
+        ctx->ev_build_used.clear();
+    }
+    return BAMSE_OK;
+} catch (...) { return on_exception(ctx, "bamse_table_time"); }
 
 int bamse_kernel_stats(bamse_ctx* ctx, int reset, uint64_t* out4) {
     CTX_CHECK(ctx);
@@ -389,90 +800,11 @@ int bamse_upload_problem(bamse_ctx* ctx, int P, const double* err, int C, int M,
     BAMSE_CUDA_TRY(ctx, ctx->d_D32.ensure(sizeof(float) * nrows * L));
     BAMSE_CUDA_TRY(ctx, ctx->d_D2.ensure(sizeof(float) * nrows * L));
     BAMSE_CUDA_TRY(ctx, ctx->d_SD2.ensure(sizeof(float) * nrows * L));
-    // ---- sub-forest tables: geometry per cluster count, stepped down until everything fits the budget
-    //      (BAMSE_TABLE_GB, default 60 % of the device memory); BAMSE_FOREST_S / BAMSE_FOREST_SH override
-    bool k_present[KMAX + 1] = {false};
-    for (int c = 0; c < C; ++c) k_present[K_of_c[c]] = true;
-    const char* env_s = getenv("BAMSE_FOREST_S");
-    const char* env_sh = getenv("BAMSE_FOREST_SH");
-    for (int K = 1; K <= KMAX; ++K) {
-        if (!k_present[K]) continue;
-        default_forest_geometry(K, &ctx->geom_s[K], &ctx->geom_sh[K]);
-        if (env_s) ctx->geom_s[K] = std::max(1, std::min({atoi(env_s), FT_SMAX, K >= 11 ? 3 : FT_SMAX}));
-        if (env_sh) ctx->geom_sh[K] = std::max(1, atoi(env_sh));
-        while (ctx->geom_s[K] > 1 && make_forest_index(K, ctx->geom_s[K], 1).nf > 65535) --ctx->geom_s[K];   // 16-bit row ids
-        ctx->geom_sh[K] = std::min(ctx->geom_sh[K], ctx->geom_s[K]);
-    }
-    double budget = 0.0;
-    {
-        size_t free_b = 0, total_b = 0;
-        BAMSE_CUDA_TRY(ctx, cudaMemGetInfo(&free_b, &total_b));
-        budget = 0.6 * (double)total_b;
-        if (const char* g = getenv("BAMSE_TABLE_GB")) budget = atof(g) * 1e9;
-    }
-    std::vector<TableBase> tbs((size_t)P * C);
-    size_t fg_rows = 0, fh_rows = 0;
-    for (;;) {
-        fg_rows = fh_rows = 0;
-        double per_k[KMAX + 1] = {0.0};
-        for (int p = 0; p < P; ++p)
-            for (int c = 0; c < C; ++c) {
-                const int K = K_of_c[c];
-                TableBase& t = tbs[(size_t)p * C + c];
-                t.fi = make_forest_index(K, ctx->geom_s[K], ctx->geom_sh[K]);
-                t.fg_row = (uint32_t)fg_rows; t.fh_row = (uint32_t)fh_rows;
-                const size_t a = (size_t)M * t.fi.nf, b = (size_t)M * K * t.fi.nfh;
-                fg_rows += a; fh_rows += b;
-                per_k[K] += (double)(2 * a + b) * L * sizeof(float);
-            }
-        const double bytes = (double)(2 * fg_rows + fh_rows) * L * sizeof(float);
-        ctx->table_bytes = bytes;
-        if ((bytes <= budget && fg_rows < 0xffffffffull && fh_rows < 0xffffffffull) || (env_s && env_sh)) break;
-        int worst = 0;                                 // step the geometry of the hungriest cluster count down
-        for (int K = 1; K <= KMAX; ++K) if (per_k[K] > per_k[worst]) worst = K;
-        if (!worst || !reduce_forest_geometry(&ctx->geom_s[worst], &ctx->geom_sh[worst])) {
-            bool any = false;
-            for (int K = 1; K <= KMAX && !any; ++K) if (k_present[K]) any = reduce_forest_geometry(&ctx->geom_s[K], &ctx->geom_sh[K]);
-            if (!any) return ctx->fail(BAMSE_ENOMEM, "bamse_upload_problem: the smallest sub-forest tables (%.1f GB) exceed the table budget (%.1f GB)", bytes / 1e9, budget / 1e9);
-        }
-    }
-    ctx->slots_needed = 2;
-    int smax = 1, max_level_rows[FT_SMAX + 2] = {0}, max_fh_items = 0;
-    for (int K = 1; K <= KMAX; ++K) {
-        if (!k_present[K]) continue;
-        const ForestIndex fi = make_forest_index(K, ctx->geom_s[K], ctx->geom_sh[K]);
-        ctx->slots_needed = std::max(ctx->slots_needed, forest_slots_needed(K, fi.s));
-        smax = std::max(smax, fi.s);
-        for (int n = 2; n <= fi.s; ++n) max_level_rows[n] = std::max(max_level_rows[n], fi.base[n + 1] - fi.base[n]);
-        max_fh_items = std::max(max_fh_items, K * fi.nfh);
-    }
-    BAMSE_CUDA_TRY(ctx, ctx->d_FG.ensure(sizeof(float) * fg_rows * L));
-    BAMSE_CUDA_TRY(ctx, ctx->d_FSG.ensure(sizeof(float) * fg_rows * L));
-    BAMSE_CUDA_TRY(ctx, ctx->d_FH.ensure(sizeof(float) * std::max<size_t>(fh_rows, 1) * L));
-    BAMSE_CUDA_TRY(ctx, ctx->d_tb.ensure(sizeof(TableBase) * tbs.size()));
+    ctx->P = P; ctx->C = C; ctx->M = M; ctx->Kmax = Kmax;
+    ctx->K_of_c.assign(K_of_c, K_of_c + C);
+    for (int K = 0; K <= KMAX; ++K) ctx->k_present[K] = false;
+    for (int c = 0; c < C; ++c) ctx->k_present[K_of_c[c]] = true;
     cudaStream_t s = ctx->stream;
-    BAMSE_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_tb.p, tbs.data(), sizeof(TableBase) * tbs.size(), cudaMemcpyHostToDevice, s));
-    if (!ctx->d_lut.p) {
-        BAMSE_CUDA_TRY(ctx, ctx->d_lut.ensure(sizeof(int16_t) * FT_LUT_SIZE));
-        BAMSE_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_lut.p, forest_lut().lut.data(), sizeof(int16_t) * FT_LUT_SIZE, cudaMemcpyHostToDevice, s));
-    }
-    {
-        const ForestRecipe* rptrs[KMAX + 1];
-        for (int K = 0; K <= KMAX; ++K) {
-            rptrs[K] = nullptr;
-            if (K == 0 || !k_present[K]) continue;
-            bamse_ctx::Recipes& r = ctx->recipes[K];
-            if (!r.buf.p || r.s != ctx->geom_s[K]) {
-                const std::vector<ForestRecipe> rec = make_forest_recipes(make_forest_index(K, ctx->geom_s[K], ctx->geom_sh[K]));
-                BAMSE_CUDA_TRY(ctx, r.buf.ensure(sizeof(ForestRecipe) * rec.size()));
-                BAMSE_CUDA_TRY(ctx, cudaMemcpy(r.buf.p, rec.data(), sizeof(ForestRecipe) * rec.size(), cudaMemcpyHostToDevice));
-                r.s = ctx->geom_s[K];
-            }
-            rptrs[K] = r.buf.as<ForestRecipe>();
-        }
-        BAMSE_CUDA_TRY(ctx, ctx->d_recipe_ptrs.ensure(sizeof rptrs));
-        BAMSE_CUDA_TRY(ctx, cudaMemcpy(ctx->d_recipe_ptrs.p, rptrs, sizeof rptrs, cudaMemcpyHostToDevice));
-    }
     BAMSE_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_K.p, K_of_c, sizeof(int32_t) * C, cudaMemcpyHostToDevice, s));
     BAMSE_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_p0.p, p0.data(), sizeof(double) * C, cudaMemcpyHostToDevice, s));
     BAMSE_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_var.p, var.data(), sizeof(double) * ncnt, cudaMemcpyHostToDevice, s));
@@ -480,44 +812,10 @@ int bamse_upload_problem(bamse_ctx* ctx, int P, const double* err, int C, int M,
     BAMSE_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_logc.p, logc.data(), sizeof(double) * ncnt, cudaMemcpyHostToDevice, s));
     BAMSE_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_logcf.p, logcf.data(), sizeof(double) * P * L, cudaMemcpyHostToDevice, s));
     BAMSE_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_log1mcf.p, log1mcf.data(), sizeof(double) * P * L, cudaMemcpyHostToDevice, s));
-    ctx->P = P; ctx->C = C; ctx->M = M; ctx->Kmax = Kmax;
-    ctx->K_of_c.assign(K_of_c, K_of_c + C);
-    launch_tables(ctx->view(), ctx->d_var.as<double>(), ctx->d_ref.as<double>(), ctx->d_logc.as<double>(),
-                  ctx->d_logcf.as<double>(), ctx->d_log1mcf.as<double>(), ctx->d_D64.as<double>(),
-                  ctx->d_D32.as<float>(), s);
-    launch_tables_fast(ctx->view(), ctx->fast(), ctx->d_D2.as<float>(), ctx->d_FG.as<float>(), ctx->d_FSG.as<float>(),
-                       ctx->d_SD2.as<float>(), s);
-    ctx->launches += 2;
-    for (int n = 2; n <= smax; ++n) {
-        launch_forest_level(ctx->view(), ctx->fast(), n, max_level_rows[n], ctx->d_FG.as<float>(), ctx->d_FSG.as<float>(), s);
-        ctx->launches++;
-    }
-    launch_forest_fh(ctx->view(), ctx->fast(), max_fh_items, ctx->d_FH.as<float>(), s);
-    ctx->launches++;
-    {   // program tables for the small K of this problem (K^(K-1) rows of 64 bytes; K = 9: 2.75 GB)
-        const char* off = getenv("BAMSE_PROGTAB");          // BAMSE_PROGTAB=0: always decode in the kernel
-        const bool enable = !(off && atoi(off) == 0);
-        const FastProgram* ptrs[KMAX + 1];
-        for (int k = 0; k <= KMAX; ++k) ptrs[k] = nullptr;
-        ctx->have_progtabs = false;
-        for (int c = 0; c < C && enable; ++c) {
-            const int K = K_of_c[c];
-            if (K > PROGTAB_KMAX || ptrs[K]) continue;
-            bamse_ctx::ProgTab& t = ctx->progtab[K];
-            const uint64_t n = ipow_u64(K, K - 1);
-            if (!t.buf.p || t.s != ctx->geom_s[K] || t.sh != ctx->geom_sh[K]) {
-                BAMSE_CUDA_TRY(ctx, t.buf.ensure(sizeof(FastProgram) * n));
-                launch_build_prog_table(make_forest_index(K, ctx->geom_s[K], ctx->geom_sh[K]), n, ctx->d_lut.as<int16_t>(),
-                                        t.buf.as<FastProgram>(), s);
-                ctx->launches++;
-                t.s = ctx->geom_s[K]; t.sh = ctx->geom_sh[K];
-            }
-            ptrs[K] = t.buf.as<FastProgram>();
-            ctx->have_progtabs = true;
-        }
-        BAMSE_CUDA_TRY(ctx, ctx->d_progtabs.ensure(sizeof ptrs));
-        BAMSE_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_progtabs.p, ptrs, sizeof ptrs, cudaMemcpyHostToDevice, s));
-    }
+    int rc = plan_tables(ctx);
+    if (rc) return rc;
+    rc = launch_table_build(ctx);
+    if (rc) return rc;
     BAMSE_CUDA_TRY(ctx, cudaGetLastError());
     BAMSE_CUDA_TRY(ctx, cudaStreamSynchronize(s));   // host staging vectors die at return
     ctx->have_problem = true;
@@ -535,6 +833,15 @@ int bamse_upload_problem(bamse_ctx* ctx, int P, const double* err, int C, int M,
     return BAMSE_OK;
 } catch (...) { return on_exception(ctx, "bamse_upload_problem"); }
 
+int bamse_rebuild_tables(bamse_ctx* ctx) try {
+    CTX_CHECK(ctx);
+    if (!ctx->have_problem) return ctx->fail(BAMSE_ESTATE, "bamse_rebuild_tables: no problem uploaded");
+    const int rc = launch_table_build(ctx);
+    if (rc) return rc;
+    BAMSE_CUDA_TRY(ctx, cudaGetLastError());
+    return BAMSE_OK;
+} catch (...) { return on_exception(ctx, "bamse_rebuild_tables"); }
+
 // ---- internal: score a host vector of items, results to host ----------------------
 static int score_items_host(bamse_ctx* ctx, const std::vector<ScoreItem>& items, int precision, double* out) {
     const size_t n = items.size();
@@ -545,8 +852,11 @@ static int score_items_host(bamse_ctx* ctx, const std::vector<ScoreItem>& items,
     BAMSE_CUDA_TRY(ctx, ctx->d_scores.ensure(sizeof(double) * n * per));
     cudaStream_t s = ctx->stream;
     BAMSE_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_items.p, items.data(), sizeof(ScoreItem) * n, cudaMemcpyHostToDevice, s));
-    if (precision == BAMSE_FP32)
+    if (precision == BAMSE_FP32) {
+        const int rc = ensure_interp(ctx);
+        if (rc) return rc;
         launch_score_items_fast(ctx->view(), ctx->fast(), ctx->d_items.as<ScoreItem>(), (int64_t)n, ctx->d_scores.as<double>(), s);
+    }
     else
         launch_score_items(precision, ctx->view(), ctx->d_items.as<ScoreItem>(), (int64_t)n, ctx->d_scores.as<double>(), s);
     ctx->launches++;
@@ -662,16 +972,28 @@ static int probe_fast_variant(bamse_ctx* ctx) {
 }
 
 // ---- internal: run an enumeration; records land in d_out [P][topk] ----------------
+// fp32 with the pair path: k_enumerate_pairs over the cluster counts that have context tables (regular trees
+// scored, irregular ones listed), k_enumerate_fast in flat mode over that list, k_enumerate_fast in range mode over
+// the cluster counts without a pair path; all of them append to one candidate bag, k_merge_topk reduces it.
 static int enumerate_dev(bamse_ctx* ctx, const double* d_const, const double* d_thr, const uint64_t* d_begin,
                          const uint64_t* d_end, int topk, int precision, double slack_abs, double slack_rel,
                          bamse_record* d_out, double* d_dense_score, double* d_dense_logscre,
                          const Segment* host_seg /* non-NULL: dense single-segment mode */) {
     const int P = ctx->P, C = ctx->C;
     cudaStream_t s = ctx->stream;
+    // which cluster counts go where
+    uint32_t mask_pairs = 0, mask_prog = 0;
+    bool irregular_any = false;
+    for (int K = 1; K <= KMAX; ++K) {
+        if (!ctx->k_present[K] || (host_seg && host_seg->K != K)) continue;
+        if (precision == BAMSE_FP32 && ctx->geom_r[K] > 0) { mask_pairs |= 1u << K; irregular_any |= ctx->pairs[K].n_irregular > 0; }
+        else mask_prog |= 1u << K;
+    }
+    if (precision == BAMSE_FP32 && (mask_prog || irregular_any)) { const int rc = ensure_interp(ctx); if (rc) return rc; }
     if (precision == BAMSE_FP32 && ctx->use_framed < 0 && !ctx->probing) {
         const char* f = getenv("BAMSE_FRAMED");
         if (f) ctx->use_framed = atoi(f) ? 1 : 0;
-        else if (host_seg) ctx->use_framed = 0;   // dense debug ranges: no probe, exponential path
+        else if (host_seg || mask_pairs || !ctx->owner.empty()) ctx->use_framed = 0;   // dense debug ranges / pair path / plan: no probe
         else { int rc = probe_fast_variant(ctx); if (rc) return rc; }
     }
     const int pi = precision == BAMSE_FP64 ? 1 : (precision == BAMSE_FP32 ? 0 : 2);
@@ -679,43 +1001,88 @@ static int enumerate_dev(bamse_ctx* ctx, const double* d_const, const double* d_
     if (precision == BAMSE_FP32) ctx->grid[pi] = enumerate_fast_grid_size(ctx->device, topk, framed, ctx->slots_needed);
     else if (ctx->grid[pi] == 0) ctx->grid[pi] = enumerate_grid_size(precision, ctx->device);
     const int grid = ctx->grid[pi];
-    // work granularity: ~32 chunks per worker (warp for fp32, CTA for the check mode), 1..16 trees
+    if (mask_pairs && ctx->grid_pairs == 0) ctx->grid_pairs = enumerate_pairs_grid_size(ctx->device);
+    // work granularity of the program kernels: ~32 chunks per worker (warp for fp32, CTA for the check mode), 1..16 trees
     const int workers = enumerate_workers(precision, grid);
-    uint64_t trees_upper = 0;
-    if (host_seg) trees_upper = host_seg->n_trees;
-    else {
-        for (int c = 0; c < C; ++c) trees_upper += ipow_u64(ctx->K_of_c[c], ctx->K_of_c[c] - 1);
-        trees_upper = trees_upper * (uint64_t)P / (uint64_t)ctx->shard_world + (uint64_t)P * C;
+    const int workers2 = mask_pairs ? enumerate_pairs_workers(ctx->grid_pairs) : 0;
+    uint64_t trees_prog = 0, trees_pairs = 0, irr_cap = 0;
+    std::vector<unsigned long long> flat_off((size_t)P + 1, 0);
+    if (host_seg) {
+        if (mask_pairs) { trees_pairs = host_seg->n_trees; irr_cap = std::min<uint64_t>(host_seg->n_trees, ctx->pairs[host_seg->K].n_irregular); }
+        else trees_prog = host_seg->n_trees;
+        for (int p = 0; p <= P; ++p) flat_off[p] = p > host_seg->p ? irr_cap : 0;
+    } else {
+        for (int p = 0; p < P; ++p) {
+            flat_off[p] = irr_cap;
+            for (int c = 0; c < C; ++c) {
+                const int K = ctx->K_of_c[c];
+                const uint64_t T = ipow_u64(K, K - 1);
+                const int own = ctx->owner.empty() ? -1 : ctx->owner[(size_t)p * C + c];
+                // upper bound of this rank's trees of (p, c): an interleaved share, the whole range, or nothing
+                const uint64_t mine = own < 0 ? (T + ctx->shard_world - 1) / ctx->shard_world : (own == ctx->shard_rank ? T : 0);
+                if ((mask_pairs >> K) & 1u) { trees_pairs += mine; irr_cap += std::min<uint64_t>(mine, ctx->pairs[K].n_irregular); }
+                else trees_prog += mine;
+            }
+        }
+        flat_off[P] = irr_cap;
+        trees_prog += (uint64_t)P * C;
     }
-    const int chunk = (int)std::min<uint64_t>(16, std::max<uint64_t>(1, trees_upper / ((uint64_t)workers * 32)));
-    const uint64_t chunks_upper = trees_upper / chunk + (uint64_t)P * C + 1;
-    const uint64_t cand_lists = std::min<uint64_t>((uint64_t)workers * P, chunks_upper + workers);
+    const int chunk = (int)std::min<uint64_t>(16, std::max<uint64_t>(1, trees_prog / ((uint64_t)workers * 32)));
+    const int chunk2 = 32;                           // one tree slot per lane
+    const uint64_t chunks_prog = trees_prog / chunk + (uint64_t)P * C + 1;
+    const uint64_t chunks_pairs = trees_pairs / chunk2 + (uint64_t)P * C + 1;
+    uint64_t cand_lists = std::min<uint64_t>((uint64_t)workers * P, chunks_prog + workers);
+    if (mask_pairs) cand_lists += std::min<uint64_t>((uint64_t)workers2 * P, chunks_pairs + workers2) +
+                                  std::min<uint64_t>((uint64_t)workers * P, irr_cap + workers);
     const uint64_t cand_cap = cand_lists * (uint64_t)(topk > 0 ? topk : 0);
     BAMSE_CUDA_TRY(ctx, ctx->d_segs.ensure(sizeof(Segment) * P * C));
+    BAMSE_CUDA_TRY(ctx, ctx->d_segs2.ensure(sizeof(Segment) * P * C));
     const bool fresh_scalars = ctx->d_scalars.p == nullptr;
-    BAMSE_CUDA_TRY(ctx, ctx->d_scalars.ensure(sizeof(uint64_t) * 10));
+    BAMSE_CUDA_TRY(ctx, ctx->d_scalars.ensure(sizeof(uint64_t) * 16));
     uint64_t* scal = ctx->d_scalars.as<uint64_t>();
-    BAMSE_CUDA_TRY(ctx, cudaMemsetAsync(scal, 0, sizeof(uint64_t) * (fresh_scalars ? 10 : 4), s));   // stats [4..8) accumulate until read
+    // [0] chunks (programs) [1] trees [2] next chunk [3] bag cursor [4..8) statistics (accumulate until read)
+    // [8] samples evaluated [10] chunks (pairs) [11] trees [12] next chunk (pairs) [13] next chunk (flat) [14] flat overflow
+    if (fresh_scalars) BAMSE_CUDA_TRY(ctx, cudaMemsetAsync(scal, 0, sizeof(uint64_t) * 16, s));
+    else {
+        BAMSE_CUDA_TRY(ctx, cudaMemsetAsync(scal, 0, sizeof(uint64_t) * 4, s));
+        BAMSE_CUDA_TRY(ctx, cudaMemsetAsync(scal + 10, 0, sizeof(uint64_t) * 6, s));
+    }
     if (topk > 0) BAMSE_CUDA_TRY(ctx, ctx->d_cand.ensure(sizeof(bamse_record) * (size_t)cand_cap));
+    unsigned long long* flat_meta = nullptr;         // [P + 1] region offsets, [P] counts, [P + 1] running sums
+    if (mask_pairs) {
+        BAMSE_CUDA_TRY(ctx, ctx->d_flat.ensure(sizeof(unsigned long long) * std::max<uint64_t>(irr_cap, 1)));
+        BAMSE_CUDA_TRY(ctx, ctx->d_flat_meta.ensure(sizeof(unsigned long long) * (3 * (size_t)P + 2)));
+        flat_meta = ctx->d_flat_meta.as<unsigned long long>();
+        BAMSE_CUDA_TRY(ctx, cudaMemcpyAsync(flat_meta, flat_off.data(), sizeof(unsigned long long) * (P + 1), cudaMemcpyHostToDevice, s));
+        BAMSE_CUDA_TRY(ctx, cudaMemsetAsync(flat_meta + P + 1, 0, sizeof(unsigned long long) * (2 * (size_t)P + 1), s));
+        BAMSE_CUDA_TRY(ctx, ctx->d_lists2.ensure(sizeof(bamse_record) * (size_t)workers2 * (size_t)(topk > 0 ? topk : 1)));
+    }
+    const int32_t* d_owner = ctx->owner.empty() ? nullptr : ctx->d_owner.as<int32_t>();
     EnumWork w;
+    memset(&w, 0, sizeof w);
     if (host_seg) {
         const Segment seg = *host_seg;
-        const uint64_t chunks = (seg.n_trees + chunk - 1) / chunk;
-        BAMSE_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_segs.p, &seg, sizeof seg, cudaMemcpyHostToDevice, s));
-        BAMSE_CUDA_TRY(ctx, cudaMemcpyAsync(scal, &chunks, sizeof chunks, cudaMemcpyHostToDevice, s));
+        const uint64_t chunks = (seg.n_trees + (mask_pairs ? chunk2 : chunk) - 1) / (mask_pairs ? chunk2 : chunk);
+        BAMSE_CUDA_TRY(ctx, cudaMemcpyAsync(mask_pairs ? ctx->d_segs2.p : ctx->d_segs.p, &seg, sizeof seg, cudaMemcpyHostToDevice, s));
+        BAMSE_CUDA_TRY(ctx, cudaMemcpyAsync(mask_pairs ? scal + 10 : scal, &chunks, sizeof chunks, cudaMemcpyHostToDevice, s));
         BAMSE_CUDA_TRY(ctx, cudaStreamSynchronize(s));
         w.n_segs = 1;
         ctx->last_evals = (int64_t)seg.n_trees;
     } else {
-        launch_build_segments(P, C, ctx->d_K.as<int32_t>(), d_const, d_thr, d_begin, d_end, slack_abs, slack_rel,
-                              chunk, ctx->shard_rank, ctx->shard_world, ctx->d_segs.as<Segment>(), scal, scal + 1, s);
-        ctx->launches++;
+        if (mask_prog || !mask_pairs) {
+            launch_build_segments(P, C, ctx->d_K.as<int32_t>(), d_const, d_thr, d_begin, d_end, slack_abs, slack_rel,
+                                  chunk, ctx->shard_rank, ctx->shard_world, mask_pairs ? mask_prog : 0xffffffffu, d_owner,
+                                  ctx->d_segs.as<Segment>(), scal, scal + 1, s);
+            ctx->launches++;
+        }
+        if (mask_pairs) {
+            launch_build_segments(P, C, ctx->d_K.as<int32_t>(), d_const, d_thr, d_begin, d_end, slack_abs, slack_rel,
+                                  chunk2, ctx->shard_rank, ctx->shard_world, mask_pairs, d_owner,
+                                  ctx->d_segs2.as<Segment>(), scal + 10, scal + 11, s);
+            ctx->launches++;
+        }
         w.n_segs = P * C;
     }
-    w.segs = ctx->d_segs.as<Segment>();
-    w.chunk = chunk;
-    w.total_chunks = scal;
-    w.next_chunk = reinterpret_cast<unsigned long long*>(scal + 2);
     w.topk = topk;
     w.cand = ctx->d_cand.as<bamse_record>();
     w.cand_count = reinterpret_cast<unsigned long long*>(scal + 3);
@@ -725,27 +1092,32 @@ static int enumerate_dev(bamse_ctx* ctx, const double* d_const, const double* d_
     w.dense_logscre = d_dense_logscre;
     w.stats = reinterpret_cast<unsigned long long*>(scal + 4);
     w.samples_done = reinterpret_cast<unsigned long long*>(scal + 8);
-    // early exit only where pruned trees cannot matter: top-k enumerations (not dense ranges, not probes)
     w.lists = nullptr;
     if (precision == BAMSE_FP32) {
         BAMSE_CUDA_TRY(ctx, ctx->d_lists.ensure(sizeof(bamse_record) * (size_t)workers * (size_t)(topk > 0 ? topk : 1)));
         w.lists = ctx->d_lists.as<bamse_record>();
     }
+    w.lists2 = ctx->d_lists2.as<bamse_record>();
     w.prog_tabs = (precision == BAMSE_FP32 && ctx->have_progtabs) ? ctx->d_progtabs.as<const FastProgram*>() : nullptr;
+    // early exit only where pruned trees cannot matter: top-k enumerations (not dense ranges, not probes)
     w.early_exit = (ctx->early_exit && !host_seg && !ctx->probing && topk > 0) ? 1 : 0;
+    if (mask_pairs) {
+        w.flat = ctx->d_flat.as<unsigned long long>();
+        w.flat_off = flat_meta;
+        w.flat_cnt = flat_meta + P + 1;
+        w.flat_prefix = flat_meta + 2 * P + 1;
+        w.flat_overflow = reinterpret_cast<unsigned long long*>(scal + 14);
+    }
     // tail splitting: when a worker gets fewer than ~48 single-tree chunks, issue the last `workers`
-    // trees in 2 (or, below 16 chunks per worker, 4) parts over the samples
-    w.split_ways = 1; w.n_split = 0; w.split_acc = nullptr; w.split_cnt = nullptr;
+    // trees in 2 (or, below 16 chunks per worker, 4) parts over the samples; always for the flat list
     const char* no_split = getenv("BAMSE_SPLIT");      // BAMSE_SPLIT=0 disables (A/B measurements)
-    if (precision == BAMSE_FP32 && chunk == 1 && !ctx->probing && ctx->M >= 4 && trees_upper < (uint64_t)workers * 48 &&
-        !(no_split && atoi(no_split) == 0)) {
-        w.split_ways = (ctx->M >= 8 && trees_upper < (uint64_t)workers * 16) ? 4 : 2;
-        w.n_split = (unsigned long long)workers;
-        const size_t bytes = (sizeof(double) + sizeof(int)) * (size_t)workers;
+    const bool split_ok = precision == BAMSE_FP32 && !ctx->probing && ctx->M >= 4 && !(no_split && atoi(no_split) == 0);
+    const bool split_prog = split_ok && chunk == 1 && trees_prog < (uint64_t)workers * 48;
+    const bool split_flat = split_ok && irregular_any;
+    if (split_prog || split_flat) {
+        const size_t bytes = (sizeof(double) + sizeof(int)) * (size_t)workers * 2;
         BAMSE_CUDA_TRY(ctx, ctx->d_split.ensure(bytes));
         BAMSE_CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_split.p, 0, bytes, s));
-        w.split_acc = ctx->d_split.as<double>();
-        w.split_cnt = reinterpret_cast<int*>(ctx->d_split.as<double>() + workers);
     }
     std::pair<cudaEvent_t, cudaEvent_t> ev;
     if (!ctx->ev_free.empty()) { ev = ctx->ev_free.back(); ctx->ev_free.pop_back(); }
@@ -754,11 +1126,54 @@ static int enumerate_dev(bamse_ctx* ctx, const double* d_const, const double* d_
         BAMSE_CUDA_TRY(ctx, cudaEventCreate(&ev.second));
     }
     BAMSE_CUDA_TRY(ctx, cudaEventRecord(ev.first, s));
-    if (precision == BAMSE_FP32) launch_enumerate_fast(ctx->view(), ctx->fast(), w, grid, framed, ctx->slots_needed, s);
-    else launch_enumerate(precision, ctx->view(), w, grid, s);
+    if (mask_pairs) {
+        EnumWork wp = w;
+        wp.segs = ctx->d_segs2.as<Segment>();
+        wp.chunk = chunk2;
+        wp.total_chunks = scal + 10;
+        wp.next_chunk = reinterpret_cast<unsigned long long*>(scal + 12);
+        launch_enumerate_pairs(ctx->view(), ctx->fast(), wp, ctx->grid_pairs, s);
+        ctx->launches++;
+        if (irregular_any) {
+            launch_flat_prefix(P, wp.flat_cnt, wp.flat_off, wp.flat_prefix, s);
+            EnumWork wf = wp;
+            wf.flat_mode = 1;
+            wf.chunk = 1;
+            wf.next_chunk = reinterpret_cast<unsigned long long*>(scal + 13);
+            wf.split_ways = 1;
+            if (split_flat) {
+                wf.split_ways = ctx->M >= 8 ? 4 : 2;
+                wf.n_split = (unsigned long long)workers;
+                wf.split_acc = ctx->d_split.as<double>() + workers;
+                wf.split_cnt = reinterpret_cast<int*>(ctx->d_split.as<double>() + 2 * (size_t)workers) + workers;
+            }
+            launch_enumerate_fast(ctx->view(), ctx->fast(), wf, grid, framed, ctx->slots_needed, s);
+            ctx->launches += 2;
+        }
+    }
+    if (mask_prog || !mask_pairs) {
+        w.segs = ctx->d_segs.as<Segment>();
+        w.chunk = chunk;
+        w.total_chunks = scal;
+        w.next_chunk = reinterpret_cast<unsigned long long*>(scal + 2);
+        w.flat = nullptr;
+        w.split_ways = 1;
+        if (split_prog) {
+            w.split_ways = (ctx->M >= 8 && trees_prog < (uint64_t)workers * 16) ? 4 : 2;
+            w.n_split = (unsigned long long)workers;
+            w.split_acc = ctx->d_split.as<double>();
+            w.split_cnt = reinterpret_cast<int*>(ctx->d_split.as<double>() + 2 * (size_t)workers);
+        }
+        if (precision == BAMSE_FP32) launch_enumerate_fast(ctx->view(), ctx->fast(), w, grid, framed, ctx->slots_needed, s);
+        else launch_enumerate(precision, ctx->view(), w, grid, s);
+        ctx->launches++;
+    }
     BAMSE_CUDA_TRY(ctx, cudaEventRecord(ev.second, s));
     ctx->ev_used.push_back(ev);
-    ctx->launches++;
+    if (ctx->ev_used.size() > 256) {
+        ctx->ev_free.push_back(ctx->ev_used.front());
+        ctx->ev_used.erase(ctx->ev_used.begin());
+    }
     BAMSE_CUDA_TRY(ctx, cudaGetLastError());
     if (topk > 0 && d_out) {
         launch_merge_topk(ctx->d_cand.as<bamse_record>(), reinterpret_cast<unsigned long long*>(scal + 3), cand_cap, P,
@@ -845,14 +1260,16 @@ int bamse_score_topk(bamse_ctx* ctx, const double* clust_const, const double* th
         BAMSE_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_thr.p, threshold, sizeof(double) * P * C, cudaMemcpyHostToDevice, s));
     }
     int64_t evals = 0;
-    for (int c = 0; c < C; ++c) {
-        const int K = ctx->K_of_c[c];
-        const uint64_t T = ipow_u64(K, K - 1);
-        uint64_t b = tree_begin ? tree_begin[c] : 0, e = tree_end ? std::min<uint64_t>(tree_end[c], T) : T;
-        if (b < e && e - b > (uint64_t)ctx->shard_rank)
-            evals += (int64_t)((e - b - ctx->shard_rank + ctx->shard_world - 1) / ctx->shard_world);
-    }
-    evals *= P;
+    for (int p = 0; p < P; ++p)
+        for (int c = 0; c < C; ++c) {
+            const int K = ctx->K_of_c[c];
+            const uint64_t T = ipow_u64(K, K - 1);
+            uint64_t b = tree_begin ? tree_begin[c] : 0, e = tree_end ? std::min<uint64_t>(tree_end[c], T) : T;
+            const int own = ctx->owner.empty() ? -1 : ctx->owner[(size_t)p * C + c];
+            if (own >= 0) { if (own == ctx->shard_rank && b < e) evals += (int64_t)(e - b); }
+            else if (b < e && e - b > (uint64_t)ctx->shard_rank)
+                evals += (int64_t)((e - b - ctx->shard_rank + ctx->shard_world - 1) / ctx->shard_world);
+        }
     if (tree_begin) {
         BAMSE_CUDA_TRY(ctx, ctx->d_begin.ensure(sizeof(uint64_t) * C));
         BAMSE_CUDA_TRY(ctx, ctx->d_end.ensure(sizeof(uint64_t) * C));

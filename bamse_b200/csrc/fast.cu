@@ -22,6 +22,7 @@ __global__ void __launch_bounds__(LD_THREADS) k_tables_fast(ProblemView pv, Fast
     const int p = row / (pv.Kmax * pv.M * pv.C);
     if (k >= pv.K_of_c[c]) return;
     const TableBase tb = ft.tb[p * pv.C + c];
+    if (!tb.mine) return;
     const size_t frow = (size_t)tb.fg_row + (size_t)m * tb.fi.nf + k;
     const int t = threadIdx.x;
     const double log2e = 1.4426950408889634074;
@@ -60,6 +61,15 @@ static __device__ __noinline__ void build_tree_program(int K, uint64_t tree, Fas
     int8_t parent[KMAX];
     decode_tree(K, tree, parent);
     build_program_forest(K, parent, nullptr, *fi, lut, prog);
+}
+
+// geometry the table-driven programs of a clustering pack with (rows of forests with <= s_prog nodes are a
+// prefix of the inside tables, so the row ids agree with the table geometry)
+__device__ __forceinline__ ForestIndex program_index(const TableBase& tb) {
+    ForestIndex f = tb.fi;
+    f.s = tb.s_prog;
+    if (f.sh > f.s) f.sh = f.s;
+    return f;
 }
 
 // Program tables.  The program of a tree depends on (K, tree index) and on the table geometry (s, sh), not on
@@ -170,7 +180,8 @@ __device__ inline double warp_eval_tree(const ProblemView& pv, const FastTables&
 // Message tables, one level (= forests with n nodes) per launch: row <- rows with fewer nodes by its recipe.
 // grid = (ceil(max rows of the level / FAST_WARPS), P * C * M); one warp per row, production convolution.
 __global__ void __launch_bounds__(FAST_THREADS) k_forest_level(ProblemView pv, FastTables ft, int n, float* __restrict__ FG,
-                                                               float* __restrict__ FSG) {
+                                                               float* __restrict__ FSG, int fsg_top,
+                                                               unsigned long long* stats) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int wid = threadIdx.x >> 5;
     int lane = threadIdx.x & 31;
@@ -178,7 +189,7 @@ __global__ void __launch_bounds__(FAST_THREADS) k_forest_level(ProblemView pv, F
     const int pcm = blockIdx.y;
     const int m = pcm % pv.M, pc = pcm / pv.M, c = pc % pv.C;
     const TableBase* tb = ft.tb + pc;
-    if (n > tb->fi.s) return;
+    if (n > tb->fi.s || !tb->mine) return;
     const int i = blockIdx.x * FAST_WARPS + wid;
     if (i >= tb->fi.base[n + 1] - tb->fi.base[n]) return;
     const int row = tb->fi.base[n] + i;
@@ -187,6 +198,7 @@ __global__ void __launch_bounds__(FAST_THREADS) k_forest_level(ProblemView pv, F
     const float add2 = (float)((pv.p0[c] - 6.2383246250395077847550890931236) * 1.4426950408889634074);
     warp_init_guards(ws, lane);
     float* a = ws->vec[0] + GUARD;
+    int chunks = 0, convs = 0;
     if (rec.kind == 1) {                            // one tree: E = D[u] + SG(children forest)
         warp_load_vec(a, FSG + (frow + rec.b) * L, lane);
         warp_add_table(a, ft.D2 + pv.table_offset(pc / pv.C, c, m) + (size_t)rec.u * L, lane);
@@ -194,10 +206,20 @@ __global__ void __launch_bounds__(FAST_THREADS) k_forest_level(ProblemView pv, F
         float* b = ws->vec[1] + GUARD;
         warp_load_vec(a, FG + (frow + rec.a) * L, lane);
         warp_load_vec(b, FG + (frow + rec.b) * L, lane);
-        warp_logconv<false>(a, b, ws->jstar, ws->fa, ws->fb, lane);
+        chunks = warp_logconv<false>(a, b, ws->jstar, ws->fa, ws->fb, lane);
+        convs = 1;
     }
     float4* og = reinterpret_cast<float4*>(FG + (frow + row) * L);
     for (int t = 0; t < 4; ++t) og[lane + 32 * t] = reinterpret_cast<const float4*>(a)[lane + 32 * t];
+    // the scanned message of a top-level forest is only read by the table-driven programs (fsg_top = 1)
+    const bool scan = !(n == tb->fi.s && !fsg_top);
+    if (stats && lane == 0) {
+        atomicAdd(stats + 0, 128ull * chunks + 512ull * convs + (scan ? 59ull * 32 : 0ull));
+        atomicAdd(stats + 1, 128ull * chunks);
+        atomicAdd(stats + 2, (unsigned long long)convs);
+        atomicAdd(stats + 3, scan ? 1ull : 0ull);
+    }
+    if (!scan) return;
     warp_log2cumsum(a, add2, lane);
     float4* os = reinterpret_cast<float4*>(FSG + (frow + row) * L);
     for (int t = 0; t < 4; ++t) os[lane + 32 * t] = reinterpret_cast<const float4*>(a)[lane + 32 * t];
@@ -216,7 +238,7 @@ __global__ void __launch_bounds__(FAST_THREADS) k_forest_fh(ProblemView pv, Fast
     const TableBase* tb = ft.tb + pc;
     const int K = tb->fi.K, nfh = tb->fi.nfh;
     const int i = blockIdx.x * FAST_WARPS + wid;
-    if (i >= K * nfh) return;
+    if (i >= K * nfh || !tb->mine) return;
     const int r = i / nfh, f = i - r * nfh;
     if ((ft.recipes[K][f].mask >> r) & 1) return;   // the root is not part of its own children
     warp_init_guards(ws, lane);
@@ -228,6 +250,122 @@ __global__ void __launch_bounds__(FAST_THREADS) k_forest_fh(ProblemView pv, Fast
     warp_logconv<false>(a, b, ws->jstar, ws->fa, ws->fb, lane);
     float* out = FH + ((size_t)tb->fh_row + ((size_t)m * K + r) * nfh + f) * L;
     for (int t = 0; t < 16; ++t) out[lane + 32 * t] = a[L - 1 - lane - 32 * t] - LOG2_L;
+}
+
+// Scanned messages of the top-level forests, built on demand (the table-driven programs read them; the pair
+// path does not).  grid = (ceil(max rows of level s / FAST_WARPS), P * C * M); one warp per row.
+__global__ void __launch_bounds__(FAST_THREADS) k_forest_scan_top(ProblemView pv, FastTables ft, const float* __restrict__ FG,
+                                                                  float* __restrict__ FSG) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int wid = threadIdx.x >> 5;
+    int lane = threadIdx.x & 31;
+    WarpSmem* ws = pin_shared(reinterpret_cast<WarpSmem*>(smem_raw) + wid);
+    const int pcm = blockIdx.y;
+    const int m = pcm % pv.M, pc = pcm / pv.M, c = pc % pv.C;
+    const TableBase* tb = ft.tb + pc;
+    const int n = tb->fi.s;
+    if (tb->s_prog < n || !tb->mine) return;        // the programs of this clustering never touch the top level
+    const int i = blockIdx.x * FAST_WARPS + wid;
+    if (i >= tb->fi.base[n + 1] - tb->fi.base[n]) return;
+    const size_t row = (size_t)tb->fg_row + (size_t)m * tb->fi.nf + tb->fi.base[n] + i;
+    const float add2 = (float)((pv.p0[c] - 6.2383246250395077847550890931236) * 1.4426950408889634074);
+    float* a = ws->vec[0] + GUARD;
+    warp_load_vec(a, FG + row * L, lane);
+    warp_log2cumsum(a, add2, lane);
+    float4* os = reinterpret_cast<float4*>(FSG + row * L);
+    for (int t = 0; t < 4; ++t) os[lane + 32 * t] = reinterpret_cast<const float4*>(a)[lane + 32 * t];
+}
+
+// Context tables (pairs.cuh), one level (= contexts with q nodes) per launch: with O the outside message at the
+// marked node v (the row of the parent context, 1/L at the root), A[y] = sum_{x >= y} O[x] d_v[x] and H the
+// forest of v's children inside the context,  T[z] = e^p0 / L^2 sum_j g_H[j] A[z + j]  (no H: e^p0 / L A[z]).
+// The suffix sum is the prefix scan of the reversed vector and the correlation the convolution of the reversed
+// (still log-concave) A with g_H, read backwards.  grid = (ceil(max rows / FAST_WARPS), P * C * M); one warp per row.
+__global__ void __launch_bounds__(FAST_THREADS) k_ctx_level(ProblemView pv, FastTables ft, int q, float* __restrict__ T,
+                                                            unsigned long long* stats) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int wid = threadIdx.x >> 5;
+    int lane = threadIdx.x & 31;
+    WarpSmem* ws = pin_shared(reinterpret_cast<WarpSmem*>(smem_raw) + wid);
+    const int pcm = blockIdx.y;
+    const int m = pcm % pv.M, pc = pcm / pv.M, c = pc % pv.C;
+    const TableBase* tb = ft.tb + pc;
+    const PairK* pk = ft.pk + tb->fi.K;
+    if (q > pk->g.r || !tb->mine) return;
+    const uint32_t i = blockIdx.x * FAST_WARPS + wid;
+    if (i >= pk->lbase[q + 1] - pk->lbase[q]) return;
+    const uint32_t row = pk->lbase[q] + i;
+    const CtxRecipe rec = pk->recipes[row];
+    const size_t trow = (size_t)tb->t_row + (size_t)m * pk->nt;
+    const float add2 = (float)((pv.p0[c] - 6.2383246250395077847550890931236) * 1.4426950408889634074);
+    warp_init_guards(ws, lane);
+    float* a = ws->vec[0] + GUARD;
+    const float* D = ft.D2 + pv.table_offset(pc / pv.C, c, m) + (size_t)rec.v * L;
+    if (rec.parent_row >= 0) {
+        const float* O = T + (trow + (size_t)rec.parent_row) * L;
+        for (int t = 0; t < 16; ++t) a[lane + 32 * t] = __ldg(O + (L - 1 - lane - 32 * t)) + __ldg(D + (L - 1 - lane - 32 * t));
+    } else {
+        for (int t = 0; t < 16; ++t) a[lane + 32 * t] = __ldg(D + (L - 1 - lane - 32 * t)) - LOG2_L;
+    }
+    __syncwarp();
+    warp_log2cumsum(a, 0.f, lane);
+    if (rec.h_row >= 0) {
+        float* b = ws->vec[1] + GUARD;
+        warp_load_vec(b, ft.FG + ((size_t)tb->fg_row + (size_t)m * tb->fi.nf + (size_t)rec.h_row) * L, lane);
+        const int chunks = warp_logconv<false>(a, b, ws->jstar, ws->fa, ws->fb, lane);
+        if (stats && lane == 0) {
+            atomicAdd(stats + 0, 128ull * chunks + 512ull);
+            atomicAdd(stats + 1, 128ull * chunks);
+            atomicAdd(stats + 2, 1ull);
+        }
+    }
+    if (stats && lane == 0) { atomicAdd(stats + 0, 59ull * 32); atomicAdd(stats + 3, 1ull); }
+    float* out = T + (trow + row) * L;
+    for (int t = 0; t < 16; ++t) out[lane + 32 * t] = a[L - 1 - lane - 32 * t] + add2;
+}
+
+// Pair table of a cluster count (data independent): the cut of every tree index, the context rows in use.
+__global__ void __launch_bounds__(128) k_build_pair_table(ForestIndex fi, PairGeom g, uint64_t n_trees,
+                                                          const int16_t* __restrict__ lut, uint64_t* __restrict__ out,
+                                                          uint8_t* __restrict__ used, unsigned long long* n_irregular) {
+    const uint64_t tree = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tree >= n_trees) return;
+    int8_t parent[KMAX];
+    decode_tree(fi.K, tree, parent);
+    uint32_t fg = 0, t = 0;
+    const bool reg = classify_tree(fi.K, parent, fi, lut, g, &fg, &t);
+    uint64_t e = 0;
+    if (reg) {
+        used[t] = 1;
+        if (out) {
+            TreeProgram ref;
+            build_program(fi.K, parent, nullptr, &ref);
+            e = pair_entry(fg, t, (uint32_t)ref.scre);
+        }
+    } else atomicAdd(n_irregular, 1ull);
+    if (out) out[tree] = e;
+}
+
+__global__ void __launch_bounds__(256) k_remap_pair_table(uint64_t* __restrict__ tab, uint64_t n_trees,
+                                                          const uint32_t* __restrict__ map) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_trees) return;
+    const uint64_t e = tab[i];
+    if (!e) return;
+    const uint32_t t = (uint32_t)(e >> 24) & 0xffffffu;
+    tab[i] = (e & ~(0xffffffull << 24)) | ((uint64_t)map[t] << 24);
+}
+
+__global__ void k_flat_prefix(int P, const unsigned long long* __restrict__ cnt, const unsigned long long* __restrict__ off,
+                              unsigned long long* __restrict__ prefix) {
+    if (threadIdx.x || blockIdx.x) return;
+    unsigned long long acc = 0;
+    for (int p = 0; p < P; ++p) {
+        prefix[p] = acc;
+        const unsigned long long cap = off[p + 1] - off[p];
+        acc += cnt[p] < cap ? cnt[p] : cap;             // an overflowing region is reported through flat_overflow
+    }
+    prefix[P] = acc;
 }
 
 // a record written by another warp of the CTA (global memory, read after the barrier): bypass L1
@@ -270,7 +408,10 @@ k_enumerate_fast(ProblemView pv, FastTables ft, EnumWork w) {
     warp_init_guards(ws, lane);
     int ntop = 0;                                    // meaningful in lane 0
     int cur_p = -1;
-    const uint64_t total = *w.total_chunks;
+    // flat mode: the work items are the entries of the per-parameter-set lists k_enumerate_pairs left behind
+    // (irregular trees), one tree per chunk
+    const bool flat = w.flat_mode != 0;
+    const uint64_t total = flat ? w.flat_prefix[pv.P] : *w.total_chunks;
     unsigned st_chunks = 0, st_convs = 0, st_scans = 0, st_samples = 0;
 
     auto flush = [&]() {
@@ -304,16 +445,28 @@ k_enumerate_fast(ProblemView pv, FastTables ft, EnumWork w) {
             step = ways;
             chunk = split_from + split_slot;
         }
-        int lo = 0, hi = w.n_segs - 1;
-        while (lo < hi) {
-            const int mid = (lo + hi + 1) >> 1;
-            if (w.segs[mid].first_chunk <= chunk) lo = mid; else hi = mid - 1;
+        int lo = 0, hi = (flat ? pv.P : w.n_segs) - 1;
+        uint64_t flat_tree = 0;
+        if (flat) {
+            while (lo < hi) {                        // parameter set of this entry
+                const int mid = (lo + hi + 1) >> 1;
+                if (w.flat_prefix[mid] <= chunk) lo = mid; else hi = mid - 1;
+            }
+            const unsigned long long ent = w.flat[w.flat_off[lo] + (chunk - w.flat_prefix[lo])];
+            lo = (int)(ent >> 40);
+            flat_tree = ent & ((1ull << 40) - 1ull);
+        } else {
+            while (lo < hi) {
+                const int mid = (lo + hi + 1) >> 1;
+                if (w.segs[mid].first_chunk <= chunk) lo = mid; else hi = mid - 1;
+            }
         }
         const Segment seg = w.segs[lo];
         if (seg.p != cur_p) { flush(); cur_p = seg.p; }
-        const uint64_t off = (chunk - seg.first_chunk) * (uint64_t)w.chunk;
+        const uint64_t off = flat ? (flat_tree - seg.tree_begin) / (uint64_t)seg.stride
+                                  : (chunk - seg.first_chunk) * (uint64_t)w.chunk;
         const uint64_t remain = seg.n_trees - off;
-        const int n = remain < (uint64_t)w.chunk ? (int)remain : w.chunk;
+        const int n = flat ? 1 : (remain < (uint64_t)w.chunk ? (int)remain : w.chunk);
         const FastProgram* tab = w.prog_tabs ? w.prog_tabs[seg.K] : nullptr;
         for (int i = 0; i < n; ++i) {
             const uint64_t tree = seg.tree_begin + (off + i) * (uint64_t)seg.stride;
@@ -321,7 +474,8 @@ k_enumerate_fast(ProblemView pv, FastTables ft, EnumWork w) {
                 if (lane < 16)
                     reinterpret_cast<uint32_t*>(&ws->prog)[lane] = __ldg(reinterpret_cast<const uint32_t*>(tab + tree) + lane);
             } else if (lane == 0) {
-                build_tree_program(seg.K, tree, &ws->prog, &ft.tb[seg.p * pv.C + seg.c].fi, ft.lut);
+                const ForestIndex fip = program_index(ft.tb[seg.p * pv.C + seg.c]);
+                build_tree_program(seg.K, tree, &ws->prog, &fip, ft.lut);
             }
             __syncwarp();
             if (ws->prog.max_sp > SLOTS) asm volatile("trap;");     // a program this instantiation cannot hold: fail loudly
@@ -411,6 +565,229 @@ k_enumerate_fast(ProblemView pv, FastTables ft, EnumWork w) {
     if (w.samples_done && lane == 0) atomicAdd(w.samples_done, (unsigned long long)st_samples);
 }
 
+// ---------------------------------------------------------------------- enumerate: pair path (fp32)
+// log2 sum_i 2^(g[i] + t[i]) of two table rows in global memory, by ONE lane.  Both rows are log-concave, so
+// the sum is unimodal: a binary search on the sign of its slope finds the maximising index, then aligned groups
+// of four terms are added outwards on both sides until the group's term nearest to the maximum is below
+// 2^-THETA of it (the terms decay at least geometrically from there: the same bound as the convolution windows).
+__device__ __forceinline__ float lane_log2dot(const float* __restrict__ g, const float* __restrict__ t, unsigned& groups) {
+    int lo = 0, hi = L - 1;
+#pragma unroll 1
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        const float s0 = __ldg(g + mid) + __ldg(t + mid), s1 = __ldg(g + mid + 1) + __ldg(t + mid + 1);
+        if (s1 >= s0) lo = mid + 1; else hi = mid;
+    }
+    const float4* g4 = reinterpret_cast<const float4*>(g);
+    const float4* t4 = reinterpret_cast<const float4*>(t);
+    const int q0 = lo >> 2;
+    float4 a = __ldg(g4 + q0), b = __ldg(t4 + q0);
+    float x0 = a.x + b.x, x1 = a.y + b.y, x2 = a.z + b.z, x3 = a.w + b.w;
+    const float m0 = fmaxf(fmaxf(x0, x1), fmaxf(x2, x3));
+    if (!(m0 > -CUDART_INF_F)) return -CUDART_INF_F;
+    float sum = (ex2f(x0 - m0) + ex2f(x1 - m0)) + (ex2f(x2 - m0) + ex2f(x3 - m0));
+    unsigned n = 1;
+#pragma unroll 1
+    for (int q = q0 + 1; q < L / 4; ++q) {
+        a = __ldg(g4 + q); b = __ldg(t4 + q);
+        x0 = (a.x + b.x) - m0;
+        if (!(x0 >= -THETA)) break;
+        x1 = (a.y + b.y) - m0; x2 = (a.z + b.z) - m0; x3 = (a.w + b.w) - m0;
+        sum += (ex2f(x0) + ex2f(x1)) + (ex2f(x2) + ex2f(x3));
+        ++n;
+    }
+#pragma unroll 1
+    for (int q = q0 - 1; q >= 0; --q) {
+        a = __ldg(g4 + q); b = __ldg(t4 + q);
+        x3 = (a.w + b.w) - m0;
+        if (!(x3 >= -THETA)) break;
+        x0 = (a.x + b.x) - m0; x1 = (a.y + b.y) - m0; x2 = (a.z + b.z) - m0;
+        sum += (ex2f(x0) + ex2f(x1)) + (ex2f(x2) + ex2f(x3));
+        ++n;
+    }
+    groups += n;
+    return m0 + lg2f(sum);
+}
+
+constexpr int PAIR_WARPS = 8;
+constexpr int PAIR_THREADS = PAIR_WARPS * 32;
+
+// One LANE per tree: persistent warps pull chunks of 32 consecutive tree slots of a segment.  A regular tree is
+// two row ids (pair table, or the cut computed here for cluster counts without a table) and costs one windowed
+// dot product per sample; an irregular tree is appended to the flat list of its parameter set for
+// k_enumerate_fast.  Per-warp top-k lists (global memory) are filled by lane 0 from the lanes that beat the
+// warp's k-th best, and appended to the candidate bag when the parameter set changes and at the end.
+__global__ void __launch_bounds__(PAIR_THREADS, 6) k_enumerate_pairs(ProblemView pv, FastTables ft, EnumWork w) {
+    const int lane = threadIdx.x & 31;
+    const int gw = blockIdx.x * PAIR_WARPS + (threadIdx.x >> 5);
+    const int kcap = w.topk > 0 ? w.topk : 1;
+    bamse_record* list = w.lists2 + (size_t)gw * kcap;
+    int ntop = 0;                                    // meaningful in lane 0
+    int cur_p = -1;
+    double kth = -CUDART_INF;                        // total of the warp's k-th best once the list is full (all lanes)
+    const uint64_t total = *w.total_chunks;
+    unsigned st_groups = 0, st_samples = 0;
+
+    auto flush = [&]() {
+        if (lane == 0 && ntop > 0) {
+            const unsigned long long pos = atomicAdd(w.cand_count, (unsigned long long)ntop);
+            if (pos + ntop <= w.cand_cap)
+                for (int i = 0; i < ntop; ++i) w.cand[pos + i] = list[i];
+            ntop = 0;
+        }
+    };
+
+    for (;;) {
+        unsigned long long chunk = 0;
+        if (lane == 0) chunk = atomicAdd(w.next_chunk, 1ull);
+        chunk = __shfl_sync(0xffffffffu, chunk, 0);
+        if (chunk >= total) break;
+        int lo = 0, hi = w.n_segs - 1;
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (w.segs[mid].first_chunk <= chunk) lo = mid; else hi = mid - 1;
+        }
+        const Segment seg = w.segs[lo];
+        if (seg.p != cur_p) { flush(); cur_p = seg.p; kth = -CUDART_INF; }
+        const uint64_t off = (chunk - seg.first_chunk) * (uint64_t)w.chunk + (uint64_t)lane;
+        const bool valid = off < seg.n_trees;
+        const uint64_t tree = seg.tree_begin + off * (uint64_t)seg.stride;
+        const TableBase* tb = ft.tb + (seg.p * pv.C + seg.c);
+        const PairK* pk = ft.pk + seg.K;
+        uint32_t fg = 0, tr = 0, scre = 0;
+        bool reg = false;
+        if (valid) {
+            if (pk->pair_tab) {
+                const uint64_t e = __ldg(pk->pair_tab + tree);
+                scre = (uint32_t)(e >> 48); fg = (uint32_t)e & 0xffffffu; tr = (uint32_t)(e >> 24) & 0xffffffu;
+                reg = scre != 0;
+            } else if (pk->g.r > 0) {
+                int8_t parent[KMAX];
+                decode_tree(seg.K, tree, parent);
+                reg = classify_tree(seg.K, parent, tb->fi, ft.lut, pk->g, &fg, &tr);
+                if (reg) {
+                    TreeProgram ref;
+                    build_program(seg.K, parent, nullptr, &ref);
+                    scre = (uint32_t)ref.scre;
+                    tr = __ldg(pk->map + tr);
+                }
+            }
+        }
+        // irregular trees: to the flat list of this parameter set (warp-aggregated append)
+        const bool irr = valid && !reg;
+        const unsigned irr_mask = __ballot_sync(0xffffffffu, irr);
+        if (irr_mask) {
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(w.flat_cnt + seg.p, (unsigned long long)__popc(irr_mask));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (irr) {
+                const unsigned long long pos = w.flat_off[seg.p] + base + (unsigned long long)__popc(irr_mask & ((1u << lane) - 1u));
+                if (pos < w.flat_off[seg.p + 1]) w.flat[pos] = ((unsigned long long)lo << 40) | tree;
+                else *w.flat_overflow = 1ull;
+            }
+        }
+        double score = -CUDART_INF, logscre = 0.0;
+        if (reg) {
+            logscre = log((double)scre);
+            double cut = -CUDART_INF;
+            if (w.early_exit) {
+                const double c0 = fmax(seg.threshold, kth - seg.clust_const);
+                cut = c0 - logscre - 1e-3 - 1e-6 * fabs(c0);
+            }
+            const int nf = tb->fi.nf;
+            const float* g = ft.FG + ((size_t)tb->fg_row + fg) * L;
+            const float* t = ft.T + ((size_t)tb->t_row + tr) * L;
+            const size_t gstep = (size_t)nf * L, tstep = (size_t)pk->nt * L;
+            double acc = 0.0;
+#pragma unroll 1
+            for (int m = 0; m < pv.M; ++m) {
+                acc += (double)lane_log2dot(g, t, st_groups) * 0.69314718055994530942;
+                ++st_samples;
+                g += gstep; t += tstep;
+                if (acc < cut) { acc = -CUDART_INF; break; }
+            }
+            score = acc;
+            if (w.dense_score) w.dense_score[off] = score;
+            if (w.dense_logscre) w.dense_logscre[off] = logscre;
+        }
+        if (w.topk > 0) {
+            const double full = score + logscre;
+            const double tot = full + seg.clust_const;
+            unsigned cmask = __ballot_sync(0xffffffffu, reg && full >= seg.threshold && full > -CUDART_INF && tot >= kth);
+            while (cmask) {
+                const int src = __ffs(cmask) - 1;
+                cmask &= cmask - 1;
+                const double r_full = __shfl_sync(0xffffffffu, full, src);
+                const unsigned long long r_tree = __shfl_sync(0xffffffffu, (unsigned long long)tree, src);
+                if (lane == 0) {
+                    bamse_record r;
+                    r.total = r_full + seg.clust_const; r.score = r_full; r.clust = seg.c; r.param = seg.p; r.tree = r_tree;
+                    if (!(ntop == w.topk && !rec_better_f(r, list[w.topk - 1]))) {
+                        int q = ntop < w.topk ? ntop : w.topk - 1;
+                        while (q > 0 && rec_better_f(r, list[q - 1])) { list[q] = list[q - 1]; --q; }
+                        list[q] = r;
+                        if (ntop < w.topk) ++ntop;
+                    }
+                    if (ntop == w.topk) kth = list[w.topk - 1].total;
+                }
+                kth = __shfl_sync(0xffffffffu, kth, 0);
+            }
+        }
+    }
+    flush();
+    // executed-work counters: 4 ex2 per group, 1 lg2 per dot
+    st_groups = __reduce_add_sync(0xffffffffu, st_groups);
+    st_samples = __reduce_add_sync(0xffffffffu, st_samples);
+    if (w.stats && lane == 0) atomicAdd(w.stats + 0, 4ull * st_groups + st_samples);
+    if (w.samples_done && lane == 0) atomicAdd(w.samples_done, (unsigned long long)st_samples);
+}
+
+int enumerate_pairs_grid_size(int device) {
+    int sms = 148, per_sm = 1;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_enumerate_pairs, PAIR_THREADS, 0);
+    if (per_sm < 1) per_sm = 1;
+    return sms * per_sm;
+}
+
+int enumerate_pairs_workers(int grid) { return grid * PAIR_WARPS; }
+
+void launch_enumerate_pairs(const ProblemView& pv, const FastTables& ft, const EnumWork& w, int grid, cudaStream_t s) {
+    k_enumerate_pairs<<<grid, PAIR_THREADS, 0, s>>>(pv, ft, w);
+}
+
+void launch_flat_prefix(int P, const unsigned long long* cnt, const unsigned long long* off, unsigned long long* prefix,
+                        cudaStream_t s) {
+    k_flat_prefix<<<1, 32, 0, s>>>(P, cnt, off, prefix);
+}
+
+void launch_ctx_level(const ProblemView& pv, const FastTables& ft, int q, int max_rows, float* T, unsigned long long* stats,
+                      cudaStream_t s) {
+    if (max_rows <= 0) return;
+    const size_t smem = sizeof(WarpSmem) * FAST_WARPS;
+    cudaFuncSetAttribute(k_ctx_level, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const dim3 grid((unsigned)((max_rows + FAST_WARPS - 1) / FAST_WARPS), (unsigned)(pv.P * pv.C * pv.M));
+    k_ctx_level<<<grid, FAST_THREADS, smem, s>>>(pv, ft, q, T, stats);
+}
+
+void launch_forest_scan_top(const ProblemView& pv, const FastTables& ft, int max_rows, const float* FG, float* FSG,
+                            cudaStream_t s) {
+    if (max_rows <= 0) return;
+    const size_t smem = sizeof(WarpSmem) * FAST_WARPS;
+    cudaFuncSetAttribute(k_forest_scan_top, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const dim3 grid((unsigned)((max_rows + FAST_WARPS - 1) / FAST_WARPS), (unsigned)(pv.P * pv.C * pv.M));
+    k_forest_scan_top<<<grid, FAST_THREADS, smem, s>>>(pv, ft, FG, FSG);
+}
+
+void launch_build_pair_table(const ForestIndex& fi, const PairGeom& g, uint64_t n_trees, const int16_t* d_lut,
+                             uint64_t* out, uint8_t* used, unsigned long long* n_irregular, cudaStream_t s) {
+    k_build_pair_table<<<(unsigned)((n_trees + 127) / 128), 128, 0, s>>>(fi, g, n_trees, d_lut, out, used, n_irregular);
+}
+
+void launch_remap_pair_table(uint64_t* tab, uint64_t n_trees, const uint32_t* d_map, cudaStream_t s) {
+    k_remap_pair_table<<<(unsigned)((n_trees + 255) / 256), 256, 0, s>>>(tab, n_trees, d_map);
+}
+
 static size_t fast_smem_bytes(int topk, bool framed = false, int slots = FAST_SLOTS) {
     const size_t per_warp = framed ? sizeof(WarpSmemT<true, 3>) : (slots == 2 ? sizeof(WarpSmemT<false, 2>) : sizeof(WarpSmemT<false, 3>));
     (void)topk;                                      // the top-k lists live in global memory (EnumWork::lists)
@@ -418,12 +795,12 @@ static size_t fast_smem_bytes(int topk, bool framed = false, int slots = FAST_SL
 }
 
 void launch_forest_level(const ProblemView& pv, const FastTables& ft, int n, int max_rows, float* FG, float* FSG,
-                         cudaStream_t s) {
+                         int fsg_top, unsigned long long* stats, cudaStream_t s) {
     if (max_rows <= 0) return;
     const size_t smem = sizeof(WarpSmem) * FAST_WARPS;
     cudaFuncSetAttribute(k_forest_level, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const dim3 grid((unsigned)((max_rows + FAST_WARPS - 1) / FAST_WARPS), (unsigned)(pv.P * pv.C * pv.M));
-    k_forest_level<<<grid, FAST_THREADS, smem, s>>>(pv, ft, n, FG, FSG);
+    k_forest_level<<<grid, FAST_THREADS, smem, s>>>(pv, ft, n, FG, FSG, fsg_top, stats);
 }
 
 void launch_forest_fh(const ProblemView& pv, const FastTables& ft, int max_items, float* FH, cudaStream_t s) {
@@ -481,7 +858,7 @@ __global__ void __launch_bounds__(FAST_THREADS) k_score_items_fast(ProblemView p
     warp_init_guards(ws, lane);
     const ScoreItem it = items[idx];
     int ok = 1;
-    if (lane == 0) ok = build_program_forest(it.k, it.parent, it.nodes, ft.tb[it.p * pv.C + it.c].fi, ft.lut, &ws->prog) ? 1 : 0;
+    if (lane == 0) ok = build_program_forest(it.k, it.parent, it.nodes, program_index(ft.tb[it.p * pv.C + it.c]), ft.lut, &ws->prog) ? 1 : 0;
     ok = __shfl_sync(0xffffffffu, ok, 0);
     if (!ok) { if (lane == 0) out[idx] = CUDART_NAN; return; }
     unsigned s0 = 0, s1 = 0, s2 = 0;

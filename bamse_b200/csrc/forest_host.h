@@ -97,7 +97,7 @@ inline void default_forest_geometry(int K, int* s, int* sh, int* r = nullptr) {
     else if (K == 3) { *s = 2; *sh = 1; rr = 1; }
     else if (K == 4) { *s = 2; *sh = 2; rr = 2; }
     else if (K == 5) { *s = 3; *sh = 2; rr = 3; }
-    else if (K == 6) { *s = 4; *sh = 2; rr = 3; }
+    else if (K == 6) { *s = 3; *sh = 2; rr = 4; }   // 371 + 846 rows in use (725 convolutions) against 2 246 + 186 (1 220) for (4, 3)
     else if (K == 7) { *s = 4; *sh = 3; rr = 4; }
     else if (K == 8) { *s = 5; *sh = 3; rr = 4; }
     else if (K <= 10) { *s = 5; *sh = 3; rr = 5; }

@@ -41,7 +41,8 @@ __global__ void __launch_bounds__(256) k_build_segments(int P, int C, const int3
                                                         const double* __restrict__ cconst, const double* __restrict__ thr,
                                                         const uint64_t* __restrict__ begin, const uint64_t* __restrict__ end,
                                                         double slack_abs, double slack_rel, int chunk, int shard_rank,
-                                                        int shard_world, Segment* __restrict__ segs,
+                                                        int shard_world, uint32_t k_mask, const int32_t* __restrict__ owner,
+                                                        Segment* __restrict__ segs,
                                                         uint64_t* __restrict__ total_chunks, uint64_t* __restrict__ total_trees) {
     // one thread per (p, c) fills its segment, then thread 0 turns chunk counts into prefix sums
     const int n = P * C;
@@ -53,11 +54,15 @@ __global__ void __launch_bounds__(256) k_build_segments(int P, int C, const int3
         if (e > T) e = T;
         if (b > e) b = e;
         Segment s;
-        s.p = p; s.c = c; s.K = K; s.stride = shard_world;
-        // interleaved shard: indices b + rank, b + rank + world, ... below e
-        const uint64_t span = e - b;
-        s.tree_begin = b + (uint64_t)shard_rank;
-        s.n_trees = span > (uint64_t)shard_rank ? (span - shard_rank + shard_world - 1) / shard_world : 0;
+        s.p = p; s.c = c; s.K = K;
+        // sharding plan: owner < 0 (or no plan) = interleaved over all ranks (indices b + rank, b + rank + world,
+        // ... below e), owner == rank = this rank scores the whole range, any other owner = nothing here
+        const int own = owner ? owner[i] : -1;
+        const int rank = own < 0 ? shard_rank : 0, world = own < 0 ? shard_world : 1;
+        const uint64_t span = (own >= 0 && own != shard_rank) || !((k_mask >> K) & 1u) ? 0 : e - b;
+        s.stride = world;
+        s.tree_begin = b + (uint64_t)rank;
+        s.n_trees = span > (uint64_t)rank ? (span - rank + world - 1) / world : 0;
         s.first_chunk = (s.n_trees + (uint64_t)chunk - 1) / (uint64_t)chunk;   // count for now
         s.clust_const = cconst ? cconst[i] : 0.0;
         double th = thr ? thr[i] : -CUDART_INF;
@@ -81,10 +86,10 @@ __global__ void __launch_bounds__(256) k_build_segments(int P, int C, const int3
 
 void launch_build_segments(int P, int C, const int32_t* d_K_of_c, const double* d_const, const double* d_thr,
                            const uint64_t* d_begin, const uint64_t* d_end, double slack_abs, double slack_rel,
-                           int chunk, int shard_rank, int shard_world, Segment* d_segs, uint64_t* d_total_chunks,
-                           uint64_t* d_total_trees, cudaStream_t s) {
+                           int chunk, int shard_rank, int shard_world, uint32_t k_mask, const int32_t* d_owner,
+                           Segment* d_segs, uint64_t* d_total_chunks, uint64_t* d_total_trees, cudaStream_t s) {
     k_build_segments<<<1, 256, 0, s>>>(P, C, d_K_of_c, d_const, d_thr, d_begin, d_end, slack_abs, slack_rel, chunk,
-                                      shard_rank, shard_world, d_segs, d_total_chunks, d_total_trees);
+                                      shard_rank, shard_world, k_mask, d_owner, d_segs, d_total_chunks, d_total_trees);
 }
 
 // --------------------------------------------------------------------- top-k helper

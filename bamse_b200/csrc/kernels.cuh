@@ -2,6 +2,7 @@
 #pragma once
 #include "common.cuh"
 #include "forest.cuh"
+#include "pairs.cuh"
 
 namespace bamse {
 
@@ -56,6 +57,17 @@ struct EnumWork {
     // fp32 kernel: the workers' private top-k lists, [workers][max(topk, 1)] records in global memory
     // (touched once per tree by one lane; keeping them out of shared memory buys a resident CTA per SM)
     bamse_record* lists;
+    // pair path (pairs.cuh): k_enumerate_pairs scores the regular trees of every segment (one lane per tree) and
+    // appends the irregular ones, as (segment << 40) | tree, to the region of their parameter set in `flat`;
+    // k_flat_prefix turns the per-p counts into running sums, and k_enumerate_fast in flat mode (flat_mode = 1)
+    // takes its work from that list instead of the segments' index ranges
+    unsigned long long* flat;             // NULL: no pair path
+    const unsigned long long* flat_off;   // [P + 1] first slot of every parameter set's region
+    unsigned long long* flat_cnt;         // [P] entries appended (zeroed before launch)
+    unsigned long long* flat_prefix;      // [P + 1] running sums of flat_cnt
+    unsigned long long* flat_overflow;    // set when a region was too small (host checks)
+    int flat_mode;
+    bamse_record* lists2;                 // the pair kernel's per-warp lists
 };
 
 void launch_tables(const ProblemView& pv, const double* d_var, const double* d_ref, const double* d_logc,
@@ -63,8 +75,9 @@ void launch_tables(const ProblemView& pv, const double* d_var, const double* d_r
                    cudaStream_t s);
 void launch_build_segments(int P, int C, const int32_t* d_K_of_c, const double* d_const, const double* d_thr,
                            const uint64_t* d_begin, const uint64_t* d_end, double slack_abs, double slack_rel,
-                           int chunk, int shard_rank, int shard_world, Segment* d_segs, uint64_t* d_total_chunks, uint64_t* d_total_trees,
-                           cudaStream_t s);
+                           int chunk, int shard_rank, int shard_world, uint32_t k_mask /* cluster counts that take part */,
+                           const int32_t* d_owner /* [P][C] sharding plan or NULL */, Segment* d_segs,
+                           uint64_t* d_total_chunks, uint64_t* d_total_trees, cudaStream_t s);
 int enumerate_grid_size(int precision, int device);
 void launch_enumerate(int precision, const ProblemView& pv, const EnumWork& w, int grid, cudaStream_t s);
 void launch_score_items(int precision, const ProblemView& pv, const ScoreItem* d_items, int64_t n,
@@ -79,8 +92,11 @@ struct FastTables;
 void launch_tables_fast(const ProblemView& pv, const FastTables& ft, float* D2, float* FG, float* FSG, float* SD2,
                         cudaStream_t s);
 // level n of the message tables (max_rows = the largest number of n-node forests of any clustering present)
+// fsg_top = 0: the scanned messages of the top level (n == s) are left to launch_forest_scan_top
 void launch_forest_level(const ProblemView& pv, const FastTables& ft, int n, int max_rows, float* FG, float* FSG,
-                         cudaStream_t s);
+                         int fsg_top, unsigned long long* stats /* NULL: no executed-work counters */, cudaStream_t s);
+void launch_forest_scan_top(const ProblemView& pv, const FastTables& ft, int max_rows, const float* FG, float* FSG,
+                            cudaStream_t s);
 // finishing tables (max_items = the largest K * nfh of any clustering present)
 void launch_forest_fh(const ProblemView& pv, const FastTables& ft, int max_items, float* FH, cudaStream_t s);
 int enumerate_fast_grid_size(int device, int topk, bool framed, int slots_needed);
@@ -88,6 +104,19 @@ int enumerate_fast_grid_size(int device, int topk, bool framed, int slots_needed
 void launch_build_prog_table(const ForestIndex& fi, uint64_t n_trees, const int16_t* d_lut, FastProgram* out, cudaStream_t s);
 void launch_enumerate_fast(const ProblemView& pv, const FastTables& ft, const EnumWork& w, int grid, bool framed,
                            int slots_needed, cudaStream_t s);
+// context tables, level q (max_rows = the largest number of q-node contexts of any cluster count present)
+void launch_ctx_level(const ProblemView& pv, const FastTables& ft, int q, int max_rows, float* T, unsigned long long* stats,
+                      cudaStream_t s);
+// pair table of a cluster count: out[tree] = pair_entry (context row in the FULL index space), used[row] = 1 for
+// every context row some regular tree refers to, *n_irregular += irregular trees.  out == NULL: mark only.
+void launch_build_pair_table(const ForestIndex& fi, const PairGeom& g, uint64_t n_trees, const int16_t* d_lut,
+                             uint64_t* out, uint8_t* used, unsigned long long* n_irregular, cudaStream_t s);
+void launch_remap_pair_table(uint64_t* tab, uint64_t n_trees, const uint32_t* d_map, cudaStream_t s);
+int enumerate_pairs_grid_size(int device);
+int enumerate_pairs_workers(int grid);
+void launch_enumerate_pairs(const ProblemView& pv, const FastTables& ft, const EnumWork& w, int grid, cudaStream_t s);
+void launch_flat_prefix(int P, const unsigned long long* cnt, const unsigned long long* off, unsigned long long* prefix,
+                        cudaStream_t s);
 void launch_score_items_fast(const ProblemView& pv, const FastTables& ft, const ScoreItem* d_items, int64_t n,
                              double* d_out, cudaStream_t s);
 

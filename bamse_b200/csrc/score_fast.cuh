@@ -17,6 +17,7 @@
 #include "common.cuh"
 #include "tree_decode.cuh"
 #include "forest.cuh"
+#include "pairs.cuh"
 
 namespace bamse {
 
@@ -39,11 +40,26 @@ constexpr int FR_A = FR_SEG + FR_B;                 // a-window floats of one se
 constexpr float FR_DEV = 50.0f;                     // allowed deviation of M_x from linear inside a block (bits)
 constexpr float FR_MAXR = 30.0f;                    // a factor above 2^FR_MAXR of the centre aborts the frame
 
-// Per (parameter set, clustering): where its sub-forest tables start and how they are indexed (forest.cuh).
+// Per (parameter set, clustering): where its tables start and how they are indexed (forest.cuh, pairs.cuh).
 struct TableBase {
     uint32_t fg_row;     // first row of FG / FSG of (p, c, m = 0); sample m starts fi.nf * m rows later
     uint32_t fh_row;     // first row of FH of (p, c, m = 0, root 0); (m, r) starts (m * K + r) * fi.nfh rows later
-    ForestIndex fi;
+    uint32_t t_row;      // first row of T of (p, c, m = 0); sample m starts PairK::nt rows later
+    int32_t s_prog;      // the table-driven programs pack forests of <= s_prog <= fi.s nodes (16-bit row ids)
+    int32_t mine;        // 0: another rank owns this (p, c) under the sharding plan -- no tables here
+    ForestIndex fi;      // geometry of the inside tables
+};
+
+// Per cluster count: the context tables of the pair path (pairs.cuh).  Only the contexts some tree's cut uses
+// (and the contexts their recipes refer to) are built: `map` sends a context row of the full index space to its
+// compact row, rows are ordered by node count so that a level is a contiguous range.
+struct PairK {
+    PairGeom g;                    // full index space; g.r == 0: no pair path for this cluster count
+    uint32_t nt;                   // compact context rows per (p, c, m)
+    uint32_t lbase[PR_RMAX + 2];   // first compact row of the q-node contexts; lbase[r + 1] = nt
+    const uint32_t* map;           // [g.nt] full row -> compact row (0xffffffff: unused)
+    const CtxRecipe* recipes;      // [nt] compact, parent_row compact
+    const uint64_t* pair_tab;      // [K^(K-1)] pair_entry per tree index (context row compact), NULL: cut in the kernel
 };
 
 struct FastTables {
@@ -53,9 +69,11 @@ struct FastTables {
                          // block are the leaf messages  log2cumsum(D) + p0 - log L       (clustering.py:377)
     const float* FSG;    // scanned messages SG(F) = log2cumsum(G(F)) + p0 - log L
     const float* FH;     // finishing tables FH[r][F][i] = 1 / L^2 * sum_j d_r[i+j] * sg_F[j], forests with <= sh nodes
+    const float* T;      // context tables (pairs.cuh), rows of L
     const TableBase* tb; // [P * C]
     const int16_t* lut;  // forest shape LUT (FT_LUT_SIZE entries)
     const ForestRecipe* const* recipes;   // [KMAX + 1] device arrays, by cluster count
+    const PairK* pk;     // [KMAX + 1]
 };
 
 // ----------------------------------------------------------------------------- warp ops

@@ -16,6 +16,8 @@ FP32 = 0
 FP64 = 1
 FP32_LOGDOMAIN = 2
 OPT_EARLY_EXIT = 1
+OPT_SHARD_PLAN = 2
+OPT_STATS = 3
 KMAX = 12
 TOPK_MAX = 64
 GRID = 512
@@ -74,6 +76,8 @@ def load_library():
     lib.bamse_decode_tree.argtypes = [i32, u64, c_p]
     lib.bamse_upload_problem.restype = i32
     lib.bamse_upload_problem.argtypes = [c_p, i32, c_p, i32, i32, i32, c_p, c_p, c_p]
+    lib.bamse_rebuild_tables.restype = i32
+    lib.bamse_rebuild_tables.argtypes = [c_p]
     lib.bamse_score_list.restype = i32
     lib.bamse_score_list.argtypes = [c_p, i64, c_p, c_p, c_p, i32, c_p]
     lib.bamse_score_range.restype = i32
@@ -86,6 +90,8 @@ def load_library():
     lib.bamse_merge_topk_dev.argtypes = [c_p, c_p, i32, i32, i32, c_p]
     lib.bamse_kernel_time.restype = i32
     lib.bamse_kernel_time.argtypes = [c_p, i32, ctypes.POINTER(dbl), ctypes.POINTER(i64)]
+    lib.bamse_table_time.restype = i32
+    lib.bamse_table_time.argtypes = [c_p, i32, ctypes.POINTER(dbl), ctypes.POINTER(i64)]
     lib.bamse_kernel_stats.restype = i32
     lib.bamse_kernel_stats.argtypes = [c_p, i32, c_p]
     lib.bamse_debug_forest_geometry.restype = i32
@@ -108,9 +114,9 @@ def load_library():
 
 EXPORTED_SYMBOLS = [
     "bamse_abi_version", "bamse_create", "bamse_destroy", "bamse_last_error", "bamse_set_stream", "bamse_set_shard", "bamse_fast_variant", "bamse_set_option", "bamse_samples_evaluated",
-    "bamse_launch_count", "bamse_last_eval_count", "bamse_last_topk_verified", "bamse_last_topk_preselected", "bamse_decode_tree", "bamse_upload_problem",
+    "bamse_launch_count", "bamse_last_eval_count", "bamse_last_topk_verified", "bamse_last_topk_preselected", "bamse_decode_tree", "bamse_upload_problem", "bamse_rebuild_tables",
     "bamse_score_list", "bamse_score_range", "bamse_score_topk", "bamse_enumerate_topk_dev",
-    "bamse_merge_topk_dev", "bamse_kernel_time", "bamse_kernel_stats",
+    "bamse_merge_topk_dev", "bamse_kernel_time", "bamse_table_time", "bamse_kernel_stats",
     "bamse_debug_forest_geometry", "bamse_debug_forest_recipes", "bamse_debug_program",
     "bamse_debug_pair_geometry", "bamse_debug_ctx_recipes", "bamse_debug_classify",
 ]
@@ -199,6 +205,15 @@ class Context(object):
         self._check(self._lib.bamse_kernel_time(self._h, 1 if reset else 0, ctypes.byref(ms), ctypes.byref(n)))
         return ms.value, n.value
 
+    def table_time(self, reset=True):
+        """(summed device ms of the table-building kernels, builds) since the last reset."""
+        ms, n = ctypes.c_double(), ctypes.c_int64()
+        self._check(self._lib.bamse_table_time(self._h, 1 if reset else 0, ctypes.byref(ms), ctypes.byref(n)))
+        return ms.value, n.value
+
+    def set_option(self, option, value):
+        self._check(self._lib.bamse_set_option(self._h, int(option), int(value)))
+
     def kernel_stats(self, reset=True):
         """dict of executed-work counters of the fp32 enumeration kernel since the last reset."""
         out = np.zeros(4, dtype=np.uint64)
@@ -219,6 +234,10 @@ class Context(object):
                                                    _ptr(var), _ptr(ref)))
         self.P, self.C, self.M, self.Kmax = len(err), C, M, Kmax
         self.K_of_c = K_of_c.copy()
+
+    def rebuild_tables(self):
+        """re-derives every table of the resident problem from the counts in device memory (asynchronous)."""
+        self._check(self._lib.bamse_rebuild_tables(self._h))
 
     # ---------------------------------------------------------------- scoring
     def score_list(self, item_clust, item_parent, item_nodes, precision=FP64):

@@ -89,6 +89,14 @@ int bamse_fast_variant(const bamse_ctx* ctx);
  * that never discards a qualifying tree.  Off by default: bench.py's headline scores every sample of
  * every tree.  bamse_samples_evaluated returns the (tree, sample) evaluations since the last reset. */
 #define BAMSE_OPT_EARLY_EXIT 1
+/* BAMSE_OPT_SHARD_PLAN (default 1): with a shard (rank, world > 1) set BEFORE bamse_upload_problem, whole
+ * (parameter set, clustering) pairs are assigned to ranks by estimated cost (tables are built only where they are
+ * needed) and only the most expensive pairs are split over all ranks by interleaved tree index; 0 = split
+ * everything.  Every rank computes the same plan.  The plan belongs to the resident problem: changing the shard
+ * afterwards requires a new upload (scoring calls fail with BAMSE_ESTATE until then).
+ * BAMSE_OPT_STATS (default 0): the table-building kernels also count their executed work (bamse_kernel_stats). */
+#define BAMSE_OPT_SHARD_PLAN 2
+#define BAMSE_OPT_STATS 3
 int bamse_set_option(bamse_ctx* ctx, int option, int value);
 int64_t bamse_samples_evaluated(bamse_ctx* ctx, int reset);
 /* bamse_score_topk selects a short list with the enumeration kernel's arithmetic, re-scores it in fp64 and
@@ -112,6 +120,12 @@ int64_t bamse_launch_count(const bamse_ctx* ctx);
 int bamse_upload_problem(bamse_ctx* ctx, int P, const double* err, int C, int M, int Kmax,
                          const int32_t* K_of_c, const int64_t* var_counts,
                          const int64_t* ref_counts);
+
+/* Rebuilds every derived table of the resident problem from the read counts already in device memory
+ * (what bamse_upload_problem does after its host->device copies): asynchronous on the ctx stream, no host
+ * copies.  bench.py's device-resident `value` calls it every step, so that the table construction -- part of
+ * the work per problem -- is inside the timed region. */
+int bamse_rebuild_tables(bamse_ctx* ctx);
 
 /* ------------------------------------------------------------------ score a list
  * Replaces clustering.get_tree_score(tree, nodes) (clustering.py:87-90) for a batch:
@@ -177,6 +191,10 @@ int64_t bamse_last_eval_count(const bamse_ctx* ctx);
  * the summed elapsed milliseconds and the number of launches since the last reset
  * (synchronises the stream).  reset != 0 clears the accumulator after reading. */
 int bamse_kernel_time(bamse_ctx* ctx, int reset, double* out_ms, int64_t* out_launches);
+
+/* The same for the table-building kernels: every bamse_upload_problem / bamse_rebuild_tables brackets its launches
+ * (binomial tables, inside levels, context levels) by CUDA events; summed milliseconds and number of builds. */
+int bamse_table_time(bamse_ctx* ctx, int reset, double* out_ms, int64_t* out_builds);
 
 /* Executed-work counters of the fp32 enumeration kernel since the last reset:
  * out4 = { MUFU (ex2/lg2) thread-level ops, convolution terms exponentiated,

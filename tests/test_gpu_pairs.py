@@ -1,0 +1,135 @@
+"""The inside x outside pair path (bamse_b200/csrc/pairs.cuh) on the GPU, through the C ABI: against the oracle,
+against the table-driven programs (BAMSE_PAIRS=0 builds the same problem without context tables) and against the
+fp64 check mode, incl. cluster counts whose irregular trees take the flat-list route (K >= 8)."""
+import math
+import os
+
+import numpy as np
+import pytest
+
+import bamse_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+FP32_RTOL = 1e-6
+
+
+@pytest.fixture(scope="module")
+def shim():
+    from bamse_b200 import cuda_shim
+    return cuda_shim
+
+
+@pytest.fixture()
+def ctx(shim):
+    c = shim.Context(0)
+    yield c
+    c.close()
+
+
+def _problem(rng, K, M, cov):
+    frac = np.sort(rng.dirichlet(np.ones(K + 1))[:K])[::-1]
+    n = rng.integers(20, 120, size=K)
+    var = np.zeros((K, M), dtype=np.int64)
+    ref = np.zeros((K, M), dtype=np.int64)
+    for k in range(K):
+        for m in range(M):
+            tot = int(n[k]) * cov
+            v = rng.binomial(tot, min(0.49, frac[k] * rng.uniform(0.6, 1.2) * 0.5 + 0.003))
+            var[k, m], ref[k, m] = v, tot - v
+    return var, ref
+
+
+class programs_only(object):
+    """uploads made inside run without the pair path (the library reads BAMSE_PAIRS at upload time)."""
+
+    def __enter__(self):
+        self.old = os.environ.get("BAMSE_PAIRS")
+        os.environ["BAMSE_PAIRS"] = "0"
+
+    def __exit__(self, *a):
+        if self.old is None:
+            del os.environ["BAMSE_PAIRS"]
+        else:
+            os.environ["BAMSE_PAIRS"] = self.old
+
+
+@pytest.mark.parametrize("K,M,cov", [(2, 2, 50), (3, 3, 200), (4, 2, 1000), (5, 3, 100), (6, 2, 300)])
+def test_all_trees_pairs_vs_oracle_and_programs(ctx, shim, K, M, cov):
+    """every tree of a clustering: pair path == oracle (K <= 5) == programs-only build == fp64 check mode."""
+    rng = np.random.default_rng(100 * K + M)
+    var, ref = _problem(rng, K, M, cov)
+    T = K ** (K - 1)
+    ctx.upload_problem([0.003], [K], var[None], ref[None])
+    s_pair, w_pair = ctx.score_range(0, 0, 0, T, shim.FP32)
+    s64, w64 = ctx.score_range(0, 0, 0, T, shim.FP64)
+    with programs_only():
+        ctx.upload_problem([0.003], [K], var[None], ref[None])
+        s_prog, w_prog = ctx.score_range(0, 0, 0, T, shim.FP32)
+    np.testing.assert_array_equal(w_pair, w64)
+    np.testing.assert_array_equal(w_prog, w64)
+    assert np.max(np.abs(s_pair - s64) / np.abs(s64)) <= FP32_RTOL
+    assert np.max(np.abs(s_prog - s64) / np.abs(s64)) <= FP32_RTOL
+    if K <= 5:
+        D = np.array([[orc.distrib(var[k, m], ref[k, m], 0.003) for m in range(M)] for k in range(K)])
+        for i in range(0, T, max(1, T // 60)):
+            want = orc.tree_score_samples(orc.decode_tree(K, i), D, orc.prior_const(K)).sum()
+            assert abs(s_pair[i] - want) <= FP32_RTOL * abs(want)
+
+
+@pytest.mark.parametrize("K,M,cov", [(7, 3, 200), (8, 2, 400), (9, 2, 100), (10, 2, 2000)])
+def test_random_ranges_pairs_vs_check_mode(ctx, shim, K, M, cov):
+    """runs of consecutive indices all over the index space (regular and irregular trees mixed): pair path +
+    flat list == fp64 check mode within 1e-6, canonizeF weights exact."""
+    rng = np.random.default_rng(7 * K)
+    var, ref = _problem(rng, K, M, cov)
+    ctx.upload_problem([0.003], [K], var[None], ref[None])
+    T = K ** (K - 1)
+    run = 700
+    for b in [0, T - run] + [int(x) for x in rng.integers(0, T - run, size=3)]:
+        s32, w32 = ctx.score_range(0, 0, b, run, shim.FP32)
+        s64, w64 = ctx.score_range(0, 0, b, run, shim.FP64)
+        np.testing.assert_array_equal(w32, w64)
+        assert np.max(np.abs(s32 - s64) / np.abs(s64)) <= FP32_RTOL, (K, b)
+
+
+def test_topk_pairs_equals_programs_and_check_mode(ctx, shim):
+    """a mixed problem (K = 3 ... 8, two parameter sets, thresholds): bamse_score_topk returns the same records
+    with the pair path, without it and in the check mode; early exit does not change them."""
+    rng = np.random.default_rng(5)
+    Ks = [3, 5, 6, 7, 8, 4]
+    M, Kmax = 3, 8
+    var = np.zeros((len(Ks), Kmax, M), dtype=np.int64)
+    ref = np.zeros((len(Ks), Kmax, M), dtype=np.int64)
+    for c, K in enumerate(Ks):
+        v, r = _problem(rng, K, M, 150)
+        var[c, :K], ref[c, :K] = v, r
+    errs = [0.001, 0.01]
+    const = rng.uniform(-5, 5, size=(2, len(Ks)))
+    out = {}
+    for mode in ("pairs", "programs", "check", "pairs_early"):
+        if mode == "programs":
+            with programs_only():
+                ctx.upload_problem(errs, Ks, var, ref)
+        else:
+            ctx.upload_problem(errs, Ks, var, ref)
+        ctx.set_early_exit(mode == "pairs_early")
+        rec, par, cnt = ctx.score_topk(const, None, None, None, topk=6, precision=shim.FP64 if mode == "check" else shim.FP32)
+        ctx.set_early_exit(False)
+        assert ctx.last_topk_verified
+        out[mode] = rec
+    for mode in ("programs", "check", "pairs_early"):
+        np.testing.assert_array_equal(out[mode]["tree"], out["pairs"]["tree"])
+        np.testing.assert_array_equal(out[mode]["clust"], out["pairs"]["clust"])
+        np.testing.assert_allclose(out[mode]["total"], out["pairs"]["total"], rtol=1e-12)
+
+
+def test_rebuild_tables_is_idempotent(ctx, shim):
+    """bamse_rebuild_tables re-derives the same tables from the resident counts."""
+    rng = np.random.default_rng(11)
+    var, ref = _problem(rng, 6, 3, 200)
+    ctx.upload_problem([0.003], [6], var[None], ref[None])
+    a, _ = ctx.score_range(0, 0, 0, 6 ** 5, shim.FP32)
+    ctx.rebuild_tables()
+    b, _ = ctx.score_range(0, 0, 0, 6 ** 5, shim.FP32)
+    np.testing.assert_array_equal(a, b)
