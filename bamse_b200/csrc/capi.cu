@@ -51,8 +51,8 @@ struct bamse_ctx {
     DBuf d_K, d_p0, d_var, d_ref, d_logc, d_logcf, d_log1mcf, d_D64, d_D32, d_D2, d_SD2;
     // sub-forest tables (forest.cuh): message tables FG / FSG, finishing tables FH, per-(p, c) bases, shape LUT,
     // per-K recipes; geometry (s, sh) per cluster count of the resident problem
-    DBuf d_FG, d_FSG, d_FH, d_tb, d_lut, d_recipe_ptrs;
-    struct Recipes { DBuf buf; int s = -1; };
+    DBuf d_FG, d_FSG, d_FH, d_tb, d_lut, d_recipe_ptrs, d_order_ptrs;
+    struct Recipes { DBuf buf, order; int s = -1; };
     Recipes recipes[KMAX + 1];
     int geom_s[KMAX + 1] = {0}, geom_sh[KMAX + 1] = {0}, geom_r[KMAX + 1] = {0};
     // pair path (pairs.cuh), per cluster count: pair table, context map / compact recipes; kept across uploads
@@ -116,6 +116,7 @@ struct bamse_ctx {
         f.T = d_T.as<float>(); f.pk = d_pk.as<PairK>();
         f.tb = d_tb.as<TableBase>(); f.lut = d_lut.as<int16_t>();
         f.recipes = d_recipe_ptrs.as<const ForestRecipe*>();
+        f.level_order = d_order_ptrs.as<const uint32_t*>();
         return f;
     }
     ProblemView view() const {
@@ -199,13 +200,14 @@ static int ensure_pair_state(bamse_ctx* ctx, int K) {
     for (int q = 1; q <= PR_RMAX + 1; ++q) {
         ps.lbase[q] = (uint32_t)comp.size();
         if (q > rK) continue;
-        for (uint32_t i = g.base[q]; i < g.base[q + 1]; ++i) {
-            if (!h_used[i]) continue;
-            map[i] = (uint32_t)comp.size();
-            CtxRecipe c = full[i];
-            if (c.parent_row >= 0) c.parent_row = (int32_t)map[(size_t)c.parent_row];
-            comp.push_back(c);
-        }
+        for (int pass = 0; pass < 2; ++pass)          // rows that need a correlation first: CTAs of one kind
+            for (uint32_t i = g.base[q]; i < g.base[q + 1]; ++i) {
+                if (!h_used[i] || (full[i].h_row >= 0) != (pass == 0)) continue;
+                map[i] = (uint32_t)comp.size();
+                CtxRecipe c = full[i];
+                if (c.parent_row >= 0) c.parent_row = (int32_t)map[(size_t)c.parent_row];
+                comp.push_back(c);
+            }
     }
     ps.lbase[0] = 0;
     ps.nt = (uint32_t)comp.size();
@@ -395,19 +397,25 @@ static int plan_tables(bamse_ctx* ctx) {
     }
     {
         const ForestRecipe* rptrs[KMAX + 1];
+        const uint32_t* optrs[KMAX + 1];
         PairK pks[KMAX + 1];
         memset(pks, 0, sizeof pks);
         for (int K = 0; K <= KMAX; ++K) {
-            rptrs[K] = nullptr;
+            rptrs[K] = nullptr; optrs[K] = nullptr;
             if (K == 0 || !k_present[K]) continue;
             bamse_ctx::Recipes& r = ctx->recipes[K];
             if (!r.buf.p || r.s != ctx->geom_s[K]) {
-                const std::vector<ForestRecipe> rec = make_forest_recipes(make_forest_index(K, ctx->geom_s[K], ctx->geom_sh[K]));
+                const ForestIndex fiK = make_forest_index(K, ctx->geom_s[K], ctx->geom_sh[K]);
+                const std::vector<ForestRecipe> rec = make_forest_recipes(fiK);
+                const std::vector<uint32_t> ord = make_level_order(fiK, rec);
                 BAMSE_CUDA_TRY(ctx, r.buf.ensure(sizeof(ForestRecipe) * rec.size()));
                 BAMSE_CUDA_TRY(ctx, cudaMemcpy(r.buf.p, rec.data(), sizeof(ForestRecipe) * rec.size(), cudaMemcpyHostToDevice));
+                BAMSE_CUDA_TRY(ctx, r.order.ensure(sizeof(uint32_t) * ord.size()));
+                BAMSE_CUDA_TRY(ctx, cudaMemcpy(r.order.p, ord.data(), sizeof(uint32_t) * ord.size(), cudaMemcpyHostToDevice));
                 r.s = ctx->geom_s[K];
             }
             rptrs[K] = r.buf.as<ForestRecipe>();
+            optrs[K] = r.order.as<uint32_t>();
             if (ctx->geom_r[K] > 0) {
                 const bamse_ctx::PairState& ps = ctx->pairs[K];
                 PairK& pk = pks[K];
@@ -421,6 +429,8 @@ static int plan_tables(bamse_ctx* ctx) {
         }
         BAMSE_CUDA_TRY(ctx, ctx->d_recipe_ptrs.ensure(sizeof rptrs));
         BAMSE_CUDA_TRY(ctx, cudaMemcpy(ctx->d_recipe_ptrs.p, rptrs, sizeof rptrs, cudaMemcpyHostToDevice));
+        BAMSE_CUDA_TRY(ctx, ctx->d_order_ptrs.ensure(sizeof optrs));
+        BAMSE_CUDA_TRY(ctx, cudaMemcpy(ctx->d_order_ptrs.p, optrs, sizeof optrs, cudaMemcpyHostToDevice));
         BAMSE_CUDA_TRY(ctx, ctx->d_pk.ensure(sizeof pks));
         BAMSE_CUDA_TRY(ctx, cudaMemcpy(ctx->d_pk.p, pks, sizeof pks, cudaMemcpyHostToDevice));
     }
@@ -575,7 +585,8 @@ void bamse_destroy(bamse_ctx* ctx) {
     for (DBuf* b : bufs) b->release();
     for (auto& t : ctx->progtab) t.buf.release();
     for (auto& t : ctx->pairs) { t.tab.release(); t.map.release(); t.recipes.release(); }
-    for (auto& r : ctx->recipes) r.buf.release();
+    for (auto& r : ctx->recipes) { r.buf.release(); r.order.release(); }
+    ctx->d_order_ptrs.release();
     ctx->d_progtabs.release();
     for (auto* v : {&ctx->ev_used, &ctx->ev_build_used, &ctx->ev_free})
         for (auto& ev : *v) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
@@ -600,6 +611,14 @@ int bamse_set_shard(bamse_ctx* ctx, int rank, int world) {
 }
 
 int bamse_fast_variant(const bamse_ctx* ctx) { return ctx ? ctx->use_framed : -1; }
+
+int bamse_get_shard_plan(bamse_ctx* ctx, int32_t* out_owner) {
+    CTX_CHECK(ctx);
+    if (!ctx->have_problem) return ctx->fail(BAMSE_ESTATE, "bamse_get_shard_plan: no problem uploaded");
+    if (!out_owner) return ctx->fail(BAMSE_EINVAL, "bamse_get_shard_plan: out_owner is NULL");
+    for (size_t i = 0; i < (size_t)ctx->P * ctx->C; ++i) out_owner[i] = ctx->owner.empty() ? -1 : ctx->owner[i];
+    return BAMSE_OK;
+}
 
 int bamse_set_option(bamse_ctx* ctx, int option, int value) {
     CTX_CHECK(ctx);

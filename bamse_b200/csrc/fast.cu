@@ -7,15 +7,16 @@
 namespace bamse {
 
 // ---------------------------------------------------------------- fast tables (fp64 -> fp32 log2)
-// one CTA (256 threads) per (p, c, m, k): EL = logcumsum(D) + p0 - log L and SEL = logcumsum(EL) + p0 - log L
-// computed in fp64 natural logs, stored as fp32 base-2 logs in rows k of the FG / FSG blocks (single-node
-// forests), plus D2 and the root table SD2 in the [P][C][M][Kmax] layout.
-__global__ void __launch_bounds__(LD_THREADS) k_tables_fast(ProblemView pv, FastTables ft, float* __restrict__ D2,
-                                                            float* __restrict__ FG, float* __restrict__ FSG,
-                                                            float* __restrict__ SD2) {
-    __shared__ double v[L];
-    __shared__ double scratch[LD_THREADS / 32];
-    const int row = blockIdx.x;
+// one WARP per (p, c, m, k): D2 = the binomial table as fp32 base-2 logs (rounded from the fp64 table), the leaf
+// message EL = log2cumsum(D2) + p0 - log L and its scan SEL in rows k of the FG / FSG blocks (single-node forests),
+// and the root table SD2 (suffix sums of d: the prefix scan of the reversed table), all with the production scan.
+__global__ void __launch_bounds__(FAST_THREADS) k_tables_fast(ProblemView pv, FastTables ft, float* __restrict__ D2,
+                                                              float* __restrict__ FG, float* __restrict__ FSG,
+                                                              float* __restrict__ SD2) {
+    __shared__ __align__(16) float vbuf[FAST_WARPS][L];
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int row = blockIdx.x * FAST_WARPS + wid;
+    if (row >= pv.P * pv.C * pv.M * pv.Kmax) return;
     const int k = row % pv.Kmax;
     const int m = (row / pv.Kmax) % pv.M;
     const int c = (row / (pv.Kmax * pv.M)) % pv.C;
@@ -24,34 +25,35 @@ __global__ void __launch_bounds__(LD_THREADS) k_tables_fast(ProblemView pv, Fast
     const TableBase tb = ft.tb[p * pv.C + c];
     if (!tb.mine) return;
     const size_t frow = (size_t)tb.fg_row + (size_t)m * tb.fi.nf + k;
-    const int t = threadIdx.x;
-    const double log2e = 1.4426950408889634074;
-    const double add = pv.p0[c] - 6.2383246250395077847550890931236;
+    const float add2 = (float)((pv.p0[c] - 6.2383246250395077847550890931236) * 1.4426950408889634074);
     const double* src = pv.D64 + (size_t)row * L;
-    v[t] = src[t]; v[t + LD_THREADS] = src[t + LD_THREADS];
-    D2[(size_t)row * L + t] = (float)(v[t] * log2e);
-    D2[(size_t)row * L + t + LD_THREADS] = (float)(v[t + LD_THREADS] * log2e);
-    __syncthreads();
-    block_logcumsum<double>(v, add, scratch);
-    FG[frow * L + t] = (float)(v[t] * log2e);
-    FG[frow * L + t + LD_THREADS] = (float)(v[t + LD_THREADS] * log2e);
-    __syncthreads();
-    block_logcumsum<double>(v, add, scratch);
-    FSG[frow * L + t] = (float)(v[t] * log2e);
-    FSG[frow * L + t + LD_THREADS] = (float)(v[t + LD_THREADS] * log2e);
-    // suffix sums of d: the prefix scan of the reversed table; SD = e^p0 / L^2 * sum_{x>=i} d[x]
-    __syncthreads();
-    v[t] = src[L - 1 - t]; v[t + LD_THREADS] = src[L - 1 - t - LD_THREADS];
-    __syncthreads();
-    block_logcumsum<double>(v, add - 6.2383246250395077847550890931236, scratch);
-    SD2[(size_t)row * L + (L - 1 - t)] = (float)(v[t] * log2e);
-    SD2[(size_t)row * L + (L - 1 - t - LD_THREADS)] = (float)(v[t + LD_THREADS] * log2e);
+    float* v = vbuf[wid];
+    float d[16];
+#pragma unroll
+    for (int t = 0; t < 16; ++t) {
+        d[t] = (float)(src[lane + 32 * t] * 1.4426950408889634074);
+        v[lane + 32 * t] = d[t];
+        D2[(size_t)row * L + lane + 32 * t] = d[t];
+    }
+    __syncwarp();
+    warp_log2cumsum(v, add2, lane);
+    for (int t = 0; t < 4; ++t) reinterpret_cast<float4*>(FG + frow * L)[lane + 32 * t] = reinterpret_cast<const float4*>(v)[lane + 32 * t];
+    warp_log2cumsum(v, add2, lane);
+    for (int t = 0; t < 4; ++t) reinterpret_cast<float4*>(FSG + frow * L)[lane + 32 * t] = reinterpret_cast<const float4*>(v)[lane + 32 * t];
+    // SD[i] = e^p0 / L^2 * sum_{x >= i} d[x]
+    __syncwarp();
+#pragma unroll
+    for (int t = 0; t < 16; ++t) v[L - 1 - lane - 32 * t] = d[t];
+    __syncwarp();
+    warp_log2cumsum(v, add2 - LOG2_L, lane);
+#pragma unroll
+    for (int t = 0; t < 16; ++t) SD2[(size_t)row * L + lane + 32 * t] = v[L - 1 - lane - 32 * t];
 }
 
 void launch_tables_fast(const ProblemView& pv, const FastTables& ft, float* D2, float* FG, float* FSG, float* SD2,
                         cudaStream_t s) {
     const int rows = pv.P * pv.C * pv.M * pv.Kmax;
-    k_tables_fast<<<rows, LD_THREADS, 0, s>>>(pv, ft, D2, FG, FSG, SD2);
+    k_tables_fast<<<(rows + FAST_WARPS - 1) / FAST_WARPS, FAST_THREADS, 0, s>>>(pv, ft, D2, FG, FSG, SD2);
 }
 
 // Index -> program: executed by one lane once per tree.  Kept out of line so that its (large) code does not
@@ -100,6 +102,11 @@ struct alignas(16) WarpSmemT {
 };
 using WarpSmem = WarpSmemT<false>;
 // dynamic shared memory: FAST_WARPS x WarpSmem
+// the table builders hold two vectors (one convolution): 22.7 KB per CTA, 10 CTAs (40 warps) per SM
+using BuildSmem = WarpSmemT<false, 2>;
+#ifndef BAMSE_BUILD_CTAS
+#define BAMSE_BUILD_CTAS 10
+#endif
 
 // Keeps the warp's shared-memory base in a register: without the opaque move ptxas
 // rematerialises it from S2R tid / cta-id several times per convolution pass.
@@ -179,20 +186,21 @@ __device__ inline double warp_eval_tree(const ProblemView& pv, const FastTables&
 
 // Message tables, one level (= forests with n nodes) per launch: row <- rows with fewer nodes by its recipe.
 // grid = (ceil(max rows of the level / FAST_WARPS), P * C * M); one warp per row, production convolution.
-__global__ void __launch_bounds__(FAST_THREADS) k_forest_level(ProblemView pv, FastTables ft, int n, float* __restrict__ FG,
+__global__ void __launch_bounds__(FAST_THREADS, BAMSE_BUILD_CTAS) k_forest_level(ProblemView pv, FastTables ft, int n, float* __restrict__ FG,
                                                                float* __restrict__ FSG, int fsg_top,
                                                                unsigned long long* stats) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int wid = threadIdx.x >> 5;
     int lane = threadIdx.x & 31;
-    WarpSmem* ws = pin_shared(reinterpret_cast<WarpSmem*>(smem_raw) + wid);
+    BuildSmem* ws = pin_shared(reinterpret_cast<BuildSmem*>(smem_raw) + wid);
     const int pcm = blockIdx.y;
     const int m = pcm % pv.M, pc = pcm / pv.M, c = pc % pv.C;
     const TableBase* tb = ft.tb + pc;
     if (n > tb->fi.s || !tb->mine) return;
     const int i = blockIdx.x * FAST_WARPS + wid;
     if (i >= tb->fi.base[n + 1] - tb->fi.base[n]) return;
-    const int row = tb->fi.base[n] + i;
+    // rows of a level in the order "convolutions first": the warps of a CTA get rows of the same kind
+    const int row = (int)ft.level_order[tb->fi.K][tb->fi.base[n] + i];
     const ForestRecipe rec = ft.recipes[tb->fi.K][row];
     const size_t frow = (size_t)tb->fg_row + (size_t)m * tb->fi.nf;
     const float add2 = (float)((pv.p0[c] - 6.2383246250395077847550890931236) * 1.4426950408889634074);
@@ -228,11 +236,11 @@ __global__ void __launch_bounds__(FAST_THREADS) k_forest_level(ProblemView pv, F
 // Finishing tables FH[r][F][i] = 1/L^2 * sum_j d_r[i+j] * sg_F[j]: the correlation of D[r] with the scanned
 // message of F is the convolution of the REVERSED (still log-concave) D[r] with it, read backwards.
 // grid = (ceil(max K * nfh / FAST_WARPS), P * C * M); one warp per (root, forest) with the production convolution.
-__global__ void __launch_bounds__(FAST_THREADS) k_forest_fh(ProblemView pv, FastTables ft, float* __restrict__ FH) {
+__global__ void __launch_bounds__(FAST_THREADS, BAMSE_BUILD_CTAS) k_forest_fh(ProblemView pv, FastTables ft, float* __restrict__ FH) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int wid = threadIdx.x >> 5;
     int lane = threadIdx.x & 31;
-    WarpSmem* ws = pin_shared(reinterpret_cast<WarpSmem*>(smem_raw) + wid);
+    BuildSmem* ws = pin_shared(reinterpret_cast<BuildSmem*>(smem_raw) + wid);
     const int pcm = blockIdx.y;
     const int m = pcm % pv.M, pc = pcm / pv.M, c = pc % pv.C;
     const TableBase* tb = ft.tb + pc;
@@ -259,7 +267,7 @@ __global__ void __launch_bounds__(FAST_THREADS) k_forest_scan_top(ProblemView pv
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int wid = threadIdx.x >> 5;
     int lane = threadIdx.x & 31;
-    WarpSmem* ws = pin_shared(reinterpret_cast<WarpSmem*>(smem_raw) + wid);
+    BuildSmem* ws = pin_shared(reinterpret_cast<BuildSmem*>(smem_raw) + wid);
     const int pcm = blockIdx.y;
     const int m = pcm % pv.M, pc = pcm / pv.M, c = pc % pv.C;
     const TableBase* tb = ft.tb + pc;
@@ -281,12 +289,12 @@ __global__ void __launch_bounds__(FAST_THREADS) k_forest_scan_top(ProblemView pv
 // forest of v's children inside the context,  T[z] = e^p0 / L^2 sum_j g_H[j] A[z + j]  (no H: e^p0 / L A[z]).
 // The suffix sum is the prefix scan of the reversed vector and the correlation the convolution of the reversed
 // (still log-concave) A with g_H, read backwards.  grid = (ceil(max rows / FAST_WARPS), P * C * M); one warp per row.
-__global__ void __launch_bounds__(FAST_THREADS) k_ctx_level(ProblemView pv, FastTables ft, int q, float* __restrict__ T,
+__global__ void __launch_bounds__(FAST_THREADS, BAMSE_BUILD_CTAS) k_ctx_level(ProblemView pv, FastTables ft, int q, float* __restrict__ T,
                                                             unsigned long long* stats) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int wid = threadIdx.x >> 5;
     int lane = threadIdx.x & 31;
-    WarpSmem* ws = pin_shared(reinterpret_cast<WarpSmem*>(smem_raw) + wid);
+    BuildSmem* ws = pin_shared(reinterpret_cast<BuildSmem*>(smem_raw) + wid);
     const int pcm = blockIdx.y;
     const int m = pcm % pv.M, pc = pcm / pv.M, c = pc % pv.C;
     const TableBase* tb = ft.tb + pc;
@@ -764,7 +772,7 @@ void launch_flat_prefix(int P, const unsigned long long* cnt, const unsigned lon
 void launch_ctx_level(const ProblemView& pv, const FastTables& ft, int q, int max_rows, float* T, unsigned long long* stats,
                       cudaStream_t s) {
     if (max_rows <= 0) return;
-    const size_t smem = sizeof(WarpSmem) * FAST_WARPS;
+    const size_t smem = sizeof(BuildSmem) * FAST_WARPS;
     cudaFuncSetAttribute(k_ctx_level, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const dim3 grid((unsigned)((max_rows + FAST_WARPS - 1) / FAST_WARPS), (unsigned)(pv.P * pv.C * pv.M));
     k_ctx_level<<<grid, FAST_THREADS, smem, s>>>(pv, ft, q, T, stats);
@@ -773,7 +781,7 @@ void launch_ctx_level(const ProblemView& pv, const FastTables& ft, int q, int ma
 void launch_forest_scan_top(const ProblemView& pv, const FastTables& ft, int max_rows, const float* FG, float* FSG,
                             cudaStream_t s) {
     if (max_rows <= 0) return;
-    const size_t smem = sizeof(WarpSmem) * FAST_WARPS;
+    const size_t smem = sizeof(BuildSmem) * FAST_WARPS;
     cudaFuncSetAttribute(k_forest_scan_top, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const dim3 grid((unsigned)((max_rows + FAST_WARPS - 1) / FAST_WARPS), (unsigned)(pv.P * pv.C * pv.M));
     k_forest_scan_top<<<grid, FAST_THREADS, smem, s>>>(pv, ft, FG, FSG);
@@ -797,7 +805,7 @@ static size_t fast_smem_bytes(int topk, bool framed = false, int slots = FAST_SL
 void launch_forest_level(const ProblemView& pv, const FastTables& ft, int n, int max_rows, float* FG, float* FSG,
                          int fsg_top, unsigned long long* stats, cudaStream_t s) {
     if (max_rows <= 0) return;
-    const size_t smem = sizeof(WarpSmem) * FAST_WARPS;
+    const size_t smem = sizeof(BuildSmem) * FAST_WARPS;
     cudaFuncSetAttribute(k_forest_level, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const dim3 grid((unsigned)((max_rows + FAST_WARPS - 1) / FAST_WARPS), (unsigned)(pv.P * pv.C * pv.M));
     k_forest_level<<<grid, FAST_THREADS, smem, s>>>(pv, ft, n, FG, FSG, fsg_top, stats);
@@ -805,7 +813,7 @@ void launch_forest_level(const ProblemView& pv, const FastTables& ft, int n, int
 
 void launch_forest_fh(const ProblemView& pv, const FastTables& ft, int max_items, float* FH, cudaStream_t s) {
     if (max_items <= 0) return;
-    const size_t smem = sizeof(WarpSmem) * FAST_WARPS;
+    const size_t smem = sizeof(BuildSmem) * FAST_WARPS;
     cudaFuncSetAttribute(k_forest_fh, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const dim3 grid((unsigned)((max_items + FAST_WARPS - 1) / FAST_WARPS), (unsigned)(pv.P * pv.C * pv.M));
     k_forest_fh<<<grid, FAST_THREADS, smem, s>>>(pv, ft, FH);

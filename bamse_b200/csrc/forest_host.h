@@ -85,6 +85,19 @@ inline std::vector<ForestRecipe> make_forest_recipes(const ForestIndex& fi) {
     return out;
 }
 
+// processing order of the rows of every level: convolution rows (kind 2) first, so that the warps of a
+// table-building CTA get rows of the same cost
+inline std::vector<uint32_t> make_level_order(const ForestIndex& fi, const std::vector<ForestRecipe>& rec) {
+    std::vector<uint32_t> out((size_t)fi.nf);
+    for (int n = 1; n <= fi.s; ++n) {
+        size_t w = (size_t)fi.base[n];
+        for (int pass = 0; pass < 2; ++pass)
+            for (int row = fi.base[n]; row < fi.base[n + 1]; ++row)
+                if ((rec[(size_t)row].kind == 2) == (pass == 0)) out[w++] = (uint32_t)row;
+    }
+    return out;
+}
+
 // Default table geometry per cluster count: inside tables for forests of <= s nodes, finishing tables of the
 // table-driven programs for forests of <= sh nodes, context tables (pairs.cuh) for contexts of <= r nodes
 // (r = 0: no pair path).  Chosen by counting rows against the trees they serve (brute force over all trees

@@ -73,6 +73,8 @@ struct FastTables {
     const TableBase* tb; // [P * C]
     const int16_t* lut;  // forest shape LUT (FT_LUT_SIZE entries)
     const ForestRecipe* const* recipes;   // [KMAX + 1] device arrays, by cluster count
+    const uint32_t* const* level_order;   // [KMAX + 1]: per cluster count, the rows of every level with the
+                                          // convolution rows first (position base[n] + i -> row)
     const PairK* pk;     // [KMAX + 1]
 };
 

@@ -58,6 +58,8 @@ def load_library():
     lib.bamse_set_stream.argtypes = [c_p, c_p]
     lib.bamse_set_shard.restype = i32
     lib.bamse_set_shard.argtypes = [c_p, i32, i32]
+    lib.bamse_get_shard_plan.restype = i32
+    lib.bamse_get_shard_plan.argtypes = [c_p, c_p]
     lib.bamse_fast_variant.restype = i32
     lib.bamse_fast_variant.argtypes = [c_p]
     lib.bamse_set_option.restype = i32
@@ -113,7 +115,7 @@ def load_library():
 
 
 EXPORTED_SYMBOLS = [
-    "bamse_abi_version", "bamse_create", "bamse_destroy", "bamse_last_error", "bamse_set_stream", "bamse_set_shard", "bamse_fast_variant", "bamse_set_option", "bamse_samples_evaluated",
+    "bamse_abi_version", "bamse_create", "bamse_destroy", "bamse_last_error", "bamse_set_stream", "bamse_set_shard", "bamse_get_shard_plan", "bamse_fast_variant", "bamse_set_option", "bamse_samples_evaluated",
     "bamse_launch_count", "bamse_last_eval_count", "bamse_last_topk_verified", "bamse_last_topk_preselected", "bamse_decode_tree", "bamse_upload_problem", "bamse_rebuild_tables",
     "bamse_score_list", "bamse_score_range", "bamse_score_topk", "bamse_enumerate_topk_dev",
     "bamse_merge_topk_dev", "bamse_kernel_time", "bamse_table_time", "bamse_kernel_stats",
@@ -234,6 +236,12 @@ class Context(object):
                                                    _ptr(var), _ptr(ref)))
         self.P, self.C, self.M, self.Kmax = len(err), C, M, Kmax
         self.K_of_c = K_of_c.copy()
+
+    def shard_plan(self):
+        """[P][C] owning rank of every (parameter set, clustering), -1 = split over all ranks."""
+        out = np.empty((self.P, self.C), dtype=np.int32)
+        self._check(self._lib.bamse_get_shard_plan(self._h, _ptr(out)))
+        return out
 
     def rebuild_tables(self):
         """re-derives every table of the resident problem from the counts in device memory (asynchronous)."""

@@ -261,8 +261,9 @@ def config_dict(args, work, world):
             "clusterings": len(work["clusts"]), "K_histogram": {str(k): v for k, v in sorted(ks.items())},
             "param_sets": len(work["errs"]), "samples": work["M"],
             "evals_per_step": work["n_evals_per_param"] * len(work["errs"]),
-            "parallelism": "interleaved tree-index sharding x%d + all-gather top-k" % world,
-            "l2": "256 MiB write between steps inside the timed region (inputs are KBs; kernel is SM-pipe bound)"}
+            "parallelism": "x%d: whole (parameter set, clustering) pairs per rank by estimated cost, the most expensive "
+                           "ones split by interleaved tree index; one all-gather of the top-k records" % world,
+            "l2": "256 MiB write between steps inside the timed region; every step rebuilds its tables (GBs) from the counts"}
 
 
 # ------------------------------------------------------------------------------------------
@@ -331,6 +332,12 @@ def main():
         for c, (o, n) in zip(clusts, spans):
             c._apply_order(s[o:o + n] if n else [])
     Ks, var, ref, Kmax = _pack_problem(clusts)
+    # ---- shard BEFORE the upload: the library plans which rank owns which (parameter set, clustering) -- whole
+    #      pairs where it can, interleaved tree indices for the most expensive ones -- and builds tables only
+    #      for what this rank scores (bamse_set_shard + BAMSE_OPT_SHARD_PLAN)
+    ctx.set_shard(rank, world)
+    if args.emulate_shard_of > 1 and world == 1:
+        ctx.set_shard(0, args.emulate_shard_of)
     ctx.upload_problem(errs, Ks, var, ref)            # all P parameter sets resident from here on
     cand = [[[-1] for _ in clusts] for _ in range(P)]
     for n in range(1, Kmax):
@@ -349,14 +356,8 @@ def main():
     thr = np.array([[sc[p, p * C + ci] + math.log(canonizeF(cand[p][ci])['scre']) for ci in range(C)] for p in range(P)])
     const = np.array([[c.cluster_prior + c.maxlikelihood for c in clusts] for _ in range(P)])
 
-    # ---- shard: rank r scores the tree indices r, r + W, r + 2W, ... of every clustering
-    #      (interleaved, so every rank sees the same mix of tree shapes; bamse_set_shard)
-    ctx.set_shard(rank, world)
     tb = te = None
     total_evals = work["n_evals_per_param"] * P
-    if args.emulate_shard_of > 1 and world == 1:
-        ctx.set_shard(0, args.emulate_shard_of)
-        total_evals = sum(-(-int(k) ** (int(k) - 1) // args.emulate_shard_of) for k in Ks) * P
     topk = args.topk
 
     # ---- device-resident state for the `value` measurement
@@ -374,8 +375,12 @@ def main():
     # fp32 selection keeps trees within `slack` nats below the fp64 threshold (the host API re-scores in fp64)
     slack = 0.0 if prec == cuda_shim.FP64 else 1e-3
 
-    def step_resident():
+    def step_resident(tables=True):
         flush.fill_(1)
+        if tables:
+            # every derived table of the problem from the read counts resident in HBM: part of the work per
+            # problem (the sub-forest / context tables ARE the memoised convolutions), so inside the timed region
+            ctx.rebuild_tables()
         ctx.enumerate_topk_dev(d_const.data_ptr(), d_thr.data_ptr(), None, None, topk, prec, slack,
                                d_local.data_ptr())
         if world > 1:
@@ -425,6 +430,7 @@ def main():
         step_resident()
     barrier()
     ctx.kernel_time(reset=True)
+    ctx.table_time(reset=True)
     ctx.kernel_stats(reset=True)
     launches0 = ctx.launch_count
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -437,14 +443,42 @@ def main():
     sampler.end()
     ms = ev0.elapsed_time(ev1)
     kern_ms, kern_n = ctx.kernel_time(reset=True)
-    stats = ctx.kernel_stats(reset=True)
+    tab_ms, tab_n = ctx.table_time(reset=True)
+    ctx.kernel_stats(reset=True)
     variant = ctx.fast_variant
     launches = ctx.launch_count - launches0
-    t = torch.tensor([ms, kern_ms / max(1, kern_n)], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms, kern_ms / max(1, kern_n), tab_ms / max(1, tab_n)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max, kern_ms_max = float(t[0]), float(t[1])
+    ms_max, kern_ms_max, tab_ms_max = float(t[0]), float(t[1]), float(t[2])
     final = d_final.cpu().numpy().view(cuda_shim.RECORD_DTYPE).reshape(P, topk)
+
+    # ---- executed-work counters of one (untimed) step: table builders + enumeration kernels of this rank
+    ctx.set_option(cuda_shim.OPT_STATS, 1)
+    step_resident()
+    barrier()
+    stats = ctx.kernel_stats(reset=True)
+    ctx.set_option(cuda_shim.OPT_STATS, 0)
+    ctx.kernel_time(reset=True)
+    ctx.table_time(reset=True)
+
+    # ---- extra (not the headline): enumeration alone over tables that stay resident between steps
+    for _ in range(2):
+        step_resident(tables=False)
+    barrier()
+    ee0, ee1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ee0.record()
+    for _ in range(args.steps):
+        step_resident(tables=False)
+    ee1.record()
+    barrier()
+    t_en = torch.tensor([ee0.elapsed_time(ee1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_en, op=dist.ReduceOp.MAX)
+    enum_only = {"value": total_evals * args.steps / (float(t_en[0]) / 1e3), "unit": UNIT,
+                 "ms_per_step": float(t_en[0]) / args.steps,
+                 "note": "tables kept from the previous step (NOT the headline: a new problem always pays its tables)"}
+    ctx.kernel_time(reset=True)
 
     # ---- extra (not the headline): the same resident pass with the exact sample-level early exit
     #      (BAMSE_OPT_EARLY_EXIT) -- trees are resolved, not all of their samples are scored
@@ -528,21 +562,27 @@ def main():
             terms += n_c * share
             xu += x * share
             flops += f * share
-        kernel_s = kern_ms_max / 1e3
+        # the step's own kernels: table builders (k_tables*, k_forest_level, k_ctx_level) + enumeration
+        # (k_enumerate_pairs, k_enumerate_fast); both groups are event-timed inside the library
+        kernel_s = (kern_ms_max + tab_ms_max) / 1e3
         if args.precision == "fp64":
+            kernel_s = kern_ms_max / 1e3
             bound, achieved, peak, unit = "fp64-pipe", 40 * terms / kernel_s / 1e12, peaks["fp64_tflops"], "TFLOP/s"
             kname, executed = "k_enumerate_logdomain<double>", None
         else:
             bound, achieved, peak, unit = "xu (MUFU ex2/lg2)", xu / kernel_s / 1e12, peaks["xu_tops"], "Tops/s"
-            kname = "k_enumerate_fast<framed=%s>" % ("true" if variant == 1 else "false")
-            ex = stats["mufu_ops"] / max(1, kern_n) / kernel_s / 1e12     # this rank's executed MUFU ops per second
+            kname = "table builders (k_forest_level, k_ctx_level) + k_enumerate_pairs / k_enumerate_fast"
+            ex = stats["mufu_ops"] / kernel_s / 1e12     # this rank's executed MUFU ops of one step per second
             executed = {"xu_tops": ex, "xu_pipe_frac": ex / peaks["xu_tops"],
-                        "conv_terms_executed_per_launch": stats["conv_terms"] / max(1, kern_n),
-                        "conv_terms_algorithmic_per_launch": terms,
+                        "mufu_ops_per_step": stats["mufu_ops"], "convolutions_per_step": stats["convs"],
+                        "conv_terms_executed_per_step": stats["conv_terms"],
+                        "conv_terms_algorithmic_per_step": terms,
+                        "table_build_ms": tab_ms_max, "enumeration_ms": kern_ms_max,
                         "note": "achieved/frac use the ALGORITHMIC op count (SURVEY 8d: every term of every "
-                                "convolution); the kernel exponentiates only the terms within 2^-26 of each "
-                                "output's maximum (log-concavity), so frac can exceed 1; xu_pipe_frac is the "
-                                "XU pipe utilisation of what actually executed"}
+                                "convolution of every tree); sub-forest / context tables memoise the convolutions "
+                                "across trees and only terms within 2^-26 of an output's maximum are exponentiated, "
+                                "so frac exceeds 1 by orders of magnitude; xu_pipe_frac is the XU pipe utilisation "
+                                "of what actually executed (table builders + enumeration kernels, event-timed)"}
         traffic = None
         try:
             with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
@@ -553,7 +593,7 @@ def main():
             pass
         roofline = {"bound": bound, "achieved": achieved, "peak": peak, "unit": unit, "frac": achieved / peak,
                     "traffic": traffic, "peak_source": peaks["source"], "kernel": kname,
-                    "kernel_ms_per_launch": kern_ms_max, "executed": executed,
+                    "kernel_ms_per_launch": 1e3 * kernel_s, "executed": executed,
                     "hbm": hbm_evidence(int(h2d), traffic, kernel_s)}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
@@ -562,6 +602,7 @@ def main():
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                         "ms_per_step": 1e3 * e2e_s / e2e_steps, "agrees_with_resident_path": bool(same)},
                 "gpu_launches": int(launches), "roofline": roofline, "search_mode_extra": search,
+                "enumeration_only_extra": enum_only,
                 "best": {"total": float(final["total"][0, 0]), "clust": int(final["clust"][0, 0]),
                          "tree": int(final["tree"][0, 0])}}
         if world == 1 and not args.no_cpu_baseline:

@@ -77,6 +77,9 @@ int bamse_set_stream(bamse_ctx* ctx, void* cuda_stream);
  * so that every rank sees the same mix of tree shapes).  Default (0, 1) = everything.
  * bamse_score_range is not affected. */
 int bamse_set_shard(bamse_ctx* ctx, int rank, int world);
+/* The sharding plan of the resident problem: out_owner [P][C] = the rank that scores the whole (p, c), or -1 when
+ * its tree indices are split over all ranks (also when there is no plan). */
+int bamse_get_shard_plan(bamse_ctx* ctx, int32_t* out_owner);
 /* Which instantiation of the fp32 enumeration kernel the resident problem uses: 0 = exponential
  * (MUFU) path only, 1 = with the linear-domain "framed" path, -1 = not decided yet.  Decided by a
  * ~1 ms timing probe on the first enumeration of a problem (BAMSE_FRAMED=0/1 overrides). */

@@ -133,3 +133,62 @@ def test_rebuild_tables_is_idempotent(ctx, shim):
     ctx.rebuild_tables()
     b, _ = ctx.score_range(0, 0, 0, 6 ** 5, shim.FP32)
     np.testing.assert_array_equal(a, b)
+
+
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_shard_plan_ranks_together_equal_one_gpu(shim, world):
+    """the sharding plan on ONE device: `world` contexts, each planned as rank r of `world` (whole clusterings per
+    rank, the most expensive ones split by interleaved index), score disjoint shares whose union is every tree;
+    the merged top-k equals the unsharded one, record for record, and every rank's eval counts add up."""
+    from bamse_b200.multigpu import merge_records
+    rng = np.random.default_rng(77)
+    Ks = [6, 6, 6, 5, 5, 4, 7, 3, 6, 5, 2]
+    M, Kmax = 3, 7
+    var = np.zeros((len(Ks), Kmax, M), dtype=np.int64)
+    ref = np.zeros((len(Ks), Kmax, M), dtype=np.int64)
+    for c, K in enumerate(Ks):
+        v, r = _problem(rng, K, M, 120)
+        var[c, :K], ref[c, :K] = v, r
+    errs = [0.002, 0.02]
+    const = rng.uniform(-3, 3, size=(2, len(Ks)))
+    total = 2 * sum(K ** (K - 1) for K in Ks)
+    with shim.Context(0) as one:
+        one.upload_problem(errs, Ks, var, ref)
+        want, _, _ = one.score_topk(const, None, None, None, topk=7, precision=shim.FP32)
+        assert one.last_eval_count == total
+    parts, evals, owners = [], 0, []
+    for r in range(world):
+        with shim.Context(0) as c:
+            c.set_shard(r, world)
+            c.upload_problem(errs, Ks, var, ref)
+            owners.append(c.shard_plan())
+            rec, _, _ = c.score_topk(const, None, None, None, topk=7, precision=shim.FP32)
+            evals += c.last_eval_count
+            parts.append(rec)
+    for o in owners[1:]:
+        np.testing.assert_array_equal(o, owners[0])          # every rank computes the same plan
+    assert (owners[0] >= 0).any()                             # some whole (p, c) pairs are owned ...
+    assert set(np.unique(owners[0])) <= set(range(-1, world))
+    assert evals == total
+    got = merge_records(np.stack(parts), 7)
+    np.testing.assert_array_equal(got["tree"], want["tree"])
+    np.testing.assert_array_equal(got["clust"], want["clust"])
+    np.testing.assert_allclose(got["total"], want["total"], rtol=1e-12)
+
+
+def test_changing_the_shard_of_a_planned_problem_needs_a_new_upload(ctx, shim):
+    rng = np.random.default_rng(3)
+    Ks = [5, 5, 4, 5]
+    var = np.zeros((4, 5, 2), dtype=np.int64)
+    ref = np.zeros((4, 5, 2), dtype=np.int64)
+    for c, K in enumerate(Ks):
+        v, r = _problem(rng, K, 2, 100)
+        var[c, :K], ref[c, :K] = v, r
+    ctx.set_shard(1, 2)
+    ctx.upload_problem([0.003], Ks, var, ref)
+    ctx.score_topk(np.zeros((1, 4)), topk=3)
+    ctx.set_shard(0, 1)
+    with pytest.raises(shim.BamseCudaError):
+        ctx.score_topk(np.zeros((1, 4)), topk=3)
+    ctx.upload_problem([0.003], Ks, var, ref)
+    ctx.score_topk(np.zeros((1, 4)), topk=3)
