@@ -7,6 +7,7 @@
 #include <cstring>
 #include <cstdlib>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "kernels.cuh"
@@ -191,10 +192,31 @@ static int ensure_pair_state(bamse_ctx* ctx, int K) {
     unsigned long long n_irr = 0;
     memcpy(&n_irr, h_used.data() + used_bytes, sizeof n_irr);
     used.release();
-    const std::vector<CtxRecipe> full = make_ctx_recipes(fi, g);
-    // a row in use needs the context its recipe starts from; parents have fewer nodes, i.e. smaller row ids
-    for (size_t i = g.nt; i-- > 0;)
-        if (h_used[i] && full[i].parent_row >= 0) h_used[(size_t)full[i].parent_row] = 1;
+    // recipes of the rows in use only (K = 10: 2.4 M of 10.6 M), level by level from the largest contexts down: a
+    // row in use needs the context its recipe starts from, which has fewer nodes; worker threads split each level
+    std::vector<CtxRecipe> full((size_t)g.nt);
+    {
+        unsigned n_thr = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+        for (int q = rK; q >= 1; --q) {
+            const uint32_t lo = g.base[q], hi = g.base[q + 1];
+            if (hi - lo < 20000) n_thr = 1;
+            auto work = [&](uint32_t a, uint32_t b) {
+                for (uint32_t i = a; i < b; ++i) if (h_used[i]) full[i] = ctx_recipe_of_row(fi, g, i);
+            };
+            if (n_thr == 1) work(lo, hi);
+            else {
+                std::vector<std::thread> pool;
+                const uint32_t step = (hi - lo + n_thr - 1) / n_thr;
+                for (unsigned t = 0; t < n_thr; ++t) {
+                    const uint32_t a = lo + t * step, b = std::min(hi, a + step);
+                    if (a < b) pool.emplace_back(work, a, b);
+                }
+                for (auto& th : pool) th.join();
+            }
+            for (uint32_t i = lo; i < hi; ++i)
+                if (h_used[i] && full[i].parent_row >= 0) h_used[(size_t)full[i].parent_row] = 1;
+        }
+    }
     std::vector<uint32_t> map(g.nt, 0xffffffffu);
     std::vector<CtxRecipe> comp;
     for (int q = 1; q <= PR_RMAX + 1; ++q) {
@@ -325,12 +347,12 @@ static int plan_tables(bamse_ctx* ctx) {
         if (const char* g = getenv("BAMSE_TABLE_GB")) budget = atof(g) * 1e9;
     }
     std::vector<TableBase> tbs((size_t)P * C);
-    size_t fg_rows = 0, fh_rows = 0, t_rows = 0;
+    size_t fg_rows = 0, fsg_rows = 0, fh_rows = 0, t_rows = 0;
     for (;;) {
         for (int K = 1; K <= KMAX; ++K)
             if (k_present[K] && ctx->geom_r[K] > 0) { const int rc = ensure_pair_state(ctx, K); if (rc) return rc; }
         make_shard_plan(ctx);
-        fg_rows = fh_rows = t_rows = 0;
+        fg_rows = fsg_rows = fh_rows = t_rows = 0;
         double per_k[KMAX + 1] = {0.0};
         for (int p = 0; p < P; ++p)
             for (int c = 0; c < C; ++c) {
@@ -339,22 +361,28 @@ static int plan_tables(bamse_ctx* ctx) {
                 t.fi = make_forest_index(K, ctx->geom_s[K], ctx->geom_sh[K]);
                 t.s_prog = program_forest_s(K, ctx->geom_s[K]);
                 t.mine = ctx->owner.empty() || ctx->owner[(size_t)p * C + c] < 0 || ctx->owner[(size_t)p * C + c] == ctx->shard_rank;
-                t.fg_row = (uint32_t)fg_rows; t.fh_row = (uint32_t)fh_rows; t.t_row = (uint32_t)t_rows;
+                t.fg_row = (uint32_t)fg_rows; t.fsg_row = (uint32_t)fsg_rows; t.fh_row = (uint32_t)fh_rows; t.t_row = (uint32_t)t_rows;
+                // scanned messages: of every forest the programs may push (<= s_prog nodes) and of the children
+                // forests the inside recipes read (< s nodes)
+                t.nfsg = t.fi.base[std::min(t.fi.s, std::max(t.s_prog, t.fi.s - 1)) + 1];
                 if (!t.mine) continue;
-                const size_t a = (size_t)M * t.fi.nf, b = (size_t)M * K * t.fi.nfh;
+                const size_t a = (size_t)M * t.fi.nf, a2 = (size_t)M * t.nfsg, b = (size_t)M * K * t.fi.nfh;
                 const size_t tt = ctx->geom_r[K] > 0 ? (size_t)M * ctx->pairs[K].nt : 0;
-                fg_rows += a; fh_rows += b; t_rows += tt;
-                per_k[K] += (double)(2 * a + b + tt) * L * sizeof(float);
+                fg_rows += a; fsg_rows += a2; fh_rows += b; t_rows += tt;
+                per_k[K] += (double)(a + a2 + b + tt) * L * sizeof(float);
             }
-        const double bytes = (double)(2 * fg_rows + fh_rows + t_rows) * L * sizeof(float);
+        const double bytes = (double)(fg_rows + fsg_rows + fh_rows + t_rows) * L * sizeof(float);
         ctx->table_bytes = bytes;
         if ((bytes <= budget && fg_rows < 0xffffffffull && fh_rows < 0xffffffffull && t_rows < 0xffffffffull) || (env_s && env_sh)) break;
         int worst = 0;                                 // step the geometry of the hungriest cluster count down
         for (int K = 1; K <= KMAX; ++K) if (per_k[K] > per_k[worst]) worst = K;
         bool stepped = false;
-        if (worst && ctx->geom_r[worst] > 0) {         // first give up the pair path of that cluster count
-            ctx->geom_r[worst] = 0;
-            ctx->geom_s[worst] = program_forest_s(worst, ctx->geom_s[worst]);
+        if (worst && ctx->geom_r[worst] > 0) {         // smaller contexts first (more irregular trees), then no pair path
+            if (ctx->geom_s[worst] + ctx->geom_r[worst] > worst) --ctx->geom_r[worst];
+            else {
+                ctx->geom_r[worst] = 0;
+                ctx->geom_s[worst] = program_forest_s(worst, ctx->geom_s[worst]);
+            }
             stepped = true;
         } else if (worst) stepped = reduce_forest_geometry(&ctx->geom_s[worst], &ctx->geom_sh[worst]);
         if (!stepped) {
@@ -387,7 +415,7 @@ static int plan_tables(bamse_ctx* ctx) {
     ctx->fh_rows = fh_rows;
     ctx->interp_ready = false;
     BAMSE_CUDA_TRY(ctx, ctx->d_FG.ensure(sizeof(float) * std::max<size_t>(fg_rows, 1) * L));
-    BAMSE_CUDA_TRY(ctx, ctx->d_FSG.ensure(sizeof(float) * std::max<size_t>(fg_rows, 1) * L));
+    BAMSE_CUDA_TRY(ctx, ctx->d_FSG.ensure(sizeof(float) * std::max<size_t>(fsg_rows, 1) * L));
     BAMSE_CUDA_TRY(ctx, ctx->d_T.ensure(sizeof(float) * std::max<size_t>(t_rows, 1) * L));
     BAMSE_CUDA_TRY(ctx, ctx->d_tb.ensure(sizeof(TableBase) * tbs.size()));
     BAMSE_CUDA_TRY(ctx, cudaMemcpy(ctx->d_tb.p, tbs.data(), sizeof(TableBase) * tbs.size(), cudaMemcpyHostToDevice));
@@ -611,6 +639,25 @@ int bamse_set_shard(bamse_ctx* ctx, int rank, int world) {
 }
 
 int bamse_fast_variant(const bamse_ctx* ctx) { return ctx ? ctx->use_framed : -1; }
+
+int bamse_debug_pair_stats(bamse_ctx* ctx, int K, int s, int r, int64_t* out4) try {
+    CTX_CHECK(ctx);
+    if (K < 2 || K > KMAX || s < 1 || s > FT_SMAX || r < 1 || r > PR_RMAX || r - 1 > s || s + r < K || !out4)
+        return ctx->fail(BAMSE_EINVAL, "bamse_debug_pair_stats: bad geometry");
+    if (!ctx->d_lut.p) {
+        BAMSE_CUDA_TRY(ctx, ctx->d_lut.ensure(sizeof(int16_t) * FT_LUT_SIZE));
+        BAMSE_CUDA_TRY(ctx, cudaMemcpy(ctx->d_lut.p, forest_lut().lut.data(), sizeof(int16_t) * FT_LUT_SIZE, cudaMemcpyHostToDevice));
+    }
+    ctx->have_problem = false;                       // the resident problem may have been planned with another geometry
+    ctx->geom_s[K] = s; ctx->geom_r[K] = r;
+    const int rc = ensure_pair_state(ctx, K);
+    if (rc) return rc;
+    out4[0] = make_forest_index(K, s, 1).nf;
+    out4[1] = make_pair_geom(K, s, r).nt;
+    out4[2] = ctx->pairs[K].nt;
+    out4[3] = (int64_t)ctx->pairs[K].n_irregular;
+    return BAMSE_OK;
+} catch (...) { return on_exception(ctx, "bamse_debug_pair_stats"); }
 
 int bamse_get_shard_plan(bamse_ctx* ctx, int32_t* out_owner) {
     CTX_CHECK(ctx);

@@ -25,6 +25,7 @@ __global__ void __launch_bounds__(FAST_THREADS) k_tables_fast(ProblemView pv, Fa
     const TableBase tb = ft.tb[p * pv.C + c];
     if (!tb.mine) return;
     const size_t frow = (size_t)tb.fg_row + (size_t)m * tb.fi.nf + k;
+    const size_t srow = (size_t)tb.fsg_row + (size_t)m * tb.nfsg + k;
     const float add2 = (float)((pv.p0[c] - 6.2383246250395077847550890931236) * 1.4426950408889634074);
     const double* src = pv.D64 + (size_t)row * L;
     float* v = vbuf[wid];
@@ -39,7 +40,7 @@ __global__ void __launch_bounds__(FAST_THREADS) k_tables_fast(ProblemView pv, Fa
     warp_log2cumsum(v, add2, lane);
     for (int t = 0; t < 4; ++t) reinterpret_cast<float4*>(FG + frow * L)[lane + 32 * t] = reinterpret_cast<const float4*>(v)[lane + 32 * t];
     warp_log2cumsum(v, add2, lane);
-    for (int t = 0; t < 4; ++t) reinterpret_cast<float4*>(FSG + frow * L)[lane + 32 * t] = reinterpret_cast<const float4*>(v)[lane + 32 * t];
+    for (int t = 0; t < 4; ++t) reinterpret_cast<float4*>(FSG + srow * L)[lane + 32 * t] = reinterpret_cast<const float4*>(v)[lane + 32 * t];
     // SD[i] = e^p0 / L^2 * sum_{x >= i} d[x]
     __syncwarp();
 #pragma unroll
@@ -146,6 +147,7 @@ __device__ inline double warp_eval_tree(const ProblemView& pv, const FastTables&
     for (int m = m_begin; m < pv.M; m += m_step) {
         const size_t base = pv.table_offset(p, c, m);
         const size_t frow = (size_t)fg_row + (size_t)m * nf;
+        const size_t srow = (size_t)tb->fsg_row + (size_t)m * tb->nfsg;
         ++done;
         int sp = 0;                                  // stack position == slot (convolution is in place)
         for (int i = 0; i < n_ops; ++i) {
@@ -153,7 +155,7 @@ __device__ inline double warp_eval_tree(const ProblemView& pv, const FastTables&
             const int arg = ws->prog.arg[i];
             if (op == FOP_PUSH_G || op == FOP_PUSH_SG) {
                 float* dst = ws->vec[sp] + GUARD;
-                warp_load_vec(dst, (op == FOP_PUSH_G ? ft.FG : ft.FSG) + (frow + (size_t)arg) * L, lane);
+                warp_load_vec(dst, op == FOP_PUSH_G ? ft.FG + (frow + (size_t)arg) * L : ft.FSG + (srow + (size_t)arg) * L, lane);
                 ++sp;
             } else if (op == FOP_SCAN) {
                 warp_log2cumsum(ws->vec[sp - 1] + GUARD, add2, lane);
@@ -203,12 +205,13 @@ __global__ void __launch_bounds__(FAST_THREADS, BAMSE_BUILD_CTAS) k_forest_level
     const int row = (int)ft.level_order[tb->fi.K][tb->fi.base[n] + i];
     const ForestRecipe rec = ft.recipes[tb->fi.K][row];
     const size_t frow = (size_t)tb->fg_row + (size_t)m * tb->fi.nf;
+    const size_t srow = (size_t)tb->fsg_row + (size_t)m * tb->nfsg;
     const float add2 = (float)((pv.p0[c] - 6.2383246250395077847550890931236) * 1.4426950408889634074);
     warp_init_guards(ws, lane);
     float* a = ws->vec[0] + GUARD;
     int chunks = 0, convs = 0;
     if (rec.kind == 1) {                            // one tree: E = D[u] + SG(children forest)
-        warp_load_vec(a, FSG + (frow + rec.b) * L, lane);
+        warp_load_vec(a, FSG + (srow + rec.b) * L, lane);
         warp_add_table(a, ft.D2 + pv.table_offset(pc / pv.C, c, m) + (size_t)rec.u * L, lane);
     } else {                                        // several trees: the first one (*) the rest
         float* b = ws->vec[1] + GUARD;
@@ -220,7 +223,7 @@ __global__ void __launch_bounds__(FAST_THREADS, BAMSE_BUILD_CTAS) k_forest_level
     float4* og = reinterpret_cast<float4*>(FG + (frow + row) * L);
     for (int t = 0; t < 4; ++t) og[lane + 32 * t] = reinterpret_cast<const float4*>(a)[lane + 32 * t];
     // the scanned message of a top-level forest is only read by the table-driven programs (fsg_top = 1)
-    const bool scan = !(n == tb->fi.s && !fsg_top);
+    const bool scan = !(n == tb->fi.s && !fsg_top) && row < tb->nfsg;
     if (stats && lane == 0) {
         atomicAdd(stats + 0, 128ull * chunks + 512ull * convs + (scan ? 59ull * 32 : 0ull));
         atomicAdd(stats + 1, 128ull * chunks);
@@ -229,7 +232,7 @@ __global__ void __launch_bounds__(FAST_THREADS, BAMSE_BUILD_CTAS) k_forest_level
     }
     if (!scan) return;
     warp_log2cumsum(a, add2, lane);
-    float4* os = reinterpret_cast<float4*>(FSG + (frow + row) * L);
+    float4* os = reinterpret_cast<float4*>(FSG + (srow + row) * L);
     for (int t = 0; t < 4; ++t) os[lane + 32 * t] = reinterpret_cast<const float4*>(a)[lane + 32 * t];
 }
 
@@ -254,7 +257,7 @@ __global__ void __launch_bounds__(FAST_THREADS, BAMSE_BUILD_CTAS) k_forest_fh(Pr
     float* b = ws->vec[1] + GUARD;
     const float* D = ft.D2 + pv.table_offset(pc / pv.C, c, m) + (size_t)r * L;
     for (int t = 0; t < 16; ++t) a[lane + 32 * t] = __ldg(D + (L - 1 - lane - 32 * t));
-    warp_load_vec(b, ft.FSG + ((size_t)tb->fg_row + (size_t)m * tb->fi.nf + f) * L, lane);
+    warp_load_vec(b, ft.FSG + ((size_t)tb->fsg_row + (size_t)m * tb->nfsg + f) * L, lane);
     warp_logconv<false>(a, b, ws->jstar, ws->fa, ws->fb, lane);
     float* out = FH + ((size_t)tb->fh_row + ((size_t)m * K + r) * nfh + f) * L;
     for (int t = 0; t < 16; ++t) out[lane + 32 * t] = a[L - 1 - lane - 32 * t] - LOG2_L;
@@ -276,11 +279,12 @@ __global__ void __launch_bounds__(FAST_THREADS) k_forest_scan_top(ProblemView pv
     const int i = blockIdx.x * FAST_WARPS + wid;
     if (i >= tb->fi.base[n + 1] - tb->fi.base[n]) return;
     const size_t row = (size_t)tb->fg_row + (size_t)m * tb->fi.nf + tb->fi.base[n] + i;
+    const size_t srow = (size_t)tb->fsg_row + (size_t)m * tb->nfsg + tb->fi.base[n] + i;
     const float add2 = (float)((pv.p0[c] - 6.2383246250395077847550890931236) * 1.4426950408889634074);
     float* a = ws->vec[0] + GUARD;
     warp_load_vec(a, FG + row * L, lane);
     warp_log2cumsum(a, add2, lane);
-    float4* os = reinterpret_cast<float4*>(FSG + row * L);
+    float4* os = reinterpret_cast<float4*>(FSG + srow * L);
     for (int t = 0; t < 4; ++t) os[lane + 32 * t] = reinterpret_cast<const float4*>(a)[lane + 32 * t];
 }
 

@@ -100,9 +100,11 @@ inline std::vector<uint32_t> make_level_order(const ForestIndex& fi, const std::
 
 // Default table geometry per cluster count: inside tables for forests of <= s nodes, finishing tables of the
 // table-driven programs for forests of <= sh nodes, context tables (pairs.cuh) for contexts of <= r nodes
-// (r = 0: no pair path).  Chosen by counting rows against the trees they serve (brute force over all trees
-// for K <= 8, 30 000 random trees above): regular trees = 100 % up to K = 7, 97.9 % at
-// K = 8, 98.1 % at K = 9, 87.9 % at K = 10.  K >= 11 needs s + r >= 11 (tens of GB per sample): programs only.
+// (r = 0: no pair path).  Chosen by counting the rows in use against the trees they serve and the irregular trees
+// left over, for every candidate (s, r), by cutting ALL trees on the GPU (profiles/r02_pair_geometry.txt):
+//   K = 6 (3,4): 371 + 846 rows, K = 7 (4,4): 5 005 + 2 821, K = 8 (4,5): 9 738 + 40 552, K = 9 (5,6): 180 507 +
+//   262 989 -- all trees regular; K = 10 (5,6): 354 907 + 2 371 810 rows, 2.0 % of the 10^9 trees irregular.
+// K >= 11 would need s + r >= 11 (tens of GB per sample): programs only.
 inline void default_forest_geometry(int K, int* s, int* sh, int* r = nullptr) {
     int rr = 0;
     if (K <= 1) { *s = 1; *sh = 1; }
@@ -110,10 +112,10 @@ inline void default_forest_geometry(int K, int* s, int* sh, int* r = nullptr) {
     else if (K == 3) { *s = 2; *sh = 1; rr = 1; }
     else if (K == 4) { *s = 2; *sh = 2; rr = 2; }
     else if (K == 5) { *s = 3; *sh = 2; rr = 3; }
-    else if (K == 6) { *s = 3; *sh = 2; rr = 4; }   // 371 + 846 rows in use (725 convolutions) against 2 246 + 186 (1 220) for (4, 3)
+    else if (K == 6) { *s = 3; *sh = 2; rr = 4; }
     else if (K == 7) { *s = 4; *sh = 3; rr = 4; }
-    else if (K == 8) { *s = 5; *sh = 3; rr = 4; }
-    else if (K <= 10) { *s = 5; *sh = 3; rr = 5; }
+    else if (K == 8) { *s = 4; *sh = 3; rr = 5; }
+    else if (K <= 10) { *s = 5; *sh = 3; rr = 6; }
     else { *s = 3; *sh = 2; }                         // K = 11, 12
     if (r) *r = rr;
 }

@@ -42,7 +42,9 @@ constexpr float FR_MAXR = 30.0f;                    // a factor above 2^FR_MAXR 
 
 // Per (parameter set, clustering): where its tables start and how they are indexed (forest.cuh, pairs.cuh).
 struct TableBase {
-    uint32_t fg_row;     // first row of FG / FSG of (p, c, m = 0); sample m starts fi.nf * m rows later
+    uint32_t fg_row;     // first row of FG of (p, c, m = 0); sample m starts fi.nf * m rows later
+    uint32_t fsg_row;    // first row of FSG of (p, c, m = 0); sample m starts nfsg rows later
+    int32_t nfsg;        // FSG rows per sample: the forests whose scanned message anything reads (a prefix of the rows)
     uint32_t fh_row;     // first row of FH of (p, c, m = 0, root 0); (m, r) starts (m * K + r) * fi.nfh rows later
     uint32_t t_row;      // first row of T of (p, c, m = 0); sample m starts PairK::nt rows later
     int32_t s_prog;      // the table-driven programs pack forests of <= s_prog <= fi.s nodes (16-bit row ids)

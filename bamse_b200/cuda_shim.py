@@ -108,6 +108,8 @@ def load_library():
     lib.bamse_debug_ctx_recipes.argtypes = [i32, i32, i32, c_p]
     lib.bamse_debug_classify.restype = i32
     lib.bamse_debug_classify.argtypes = [i32, c_p, i32, i32, c_p]
+    lib.bamse_debug_pair_stats.restype = i32
+    lib.bamse_debug_pair_stats.argtypes = [c_p, i32, i32, i32, c_p]
     if lib.bamse_abi_version() != 1:
         raise RuntimeError("libbamse_cuda ABI version mismatch")
     _lib = lib
@@ -120,7 +122,7 @@ EXPORTED_SYMBOLS = [
     "bamse_score_list", "bamse_score_range", "bamse_score_topk", "bamse_enumerate_topk_dev",
     "bamse_merge_topk_dev", "bamse_kernel_time", "bamse_table_time", "bamse_kernel_stats",
     "bamse_debug_forest_geometry", "bamse_debug_forest_recipes", "bamse_debug_program",
-    "bamse_debug_pair_geometry", "bamse_debug_ctx_recipes", "bamse_debug_classify",
+    "bamse_debug_pair_geometry", "bamse_debug_ctx_recipes", "bamse_debug_classify", "bamse_debug_pair_stats",
 ]
 
 
@@ -242,6 +244,12 @@ class Context(object):
         out = np.empty((self.P, self.C), dtype=np.int32)
         self._check(self._lib.bamse_get_shard_plan(self._h, _ptr(out)))
         return out
+
+    def pair_stats(self, K, s, r):
+        """dict(nf, nt_full, nt_used, irregular) of the pair geometry (s, r) at K clusters (cuts every tree on the GPU)."""
+        out = np.zeros(4, dtype=np.int64)
+        self._check(self._lib.bamse_debug_pair_stats(self._h, int(K), int(s), int(r), _ptr(out)))
+        return dict(nf=int(out[0]), nt_full=int(out[1]), nt_used=int(out[2]), irregular=int(out[3]))
 
     def rebuild_tables(self):
         """re-derives every table of the resident problem from the counts in device memory (asynchronous)."""

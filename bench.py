@@ -282,6 +282,9 @@ def main():
     ap.add_argument("--search-only", action="store_true",
                     help="not a bench line: run ONE pass of the early-exit search (for configurations whose full\n"
                          "scoring pass is too long, e.g. c4 = 3e9 trees) and print its own JSON")
+    ap.add_argument("--lean", action="store_true",
+                    help="long configurations (c4): skip the extra legs (enumeration-only, early-exit search) and time "
+                         "ONE end-to-end step without its own warm-up")
     ap.add_argument("--emulate-shard-of", type=int, default=0,
                     help="debug: one GPU scores only shard 0 of W (what each rank of a W-GPU run does)")
     args = ap.parse_args()
@@ -463,27 +466,29 @@ def main():
     ctx.table_time(reset=True)
 
     # ---- extra (not the headline): enumeration alone over tables that stay resident between steps
-    for _ in range(2):
-        step_resident(tables=False)
-    barrier()
-    ee0, ee1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ee0.record()
-    for _ in range(args.steps):
-        step_resident(tables=False)
-    ee1.record()
-    barrier()
-    t_en = torch.tensor([ee0.elapsed_time(ee1)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t_en, op=dist.ReduceOp.MAX)
-    enum_only = {"value": total_evals * args.steps / (float(t_en[0]) / 1e3), "unit": UNIT,
-                 "ms_per_step": float(t_en[0]) / args.steps,
-                 "note": "tables kept from the previous step (NOT the headline: a new problem always pays its tables)"}
-    ctx.kernel_time(reset=True)
+    enum_only = None
+    if not args.lean:
+        for _ in range(2):
+            step_resident(tables=False)
+        barrier()
+        ee0, ee1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ee0.record()
+        for _ in range(args.steps):
+            step_resident(tables=False)
+        ee1.record()
+        barrier()
+        t_en = torch.tensor([ee0.elapsed_time(ee1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t_en, op=dist.ReduceOp.MAX)
+        enum_only = {"value": total_evals * args.steps / (float(t_en[0]) / 1e3), "unit": UNIT,
+                     "ms_per_step": float(t_en[0]) / args.steps,
+                     "note": "tables kept from the previous step (NOT the headline: a new problem always pays its tables)"}
+        ctx.kernel_time(reset=True)
 
     # ---- extra (not the headline): the same resident pass with the exact sample-level early exit
     #      (BAMSE_OPT_EARLY_EXIT) -- trees are resolved, not all of their samples are scored
     search = None
-    if prec == cuda_shim.FP32:
+    if prec == cuda_shim.FP32 and not args.lean:
         ctx.set_early_exit(True)
         step_resident()
         barrier()
@@ -531,10 +536,10 @@ def main():
             return out.numpy().view(cuda_shim.RECORD_DTYPE).reshape(P, topk)
         return rec
 
-    for _ in range(min(args.warmup, 2)):
+    for _ in range(0 if args.lean else min(args.warmup, 2)):
         step_e2e()
     barrier()
-    e2e_steps = args.steps
+    e2e_steps = 1 if args.lean else args.steps
     sampler.begin()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):

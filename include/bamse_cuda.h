@@ -226,6 +226,9 @@ int bamse_debug_program(int k, const int8_t* parent, const int8_t* nodes, int Kc
 int bamse_debug_pair_geometry(int K, int32_t* s, int32_t* r, int32_t* out_nf, int32_t* out_nt);
 int bamse_debug_ctx_recipes(int K, int s, int r, int32_t* out);
 int bamse_debug_classify(int K, const int8_t* parent, int s, int r, int32_t* out);
+/* Needs the GPU (cuts all K^(K-1) trees on the device): out4 = {inside rows, context rows of the full index space,
+ * context rows in use, irregular trees} of the pair geometry (s, r).  Invalidates the resident problem. */
+int bamse_debug_pair_stats(bamse_ctx* ctx, int K, int s, int r, int64_t* out4);
 
 /* Host helper shared with the oracle's definition: index -> parent vector. */
 int bamse_decode_tree(int K, uint64_t tree_index, int8_t* out_parent /* [K] */);
