@@ -66,7 +66,7 @@ struct bamse_ctx {
         uint64_t n_irregular = 0;
     };
     PairState pairs[KMAX + 1];
-    DBuf d_T, d_pk, d_flat, d_flat_meta, d_lists2, d_segs2, d_owner;
+    DBuf d_T, d_pk, d_flat, d_flat_meta, d_lists2, d_segs2, d_owner, d_part;
     std::vector<int32_t> owner;          // [P][C] sharding plan (empty: none): -1 split over all ranks, else the owning rank
     bool k_present[KMAX + 1] = {false};
     bool interp_ready = false;           // finishing tables + top-level scanned messages of the resident problem built
@@ -609,7 +609,7 @@ void bamse_destroy(bamse_ctx* ctx) {
                     &ctx->d_recipe_ptrs, &ctx->d_segs, &ctx->d_scalars, &ctx->d_cand, &ctx->d_items,
                     &ctx->d_scores, &ctx->d_const, &ctx->d_thr, &ctx->d_begin, &ctx->d_end, &ctx->d_records,
                     &ctx->d_dense0, &ctx->d_dense1, &ctx->d_split, &ctx->d_lists, &ctx->d_T, &ctx->d_pk, &ctx->d_flat,
-                    &ctx->d_flat_meta, &ctx->d_lists2, &ctx->d_segs2, &ctx->d_owner};
+                    &ctx->d_flat_meta, &ctx->d_lists2, &ctx->d_segs2, &ctx->d_owner, &ctx->d_part};
     for (DBuf* b : bufs) b->release();
     for (auto& t : ctx->progtab) t.buf.release();
     for (auto& t : ctx->pairs) { t.tab.release(); t.map.release(); t.recipes.release(); }
@@ -1095,6 +1095,13 @@ static int enumerate_dev(bamse_ctx* ctx, const double* d_const, const double* d_
     }
     const int chunk = (int)std::min<uint64_t>(16, std::max<uint64_t>(1, trees_prog / ((uint64_t)workers * 32)));
     const int chunk2 = 32;                           // one tree slot per lane
+    // sample-major pair path (the warps in flight share one sample's tables, L2 resident): when every pair cluster
+    // count is small enough for that to matter (K <= 8), nothing exits early and the per-sample results fit
+    bool sample_major = mask_pairs != 0 && ctx->M > 1 && !(ctx->early_exit && !host_seg && topk > 0) && (mask_pairs >> 9) == 0;
+    const uint64_t part_slots = (trees_pairs / chunk2 + (uint64_t)P * C + 1) * chunk2;
+    if (sample_major && part_slots * (uint64_t)ctx->M * sizeof(float) > (8ull << 30)) sample_major = false;
+    if (const char* e = getenv("BAMSE_SAMPLE_MAJOR")) sample_major = sample_major && atoi(e) != 0;
+    const int reps2 = sample_major ? ctx->M : 1;
     const uint64_t chunks_prog = trees_prog / chunk + (uint64_t)P * C + 1;
     const uint64_t chunks_pairs = trees_pairs / chunk2 + (uint64_t)P * C + 1;
     uint64_t cand_lists = std::min<uint64_t>((uint64_t)workers * P, chunks_prog + workers);
@@ -1122,13 +1129,14 @@ static int enumerate_dev(bamse_ctx* ctx, const double* d_const, const double* d_
         BAMSE_CUDA_TRY(ctx, cudaMemcpyAsync(flat_meta, flat_off.data(), sizeof(unsigned long long) * (P + 1), cudaMemcpyHostToDevice, s));
         BAMSE_CUDA_TRY(ctx, cudaMemsetAsync(flat_meta + P + 1, 0, sizeof(unsigned long long) * (2 * (size_t)P + 1), s));
         BAMSE_CUDA_TRY(ctx, ctx->d_lists2.ensure(sizeof(bamse_record) * (size_t)workers2 * (size_t)(topk > 0 ? topk : 1)));
+        if (sample_major) BAMSE_CUDA_TRY(ctx, ctx->d_part.ensure(sizeof(float) * part_slots * (size_t)ctx->M));
     }
     const int32_t* d_owner = ctx->owner.empty() ? nullptr : ctx->d_owner.as<int32_t>();
     EnumWork w;
     memset(&w, 0, sizeof w);
     if (host_seg) {
         const Segment seg = *host_seg;
-        const uint64_t chunks = (seg.n_trees + (mask_pairs ? chunk2 : chunk) - 1) / (mask_pairs ? chunk2 : chunk);
+        const uint64_t chunks = (seg.n_trees + (mask_pairs ? chunk2 : chunk) - 1) / (mask_pairs ? chunk2 : chunk) * (mask_pairs ? reps2 : 1);
         BAMSE_CUDA_TRY(ctx, cudaMemcpyAsync(mask_pairs ? ctx->d_segs2.p : ctx->d_segs.p, &seg, sizeof seg, cudaMemcpyHostToDevice, s));
         BAMSE_CUDA_TRY(ctx, cudaMemcpyAsync(mask_pairs ? scal + 10 : scal, &chunks, sizeof chunks, cudaMemcpyHostToDevice, s));
         BAMSE_CUDA_TRY(ctx, cudaStreamSynchronize(s));
@@ -1137,13 +1145,13 @@ static int enumerate_dev(bamse_ctx* ctx, const double* d_const, const double* d_
     } else {
         if (mask_prog || !mask_pairs) {
             launch_build_segments(P, C, ctx->d_K.as<int32_t>(), d_const, d_thr, d_begin, d_end, slack_abs, slack_rel,
-                                  chunk, ctx->shard_rank, ctx->shard_world, mask_pairs ? mask_prog : 0xffffffffu, d_owner,
+                                  chunk, 1, ctx->shard_rank, ctx->shard_world, mask_pairs ? mask_prog : 0xffffffffu, d_owner,
                                   ctx->d_segs.as<Segment>(), scal, scal + 1, s);
             ctx->launches++;
         }
         if (mask_pairs) {
             launch_build_segments(P, C, ctx->d_K.as<int32_t>(), d_const, d_thr, d_begin, d_end, slack_abs, slack_rel,
-                                  chunk2, ctx->shard_rank, ctx->shard_world, mask_pairs, d_owner,
+                                  chunk2, reps2, ctx->shard_rank, ctx->shard_world, mask_pairs, d_owner,
                                   ctx->d_segs2.as<Segment>(), scal + 10, scal + 11, s);
             ctx->launches++;
         }
@@ -1198,8 +1206,17 @@ static int enumerate_dev(bamse_ctx* ctx, const double* d_const, const double* d_
         wp.chunk = chunk2;
         wp.total_chunks = scal + 10;
         wp.next_chunk = reinterpret_cast<unsigned long long*>(scal + 12);
-        launch_enumerate_pairs(ctx->view(), ctx->fast(), wp, ctx->grid_pairs, s);
-        ctx->launches++;
+        wp.part = ctx->d_part.as<float>();
+        if (sample_major) {
+            launch_enumerate_pairs(ctx->view(), ctx->fast(), wp, ctx->grid_pairs, 1, s);
+            EnumWork wr = wp;                          // second pass: its own chunk counter
+            wr.next_chunk = reinterpret_cast<unsigned long long*>(scal + 15);
+            launch_enumerate_pairs(ctx->view(), ctx->fast(), wr, ctx->grid_pairs, 2, s);
+            ctx->launches += 2;
+        } else {
+            launch_enumerate_pairs(ctx->view(), ctx->fast(), wp, ctx->grid_pairs, 0, s);
+            ctx->launches++;
+        }
         if (irregular_any) {
             launch_flat_prefix(P, wp.flat_cnt, wp.flat_off, wp.flat_prefix, s);
             EnumWork wf = wp;

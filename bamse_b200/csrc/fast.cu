@@ -629,6 +629,14 @@ constexpr int PAIR_THREADS = PAIR_WARPS * 32;
 // dot product per sample; an irregular tree is appended to the flat list of its parameter set for
 // k_enumerate_fast.  Per-warp top-k lists (global memory) are filled by lane 0 from the lanes that beat the
 // warp's k-th best, and appended to the candidate bag when the parameter set changes and at the end.
+//
+// MODE 0, tree-major: a lane takes its tree through all samples (early exit possible; the only mode for cluster
+//   counts whose tables per sample exceed the L2 anyway).
+// MODE 1 + MODE 2, sample-major: the chunks of a segment are ordered sample by sample, so the warps in flight read
+//   the tables of ONE sample of one clustering (K = 7: 16 MB, L2 resident) instead of all samples at once (DRAM
+//   traffic 2.5x the tables); MODE 1 stores the per-sample log2 results in `part` [M][slots], MODE 2 sums them in
+//   sample order -- the same fp64 additions as MODE 0, bit for bit -- and ranks.
+template <int MODE>
 __global__ void __launch_bounds__(PAIR_THREADS, 6) k_enumerate_pairs(ProblemView pv, FastTables ft, EnumWork w) {
     const int lane = threadIdx.x & 31;
     const int gw = blockIdx.x * PAIR_WARPS + (threadIdx.x >> 5);
@@ -637,7 +645,10 @@ __global__ void __launch_bounds__(PAIR_THREADS, 6) k_enumerate_pairs(ProblemView
     int ntop = 0;                                    // meaningful in lane 0
     int cur_p = -1;
     double kth = -CUDART_INF;                        // total of the warp's k-th best once the list is full (all lanes)
-    const uint64_t total = *w.total_chunks;
+    const int reps = MODE == 0 ? 1 : pv.M;           // chunk counts of the segments are multiples of `reps`
+    const uint64_t total_all = *w.total_chunks;
+    const uint64_t total = MODE == 2 ? total_all / (uint64_t)reps : total_all;
+    const uint64_t slots = total_all / (uint64_t)reps * 32ull;      // tree slots of the launch (sample-major)
     unsigned st_groups = 0, st_samples = 0;
 
     auto flush = [&]() {
@@ -654,14 +665,24 @@ __global__ void __launch_bounds__(PAIR_THREADS, 6) k_enumerate_pairs(ProblemView
         if (lane == 0) chunk = atomicAdd(w.next_chunk, 1ull);
         chunk = __shfl_sync(0xffffffffu, chunk, 0);
         if (chunk >= total) break;
+        const uint64_t key = MODE == 2 ? chunk * (uint64_t)reps : chunk;
         int lo = 0, hi = w.n_segs - 1;
         while (lo < hi) {
             const int mid = (lo + hi + 1) >> 1;
-            if (w.segs[mid].first_chunk <= chunk) lo = mid; else hi = mid - 1;
+            if (w.segs[mid].first_chunk <= key) lo = mid; else hi = mid - 1;
         }
         const Segment seg = w.segs[lo];
-        if (seg.p != cur_p) { flush(); cur_p = seg.p; kth = -CUDART_INF; }
-        const uint64_t off = (chunk - seg.first_chunk) * (uint64_t)w.chunk + (uint64_t)lane;
+        if (MODE != 1 && seg.p != cur_p) { flush(); cur_p = seg.p; kth = -CUDART_INF; }
+        // position inside the segment: tree block and (sample-major accumulation) the sample
+        uint64_t blk = key - seg.first_chunk;
+        int m_one = 0;
+        if (MODE == 1) {
+            const uint64_t cpm = (seg.n_trees + 31ull) / 32ull;
+            m_one = (int)(blk / cpm);
+            blk -= (uint64_t)m_one * cpm;
+        } else if (MODE == 2) blk /= (uint64_t)reps;
+        const uint64_t off = blk * 32ull + (uint64_t)lane;
+        const uint64_t slot = seg.first_chunk / (uint64_t)reps * 32ull + off;
         const bool valid = off < seg.n_trees;
         const uint64_t tree = seg.tree_begin + off * (uint64_t)seg.stride;
         const TableBase* tb = ft.tb + (seg.p * pv.C + seg.c);
@@ -685,38 +706,51 @@ __global__ void __launch_bounds__(PAIR_THREADS, 6) k_enumerate_pairs(ProblemView
                 }
             }
         }
-        // irregular trees: to the flat list of this parameter set (warp-aggregated append)
-        const bool irr = valid && !reg;
-        const unsigned irr_mask = __ballot_sync(0xffffffffu, irr);
-        if (irr_mask) {
-            unsigned long long base = 0;
-            if (lane == 0) base = atomicAdd(w.flat_cnt + seg.p, (unsigned long long)__popc(irr_mask));
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (irr) {
-                const unsigned long long pos = w.flat_off[seg.p] + base + (unsigned long long)__popc(irr_mask & ((1u << lane) - 1u));
-                if (pos < w.flat_off[seg.p + 1]) w.flat[pos] = ((unsigned long long)lo << 40) | tree;
-                else *w.flat_overflow = 1ull;
+        // irregular trees: to the flat list of this parameter set (warp-aggregated append), once
+        if (MODE == 0 || (MODE == 1 && m_one == 0)) {
+            const bool irr = valid && !reg;
+            const unsigned irr_mask = __ballot_sync(0xffffffffu, irr);
+            if (irr_mask) {
+                unsigned long long base = 0;
+                if (lane == 0) base = atomicAdd(w.flat_cnt + seg.p, (unsigned long long)__popc(irr_mask));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (irr) {
+                    const unsigned long long pos = w.flat_off[seg.p] + base + (unsigned long long)__popc(irr_mask & ((1u << lane) - 1u));
+                    if (pos < w.flat_off[seg.p + 1]) w.flat[pos] = ((unsigned long long)lo << 40) | tree;
+                    else *w.flat_overflow = 1ull;
+                }
             }
+        }
+        const float* g = ft.FG + ((size_t)tb->fg_row + fg) * L;
+        const float* t = ft.T + ((size_t)tb->t_row + tr) * L;
+        const size_t gstep = (size_t)tb->fi.nf * L, tstep = (size_t)pk->nt * L;
+        if (MODE == 1) {
+            if (reg) {
+                w.part[(size_t)m_one * slots + slot] = lane_log2dot(g + (size_t)m_one * gstep, t + (size_t)m_one * tstep, st_groups);
+                ++st_samples;
+            }
+            continue;
         }
         double score = -CUDART_INF, logscre = 0.0;
         if (reg) {
             logscre = log((double)scre);
-            double cut = -CUDART_INF;
-            if (w.early_exit) {
-                const double c0 = fmax(seg.threshold, kth - seg.clust_const);
-                cut = c0 - logscre - 1e-3 - 1e-6 * fabs(c0);
-            }
-            const int nf = tb->fi.nf;
-            const float* g = ft.FG + ((size_t)tb->fg_row + fg) * L;
-            const float* t = ft.T + ((size_t)tb->t_row + tr) * L;
-            const size_t gstep = (size_t)nf * L, tstep = (size_t)pk->nt * L;
             double acc = 0.0;
+            if (MODE == 0) {
+                double cut = -CUDART_INF;
+                if (w.early_exit) {
+                    const double c0 = fmax(seg.threshold, kth - seg.clust_const);
+                    cut = c0 - logscre - 1e-3 - 1e-6 * fabs(c0);
+                }
 #pragma unroll 1
-            for (int m = 0; m < pv.M; ++m) {
-                acc += (double)lane_log2dot(g, t, st_groups) * 0.69314718055994530942;
-                ++st_samples;
-                g += gstep; t += tstep;
-                if (acc < cut) { acc = -CUDART_INF; break; }
+                for (int m = 0; m < pv.M; ++m) {
+                    acc += (double)lane_log2dot(g, t, st_groups) * 0.69314718055994530942;
+                    ++st_samples;
+                    g += gstep; t += tstep;
+                    if (acc < cut) { acc = -CUDART_INF; break; }
+                }
+            } else {
+#pragma unroll 1
+                for (int m = 0; m < pv.M; ++m) acc += (double)w.part[(size_t)m * slots + slot] * 0.69314718055994530942;
             }
             score = acc;
             if (w.dense_score) w.dense_score[off] = score;
@@ -746,26 +780,30 @@ __global__ void __launch_bounds__(PAIR_THREADS, 6) k_enumerate_pairs(ProblemView
             }
         }
     }
-    flush();
+    if (MODE != 1) flush();
     // executed-work counters: 4 ex2 per group, 1 lg2 per dot
     st_groups = __reduce_add_sync(0xffffffffu, st_groups);
     st_samples = __reduce_add_sync(0xffffffffu, st_samples);
-    if (w.stats && lane == 0) atomicAdd(w.stats + 0, 4ull * st_groups + st_samples);
-    if (w.samples_done && lane == 0) atomicAdd(w.samples_done, (unsigned long long)st_samples);
+    if (MODE != 2) {
+        if (w.stats && lane == 0) atomicAdd(w.stats + 0, 4ull * st_groups + st_samples);
+        if (w.samples_done && lane == 0) atomicAdd(w.samples_done, (unsigned long long)st_samples);
+    }
 }
 
 int enumerate_pairs_grid_size(int device) {
     int sms = 148, per_sm = 1;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_enumerate_pairs, PAIR_THREADS, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_enumerate_pairs<0>, PAIR_THREADS, 0);
     if (per_sm < 1) per_sm = 1;
     return sms * per_sm;
 }
 
 int enumerate_pairs_workers(int grid) { return grid * PAIR_WARPS; }
 
-void launch_enumerate_pairs(const ProblemView& pv, const FastTables& ft, const EnumWork& w, int grid, cudaStream_t s) {
-    k_enumerate_pairs<<<grid, PAIR_THREADS, 0, s>>>(pv, ft, w);
+void launch_enumerate_pairs(const ProblemView& pv, const FastTables& ft, const EnumWork& w, int grid, int mode, cudaStream_t s) {
+    if (mode == 0) k_enumerate_pairs<0><<<grid, PAIR_THREADS, 0, s>>>(pv, ft, w);
+    else if (mode == 1) k_enumerate_pairs<1><<<grid, PAIR_THREADS, 0, s>>>(pv, ft, w);
+    else k_enumerate_pairs<2><<<grid, PAIR_THREADS, 0, s>>>(pv, ft, w);
 }
 
 void launch_flat_prefix(int P, const unsigned long long* cnt, const unsigned long long* off, unsigned long long* prefix,

@@ -40,7 +40,7 @@ void launch_tables(const ProblemView& pv, const double* d_var, const double* d_r
 __global__ void __launch_bounds__(256) k_build_segments(int P, int C, const int32_t* __restrict__ K_of_c,
                                                         const double* __restrict__ cconst, const double* __restrict__ thr,
                                                         const uint64_t* __restrict__ begin, const uint64_t* __restrict__ end,
-                                                        double slack_abs, double slack_rel, int chunk, int shard_rank,
+                                                        double slack_abs, double slack_rel, int chunk, int reps, int shard_rank,
                                                         int shard_world, uint32_t k_mask, const int32_t* __restrict__ owner,
                                                         Segment* __restrict__ segs,
                                                         uint64_t* __restrict__ total_chunks, uint64_t* __restrict__ total_trees) {
@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(256) k_build_segments(int P, int C, const int3
         s.stride = world;
         s.tree_begin = b + (uint64_t)rank;
         s.n_trees = span > (uint64_t)rank ? (span - rank + world - 1) / world : 0;
-        s.first_chunk = (s.n_trees + (uint64_t)chunk - 1) / (uint64_t)chunk;   // count for now
+        s.first_chunk = (s.n_trees + (uint64_t)chunk - 1) / (uint64_t)chunk * (uint64_t)reps;   // count for now
         s.clust_const = cconst ? cconst[i] : 0.0;
         double th = thr ? thr[i] : -CUDART_INF;
         if (th > -CUDART_INF) th -= slack_abs + slack_rel * fabs(th);
@@ -86,10 +86,10 @@ __global__ void __launch_bounds__(256) k_build_segments(int P, int C, const int3
 
 void launch_build_segments(int P, int C, const int32_t* d_K_of_c, const double* d_const, const double* d_thr,
                            const uint64_t* d_begin, const uint64_t* d_end, double slack_abs, double slack_rel,
-                           int chunk, int shard_rank, int shard_world, uint32_t k_mask, const int32_t* d_owner,
+                           int chunk, int reps, int shard_rank, int shard_world, uint32_t k_mask, const int32_t* d_owner,
                            Segment* d_segs, uint64_t* d_total_chunks, uint64_t* d_total_trees, cudaStream_t s) {
     k_build_segments<<<1, 256, 0, s>>>(P, C, d_K_of_c, d_const, d_thr, d_begin, d_end, slack_abs, slack_rel, chunk,
-                                      shard_rank, shard_world, k_mask, d_owner, d_segs, d_total_chunks, d_total_trees);
+                                      reps, shard_rank, shard_world, k_mask, d_owner, d_segs, d_total_chunks, d_total_trees);
 }
 
 // --------------------------------------------------------------------- top-k helper

@@ -68,6 +68,7 @@ struct EnumWork {
     unsigned long long* flat_overflow;    // set when a region was too small (host checks)
     int flat_mode;
     bamse_record* lists2;                 // the pair kernel's per-warp lists
+    float* part;                          // sample-major pair path: per-sample log2 results [M][tree slots]
 };
 
 void launch_tables(const ProblemView& pv, const double* d_var, const double* d_ref, const double* d_logc,
@@ -75,7 +76,8 @@ void launch_tables(const ProblemView& pv, const double* d_var, const double* d_r
                    cudaStream_t s);
 void launch_build_segments(int P, int C, const int32_t* d_K_of_c, const double* d_const, const double* d_thr,
                            const uint64_t* d_begin, const uint64_t* d_end, double slack_abs, double slack_rel,
-                           int chunk, int shard_rank, int shard_world, uint32_t k_mask /* cluster counts that take part */,
+                           int chunk, int reps /* chunks per `chunk` trees */, int shard_rank, int shard_world,
+                           uint32_t k_mask /* cluster counts that take part */,
                            const int32_t* d_owner /* [P][C] sharding plan or NULL */, Segment* d_segs,
                            uint64_t* d_total_chunks, uint64_t* d_total_trees, cudaStream_t s);
 int enumerate_grid_size(int precision, int device);
@@ -114,7 +116,9 @@ void launch_build_pair_table(const ForestIndex& fi, const PairGeom& g, uint64_t 
 void launch_remap_pair_table(uint64_t* tab, uint64_t n_trees, const uint32_t* d_map, cudaStream_t s);
 int enumerate_pairs_grid_size(int device);
 int enumerate_pairs_workers(int grid);
-void launch_enumerate_pairs(const ProblemView& pv, const FastTables& ft, const EnumWork& w, int grid, cudaStream_t s);
+// mode 0: tree-major; 1 + 2: sample-major (accumulate per sample into w.part, then sum and rank); the segments of
+// modes 1 / 2 carry M chunks per 32 trees (launch_build_segments with reps = M)
+void launch_enumerate_pairs(const ProblemView& pv, const FastTables& ft, const EnumWork& w, int grid, int mode, cudaStream_t s);
 void launch_flat_prefix(int P, const unsigned long long* cnt, const unsigned long long* off, unsigned long long* prefix,
                         cudaStream_t s);
 void launch_score_items_fast(const ProblemView& pv, const FastTables& ft, const ScoreItem* d_items, int64_t n,
