@@ -66,7 +66,8 @@ struct bamse_ctx {
         uint64_t n_irregular = 0;
     };
     PairState pairs[KMAX + 1];
-    DBuf d_T, d_pk, d_flat, d_flat_meta, d_lists2, d_segs2, d_owner, d_part;
+    DBuf d_T, d_pk, d_flat, d_flat_meta, d_lists2, d_segs2, d_owner, d_part, d_pcm;
+    int n_pcm = 0;
     std::vector<int32_t> owner;          // [P][C] sharding plan (empty: none): -1 split over all ranks, else the owning rank
     bool k_present[KMAX + 1] = {false};
     bool interp_ready = false;           // finishing tables + top-level scanned messages of the resident problem built
@@ -115,6 +116,7 @@ struct bamse_ctx {
         f.D2 = d_D2.as<float>(); f.SD2 = d_SD2.as<float>();
         f.FG = d_FG.as<float>(); f.FSG = d_FSG.as<float>(); f.FH = d_FH.as<float>();
         f.T = d_T.as<float>(); f.pk = d_pk.as<PairK>();
+        f.pcm_list = d_pcm.as<int32_t>(); f.n_pcm = n_pcm; f.grid_blocks = 1;
         f.tb = d_tb.as<TableBase>(); f.lut = d_lut.as<int16_t>();
         f.recipes = d_recipe_ptrs.as<const ForestRecipe*>();
         f.level_order = d_order_ptrs.as<const uint32_t*>();
@@ -419,6 +421,14 @@ static int plan_tables(bamse_ctx* ctx) {
     BAMSE_CUDA_TRY(ctx, ctx->d_T.ensure(sizeof(float) * std::max<size_t>(t_rows, 1) * L));
     BAMSE_CUDA_TRY(ctx, ctx->d_tb.ensure(sizeof(TableBase) * tbs.size()));
     BAMSE_CUDA_TRY(ctx, cudaMemcpy(ctx->d_tb.p, tbs.data(), sizeof(TableBase) * tbs.size(), cudaMemcpyHostToDevice));
+    {   // the table kernels run over the (p, c, m) triples of this rank only
+        std::vector<int32_t> pcm;
+        for (int pc = 0; pc < P * C; ++pc)
+            if (tbs[(size_t)pc].mine) for (int m = 0; m < M; ++m) pcm.push_back(pc * M + m);
+        ctx->n_pcm = (int)pcm.size();
+        BAMSE_CUDA_TRY(ctx, ctx->d_pcm.ensure(sizeof(int32_t) * std::max<size_t>(pcm.size(), 1)));
+        BAMSE_CUDA_TRY(ctx, cudaMemcpy(ctx->d_pcm.p, pcm.data(), sizeof(int32_t) * pcm.size(), cudaMemcpyHostToDevice));
+    }
     if (!ctx->owner.empty()) {
         BAMSE_CUDA_TRY(ctx, ctx->d_owner.ensure(sizeof(int32_t) * ctx->owner.size()));
         BAMSE_CUDA_TRY(ctx, cudaMemcpy(ctx->d_owner.p, ctx->owner.data(), sizeof(int32_t) * ctx->owner.size(), cudaMemcpyHostToDevice));
@@ -609,7 +619,7 @@ void bamse_destroy(bamse_ctx* ctx) {
                     &ctx->d_recipe_ptrs, &ctx->d_segs, &ctx->d_scalars, &ctx->d_cand, &ctx->d_items,
                     &ctx->d_scores, &ctx->d_const, &ctx->d_thr, &ctx->d_begin, &ctx->d_end, &ctx->d_records,
                     &ctx->d_dense0, &ctx->d_dense1, &ctx->d_split, &ctx->d_lists, &ctx->d_T, &ctx->d_pk, &ctx->d_flat,
-                    &ctx->d_flat_meta, &ctx->d_lists2, &ctx->d_segs2, &ctx->d_owner, &ctx->d_part};
+                    &ctx->d_flat_meta, &ctx->d_lists2, &ctx->d_segs2, &ctx->d_owner, &ctx->d_part, &ctx->d_pcm};
     for (DBuf* b : bufs) b->release();
     for (auto& t : ctx->progtab) t.buf.release();
     for (auto& t : ctx->pairs) { t.tab.release(); t.map.release(); t.recipes.release(); }

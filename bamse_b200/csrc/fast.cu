@@ -195,11 +195,13 @@ __global__ void __launch_bounds__(FAST_THREADS, BAMSE_BUILD_CTAS) k_forest_level
     const int wid = threadIdx.x >> 5;
     int lane = threadIdx.x & 31;
     BuildSmem* ws = pin_shared(reinterpret_cast<BuildSmem*>(smem_raw) + wid);
-    const int pcm = blockIdx.y;
+    // 1-D grid = (p, c, m) triples this rank builds tables for  x  row blocks (no 65 535 limit on either)
+    const unsigned nblk = (unsigned)ft.grid_blocks, blk_x = blockIdx.x % nblk;
+    const int pcm = ft.pcm_list[blockIdx.x / nblk];
     const int m = pcm % pv.M, pc = pcm / pv.M, c = pc % pv.C;
     const TableBase* tb = ft.tb + pc;
     if (n > tb->fi.s || !tb->mine) return;
-    const int i = blockIdx.x * FAST_WARPS + wid;
+    const int i = (int)(blk_x * FAST_WARPS + wid);
     if (i >= tb->fi.base[n + 1] - tb->fi.base[n]) return;
     // rows of a level in the order "convolutions first": the warps of a CTA get rows of the same kind
     const int row = (int)ft.level_order[tb->fi.K][tb->fi.base[n] + i];
@@ -244,11 +246,13 @@ __global__ void __launch_bounds__(FAST_THREADS, BAMSE_BUILD_CTAS) k_forest_fh(Pr
     const int wid = threadIdx.x >> 5;
     int lane = threadIdx.x & 31;
     BuildSmem* ws = pin_shared(reinterpret_cast<BuildSmem*>(smem_raw) + wid);
-    const int pcm = blockIdx.y;
+    // 1-D grid = (p, c, m) triples this rank builds tables for  x  row blocks (no 65 535 limit on either)
+    const unsigned nblk = (unsigned)ft.grid_blocks, blk_x = blockIdx.x % nblk;
+    const int pcm = ft.pcm_list[blockIdx.x / nblk];
     const int m = pcm % pv.M, pc = pcm / pv.M, c = pc % pv.C;
     const TableBase* tb = ft.tb + pc;
     const int K = tb->fi.K, nfh = tb->fi.nfh;
-    const int i = blockIdx.x * FAST_WARPS + wid;
+    const int i = (int)(blk_x * FAST_WARPS + wid);
     if (i >= K * nfh || !tb->mine) return;
     const int r = i / nfh, f = i - r * nfh;
     if ((ft.recipes[K][f].mask >> r) & 1) return;   // the root is not part of its own children
@@ -271,12 +275,14 @@ __global__ void __launch_bounds__(FAST_THREADS) k_forest_scan_top(ProblemView pv
     const int wid = threadIdx.x >> 5;
     int lane = threadIdx.x & 31;
     BuildSmem* ws = pin_shared(reinterpret_cast<BuildSmem*>(smem_raw) + wid);
-    const int pcm = blockIdx.y;
+    // 1-D grid = (p, c, m) triples this rank builds tables for  x  row blocks (no 65 535 limit on either)
+    const unsigned nblk = (unsigned)ft.grid_blocks, blk_x = blockIdx.x % nblk;
+    const int pcm = ft.pcm_list[blockIdx.x / nblk];
     const int m = pcm % pv.M, pc = pcm / pv.M, c = pc % pv.C;
     const TableBase* tb = ft.tb + pc;
     const int n = tb->fi.s;
     if (tb->s_prog < n || !tb->mine) return;        // the programs of this clustering never touch the top level
-    const int i = blockIdx.x * FAST_WARPS + wid;
+    const int i = (int)(blk_x * FAST_WARPS + wid);
     if (i >= tb->fi.base[n + 1] - tb->fi.base[n]) return;
     const size_t row = (size_t)tb->fg_row + (size_t)m * tb->fi.nf + tb->fi.base[n] + i;
     const size_t srow = (size_t)tb->fsg_row + (size_t)m * tb->nfsg + tb->fi.base[n] + i;
@@ -299,12 +305,14 @@ __global__ void __launch_bounds__(FAST_THREADS, BAMSE_BUILD_CTAS) k_ctx_level(Pr
     const int wid = threadIdx.x >> 5;
     int lane = threadIdx.x & 31;
     BuildSmem* ws = pin_shared(reinterpret_cast<BuildSmem*>(smem_raw) + wid);
-    const int pcm = blockIdx.y;
+    // 1-D grid = (p, c, m) triples this rank builds tables for  x  row blocks (no 65 535 limit on either)
+    const unsigned nblk = (unsigned)ft.grid_blocks, blk_x = blockIdx.x % nblk;
+    const int pcm = ft.pcm_list[blockIdx.x / nblk];
     const int m = pcm % pv.M, pc = pcm / pv.M, c = pc % pv.C;
     const TableBase* tb = ft.tb + pc;
     const PairK* pk = ft.pk + tb->fi.K;
     if (q > pk->g.r || !tb->mine) return;
-    const uint32_t i = blockIdx.x * FAST_WARPS + wid;
+    const uint32_t i = blk_x * FAST_WARPS + wid;
     if (i >= pk->lbase[q + 1] - pk->lbase[q]) return;
     const uint32_t row = pk->lbase[q] + i;
     const CtxRecipe rec = pk->recipes[row];
@@ -816,8 +824,10 @@ void launch_ctx_level(const ProblemView& pv, const FastTables& ft, int q, int ma
     if (max_rows <= 0) return;
     const size_t smem = sizeof(BuildSmem) * FAST_WARPS;
     cudaFuncSetAttribute(k_ctx_level, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    const dim3 grid((unsigned)((max_rows + FAST_WARPS - 1) / FAST_WARPS), (unsigned)(pv.P * pv.C * pv.M));
-    k_ctx_level<<<grid, FAST_THREADS, smem, s>>>(pv, ft, q, T, stats);
+    FastTables ftg = ft;
+    ftg.grid_blocks = (max_rows + FAST_WARPS - 1) / FAST_WARPS;
+    const unsigned grid = (unsigned)ftg.grid_blocks * (unsigned)ft.n_pcm;
+    k_ctx_level<<<grid, FAST_THREADS, smem, s>>>(pv, ftg, q, T, stats);
 }
 
 void launch_forest_scan_top(const ProblemView& pv, const FastTables& ft, int max_rows, const float* FG, float* FSG,
@@ -825,8 +835,10 @@ void launch_forest_scan_top(const ProblemView& pv, const FastTables& ft, int max
     if (max_rows <= 0) return;
     const size_t smem = sizeof(BuildSmem) * FAST_WARPS;
     cudaFuncSetAttribute(k_forest_scan_top, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    const dim3 grid((unsigned)((max_rows + FAST_WARPS - 1) / FAST_WARPS), (unsigned)(pv.P * pv.C * pv.M));
-    k_forest_scan_top<<<grid, FAST_THREADS, smem, s>>>(pv, ft, FG, FSG);
+    FastTables ftg = ft;
+    ftg.grid_blocks = (max_rows + FAST_WARPS - 1) / FAST_WARPS;
+    const unsigned grid = (unsigned)ftg.grid_blocks * (unsigned)ft.n_pcm;
+    k_forest_scan_top<<<grid, FAST_THREADS, smem, s>>>(pv, ftg, FG, FSG);
 }
 
 void launch_build_pair_table(const ForestIndex& fi, const PairGeom& g, uint64_t n_trees, const int16_t* d_lut,
@@ -849,16 +861,20 @@ void launch_forest_level(const ProblemView& pv, const FastTables& ft, int n, int
     if (max_rows <= 0) return;
     const size_t smem = sizeof(BuildSmem) * FAST_WARPS;
     cudaFuncSetAttribute(k_forest_level, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    const dim3 grid((unsigned)((max_rows + FAST_WARPS - 1) / FAST_WARPS), (unsigned)(pv.P * pv.C * pv.M));
-    k_forest_level<<<grid, FAST_THREADS, smem, s>>>(pv, ft, n, FG, FSG, fsg_top, stats);
+    FastTables ftg = ft;
+    ftg.grid_blocks = (max_rows + FAST_WARPS - 1) / FAST_WARPS;
+    const unsigned grid = (unsigned)ftg.grid_blocks * (unsigned)ft.n_pcm;
+    k_forest_level<<<grid, FAST_THREADS, smem, s>>>(pv, ftg, n, FG, FSG, fsg_top, stats);
 }
 
 void launch_forest_fh(const ProblemView& pv, const FastTables& ft, int max_items, float* FH, cudaStream_t s) {
     if (max_items <= 0) return;
     const size_t smem = sizeof(BuildSmem) * FAST_WARPS;
     cudaFuncSetAttribute(k_forest_fh, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    const dim3 grid((unsigned)((max_items + FAST_WARPS - 1) / FAST_WARPS), (unsigned)(pv.P * pv.C * pv.M));
-    k_forest_fh<<<grid, FAST_THREADS, smem, s>>>(pv, ft, FH);
+    FastTables ftg = ft;
+    ftg.grid_blocks = (max_items + FAST_WARPS - 1) / FAST_WARPS;
+    const unsigned grid = (unsigned)ftg.grid_blocks * (unsigned)ft.n_pcm;
+    k_forest_fh<<<grid, FAST_THREADS, smem, s>>>(pv, ftg, FH);
 }
 
 int enumerate_workers(int precision, int grid) { return precision == BAMSE_FP32 ? grid * FAST_WARPS : grid; }

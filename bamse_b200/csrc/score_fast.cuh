@@ -78,6 +78,9 @@ struct FastTables {
     const uint32_t* const* level_order;   // [KMAX + 1]: per cluster count, the rows of every level with the
                                           // convolution rows first (position base[n] + i -> row)
     const PairK* pk;     // [KMAX + 1]
+    const int32_t* pcm_list;   // [n_pcm] the (p * C + c) * M + m of the tables this rank builds (sharding plan)
+    int n_pcm;
+    int grid_blocks;           // table kernels: row blocks per (p, c, m) of this launch
 };
 
 // ----------------------------------------------------------------------------- warp ops
