@@ -32,6 +32,7 @@ def build_parser():
     parser.add_argument('-t', metavar='top_trees', default=1, type=int, help='Number of top solutions to return')
     # additions (defaults reproduce the reference behaviour)
     parser.add_argument('--device', default=0, type=int, help='CUDA device ordinal (B200)')
+    parser.add_argument('--gpus', default=1, type=int, help='number of GPUs of this box to use (devices --device .. --device+N-1; one process drives them all)')
     parser.add_argument('--check', action='store_true', help='score everything in the fp64 check mode')
     parser.add_argument('--seed', default=None, type=int, help='seed numpy/sklearn RNG for reproducible KMeans restarts')
     parser.add_argument('--tree-budget', default=2e11, type=float,
@@ -77,7 +78,11 @@ def main(argv=None):
     X_As, X_Bs, sample_names = read_input(inputfile)
     print(sample_names)
     print(X_As.shape)
-    ctx = get_context(args.device)
+    if args.gpus > 1:
+        from .multigpu import MultiContext
+        ctx = MultiContext(range(args.device, args.device + args.gpus))
+    else:
+        ctx = get_context(args.device)
     clusts, pf = candidate_clusterings(X_As, X_Bs, max_clusts, n_trees, err, ctx=ctx, verbose=True)
     if any(int(c.As.shape[0]) > cuda_shim.KMAX for c in clusts):
         raise SystemExit("bamse: more than %d clusters is not supported by the CUDA scorer" % cuda_shim.KMAX)

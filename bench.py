@@ -219,7 +219,19 @@ def cpu_reference_rate(work, n_items, cores, seed=0):
     n = sum(r[0] for r in res)
     per_core = statistics.mean(r[0] / r[1] for r in res)     # the reference is single-threaded: its rate on one core
     return dict(value=n / busy, unit=UNIT, cores=len(chunks), kind=kind, wall_s=wall, per_core=per_core,
+                single_process_evals_per_s=per_core, cpu_model=cpu_model(),
                 sample="%d seeded random (clustering, tree) items of %s, %d worker processes" % (n, work["name"], len(chunks)))
+
+
+def cpu_model():
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.lower().startswith("model name"):
+                    return line.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
 
 
 # ------------------------------------------------------------------------------------------
@@ -277,7 +289,7 @@ def main():
     ap.add_argument("--precision", default="fp32", choices=["fp32", "fp64"])
     ap.add_argument("--topk", type=int, default=5)
     ap.add_argument("--ref-items", type=int, default=16, help="work items per step of the reference arm")
-    ap.add_argument("--cpu-items", type=int, default=48, help="sample size of the cpu_baseline leg (about 10 s on 16 cores)")
+    ap.add_argument("--cpu-items", type=int, default=200, help="sample size of the cpu_baseline leg (SURVEY 8d: >= 200 items; ~30 s on 16 cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--search-only", action="store_true",
                     help="not a bench line: run ONE pass of the early-exit search (for configurations whose full\n"
@@ -362,6 +374,18 @@ def main():
     tb = te = None
     total_evals = work["n_evals_per_param"] * P
     topk = args.topk
+
+    # ---- cold single shot: a FRESH context (what one command-line run pays): data-independent pair tables /
+    #      recipes of every cluster count present + upload + tables + enumeration + fp64 re-score, timed once
+    cold_ms = None
+    if not args.lean:
+        torch.cuda.synchronize()
+        t_cold = time.perf_counter()
+        with cuda_shim.Context(local_rank) as cold:
+            cold.set_shard(rank, world)
+            cold.upload_problem(errs, Ks, var, ref)
+            cold.score_topk(const, thr, None, None, topk=topk, precision=prec)
+        cold_ms = 1e3 * (time.perf_counter() - t_cold)
 
     # ---- device-resident state for the `value` measurement
     # a real (non-default) torch stream: handle 0 would mean "the ctx's own stream" to the ABI
@@ -605,7 +629,8 @@ def main():
                 "scaling": "strong", "vs_baseline": None, "dtype": "f32" if prec == cuda_shim.FP32 else "f64",
                 "data": "synthetic", "config": config_dict(args, work, world), "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                        "ms_per_step": 1e3 * e2e_s / e2e_steps, "agrees_with_resident_path": bool(same)},
+                        "ms_per_step": 1e3 * e2e_s / e2e_steps, "agrees_with_resident_path": bool(same),
+                        "cold_single_shot_ms": cold_ms},
                 "gpu_launches": int(launches), "roofline": roofline, "search_mode_extra": search,
                 "enumeration_only_extra": enum_only,
                 "best": {"total": float(final["total"][0, 0]), "clust": int(final["clust"][0, 0]),

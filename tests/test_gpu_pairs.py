@@ -192,3 +192,36 @@ def test_changing_the_shard_of_a_planned_problem_needs_a_new_upload(ctx, shim):
         ctx.score_topk(np.zeros((1, 4)), topk=3)
     ctx.upload_problem([0.003], Ks, var, ref)
     ctx.score_topk(np.zeros((1, 4)), topk=3)
+
+
+def _run_cli(tmp_path, monkeypatch, sub, extra):
+    import bamse_b200.clustering as C
+    from bamse_b200 import cli, simdata
+    d = simdata.simulate(4, 3, 60, seed=33)
+    out = tmp_path / sub
+    out.mkdir()
+    inp = out / "in.dat"
+    simdata.write_input_file(str(inp), d["As"], d["Bs"])
+    monkeypatch.chdir(out)
+    monkeypatch.setattr(C, "_default_ctx", None)
+    assert cli.main(["-e", "0.003", "-nc", "6", "-n", "4", "-t", "3", "--seed", "9"] + extra + [str(inp)]) == 0
+    names = ["bamse_output.txt"] + ["tree_number_%d%s" % (t, sfx) for t in range(3) for sfx in ("_subclones.dot", "_samples.dot", ".txt")]
+    return {n: (out / n).read_bytes() for n in names if (out / n).exists()}
+
+
+def test_cli_multi_gpu_output_is_byte_identical(tmp_path, monkeypatch, shim):
+    """`bamse.py --gpus 2` (one process, one context per GPU, sharding plan, host merge) writes byte-identical
+    output files to the single-GPU run.  On a one-GPU box the second context sits on the same device."""
+    import torch
+    from bamse_b200 import multigpu
+    one = _run_cli(tmp_path, monkeypatch, "one", [])
+    assert "bamse_output.txt" in one and len(one) >= 4
+    if torch.cuda.device_count() >= 2:
+        two = _run_cli(tmp_path, monkeypatch, "two", ["--gpus", "2"])
+    else:
+        real = multigpu.MultiContext
+        monkeypatch.setattr(multigpu, "MultiContext", lambda devs: real([0 for _ in devs]))
+        two = _run_cli(tmp_path, monkeypatch, "two", ["--gpus", "2"])
+    assert one.keys() == two.keys()
+    for n in one:
+        assert one[n] == two[n], n

@@ -177,6 +177,88 @@ def test_fraction_solver_recovers_planted_fractions():
     np.testing.assert_allclose(res['s'], x_true, atol=2e-3)
 
 
+def _barrier_newton(B, a, b, er):
+    """independent solve of solve4's concave program for one sample: log-barrier Newton in prevalence space
+    y = B x (the likelihood is separable there), constraints A y >= 0, 0 <= y <= 1 with A = B^-1."""
+    K = len(a)
+    A = np.linalg.inv(B)
+    h = 0.5 - er
+    scale = float(np.sum(a + b))
+
+    def f(y):
+        q = er + y * h
+        return -(np.sum(a * np.log(q)) + np.sum(b * np.log1p(-q))) / scale
+
+    y = B.dot(np.full(K, 0.5 / K))                      # strictly feasible: x > 0, sum x < 1
+    mu = 1e-2
+    for _ in range(60):
+        for _ in range(50):
+            q = er + y * h
+            x = A.dot(y)
+            g = -(a / q - b / (1 - q)) * h / scale - mu * (A.T.dot(1 / x) + 1 / y - 1 / (1 - y))
+            H = np.diag((a / q ** 2 + b / (1 - q) ** 2) * h * h / scale + mu * (1 / y ** 2 + 1 / (1 - y) ** 2)) \
+                + mu * A.T.dot(np.diag(1 / x ** 2)).dot(A)
+            step = -np.linalg.solve(H, g)
+            t = 1.0
+            phi = lambda z: f(z) - mu * (np.sum(np.log(A.dot(z))) + np.sum(np.log(z)) + np.sum(np.log(1 - z)))
+            while True:
+                z = y + t * step
+                if (z > 0).all() and (z < 1).all() and (A.dot(z) > 0).all() and phi(z) <= phi(y) + 1e-4 * t * g.dot(step):
+                    break
+                t *= 0.5
+                if t < 1e-12:
+                    break
+            y = y + t * step
+            if np.abs(g.dot(step)) < 1e-18:
+                break
+        mu *= 0.3
+        if mu < 1e-16:
+            break
+    return A.dot(y), f(y) * scale
+
+
+def test_fraction_solver_against_an_independent_solve():
+    """the SLSQP solve of solve4's concave program (reference clustering.py:410-426; cvxpy is absent
+    here, so its digits are unpinned) against a second, independent solver (a log-barrier Newton method written
+    here) on 40 random trees x counts incl. the bamse.dat KMeans-4 tables: every solution is feasible, objective
+    values agree to 1e-9 relative and fractions to 2e-4 absolute.  That is the tolerance INTEGRATION.md states for
+    `clone_proportions` / `vaf`."""
+    import bamse_oracle as orc
+    from bamse_b200.fractions import solve4
+    rng = np.random.default_rng(8)
+    cases = []
+    for _ in range(39):
+        K = int(rng.integers(2, 8))
+        tree = orc.decode_tree(K, int(rng.integers(0, K ** (K - 1))))
+        cov = int(rng.choice([60, 200, 5000]))
+        x = rng.dirichlet(np.ones(K + 1))[:K]
+        B = tree_tools.get_matrix(tree)[0]
+        prev = np.clip(B.dot(x), 0, 1)
+        n = rng.integers(3, 60, size=K) * cov
+        a = rng.binomial(n, 0.003 + prev * (0.5 - 0.003))
+        cases.append((B, a[:, None], (n - a)[:, None], 0.003))
+    As = np.array([[17647, 28962, 31830], [65454, 115303, 57305], [2259, 8349, 3164], [13461, 6383, 11212]])
+    Bs = np.array([[52353, 41038, 38170], [324546, 274697, 332695], [37741, 31651, 36836], [286539, 293617, 288788]])
+    cases.append((tree_tools.get_matrix([-1, 0, 1, 2])[0], As, Bs, 0.001))
+    worst_x = worst_f = 0.0
+    for B, a, b, er in cases:
+        K, M = a.shape
+        res = solve4(B, a, b, er, [np.ones(K)] * M)
+        total = 0.0
+        for m in range(M):
+            am, bm = a[:, m].astype(float), b[:, m].astype(float)
+            x_s = res['s'][:, m]
+            assert (x_s >= -1e-9).all() and (B.dot(x_s) <= 1 + 1e-9).all() and (B.dot(x_s) >= -1e-9).all()
+            q = er + B.dot(x_s) * (0.5 - er)
+            f1 = -(np.sum(am * np.log(q)) + np.sum(bm * np.log1p(-q)))
+            x2, f2 = _barrier_newton(B, am, bm, er)
+            worst_f = max(worst_f, abs(f1 - f2) / abs(f2))
+            worst_x = max(worst_x, float(np.max(np.abs(x_s - x2))))
+            total += -f1
+        assert res['value'] == pytest.approx(total, rel=1e-12)
+    assert worst_f <= 1e-9 and worst_x <= 2e-4, (worst_f, worst_x)
+
+
 def test_workloads_are_reproducible():
     """the BASELINE.json configurations as work lists: seeded, same clusterings every time."""
     from bamse_b200 import workloads
