@@ -591,16 +591,30 @@ k_enumerate_fast(ProblemView pv, FastTables ft, EnumWork w) {
 // of four terms are added outwards on both sides until the group's term nearest to the maximum is below
 // 2^-THETA of it (the terms decay at least geometrically from there: the same bound as the convolution windows).
 __device__ __forceinline__ float lane_log2dot(const float* __restrict__ g, const float* __restrict__ t, unsigned& groups) {
-    int lo = 0, hi = L - 1;
+    // search over the EVEN positions only: (v[2e], v[2e+1]) is one aligned 8-byte load per row, and the group of
+    // four that holds the last even position with a non-negative slope (or its right neighbour) holds the maximum.
+    // The kernel is bound by L1 wavefronts (every lane touches its own sector), so loads are what is counted.
+    const float2* g2 = reinterpret_cast<const float2*>(g);
+    const float2* t2 = reinterpret_cast<const float2*>(t);
+    int lo = 0, hi = L / 2;                           // first pair whose slope is negative, in [0, 256]
 #pragma unroll 1
     while (lo < hi) {
         const int mid = (lo + hi) >> 1;
-        const float s0 = __ldg(g + mid) + __ldg(t + mid), s1 = __ldg(g + mid + 1) + __ldg(t + mid + 1);
-        if (s1 >= s0) lo = mid + 1; else hi = mid;
+        const float2 a2 = __ldg(g2 + mid), b2 = __ldg(t2 + mid);
+        if ((a2.y + b2.y) >= (a2.x + b2.x)) lo = mid + 1; else hi = mid;
     }
+    // the maximum is at index 2 lo - 1, 2 lo or (slope between the pairs) just left of it: take the group of the
+    // last rising pair and let the outward walk find the rest
     const float4* g4 = reinterpret_cast<const float4*>(g);
     const float4* t4 = reinterpret_cast<const float4*>(t);
-    const int q0 = lo >> 2;
+    int q0 = lo > 0 ? (2 * lo - 1) >> 2 : 0;
+    {   // the true maximum may sit in the next group (2 lo is its first element): compare the two group maxima
+        if (2 * lo < L && ((2 * lo) >> 2) != q0) {
+            const float2 c2 = __ldg(g2 + lo), d2 = __ldg(t2 + lo);
+            const float2 e2 = __ldg(g2 + lo - 1), f2 = __ldg(t2 + lo - 1);
+            if ((c2.x + d2.x) > (e2.y + f2.y)) q0 = (2 * lo) >> 2;
+        }
+    }
     float4 a = __ldg(g4 + q0), b = __ldg(t4 + q0);
     float x0 = a.x + b.x, x1 = a.y + b.y, x2 = a.z + b.z, x3 = a.w + b.w;
     const float m0 = fmaxf(fmaxf(x0, x1), fmaxf(x2, x3));
