@@ -1397,13 +1397,16 @@ int bamse_score_topk(bamse_ctx* ctx, const double* clust_const, const double* th
         if (rc) return rc;
         ctx->last_evals = evals;
         recs.assign((size_t)P * ksel, bamse_record());
-        uint64_t bag[2] = {0, 0};                     // scalars [3] = records appended to the bag
+        uint64_t bag[2] = {0, 0};                     // scalars [3] = records appended to the bag, [14] = flat-list overflow
         BAMSE_CUDA_TRY(ctx, cudaMemcpyAsync(recs.data(), ctx->d_records.p, sizeof(bamse_record) * P * ksel, cudaMemcpyDeviceToHost, s));
         BAMSE_CUDA_TRY(ctx, cudaMemcpyAsync(bag, ctx->d_scalars.as<uint64_t>() + 3, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+        BAMSE_CUDA_TRY(ctx, cudaMemcpyAsync(bag + 1, ctx->d_scalars.as<uint64_t>() + 14, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
         BAMSE_CUDA_TRY(ctx, cudaStreamSynchronize(s));
         if (bag[0] > ctx->last_cand_cap)
             return ctx->fail(BAMSE_EINTERNAL, "bamse_score_topk: candidate bag overflow (%llu records, capacity %llu)",
                              (unsigned long long)bag[0], (unsigned long long)ctx->last_cand_cap);
+        if (bag[1] != 0)
+            return ctx->fail(BAMSE_EINTERNAL, "bamse_score_topk: the list of irregular trees overflowed its capacity");
         // worst selected total and list fill per parameter set, before the re-score reorders anything
         std::vector<double> t_last(P, -INFINITY);
         std::vector<int> n_sel(P, 0);

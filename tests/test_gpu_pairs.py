@@ -225,3 +225,28 @@ def test_cli_multi_gpu_output_is_byte_identical(tmp_path, monkeypatch, shim):
     assert one.keys() == two.keys()
     for n in one:
         assert one[n] == two[n], n
+
+
+def test_trivial_cluster_counts_in_a_mixed_problem(ctx, shim):
+    """K = 1 (one tree, no pair path) and K = 2, 3 next to K = 5: every tree of every clustering is ranked once,
+    scores equal the check mode."""
+    rng = np.random.default_rng(21)
+    Ks = [1, 2, 3, 5, 1]
+    M, Kmax = 2, 5
+    var = np.zeros((len(Ks), Kmax, M), dtype=np.int64)
+    ref = np.zeros((len(Ks), Kmax, M), dtype=np.int64)
+    for c, K in enumerate(Ks):
+        v, r = _problem(rng, K, M, 80)
+        var[c, :K], ref[c, :K] = v, r
+    ctx.upload_problem([0.003], Ks, var, ref)
+    total = sum(K ** (K - 1) for K in Ks)
+    assert total <= shim.TOPK_MAX * 20
+    rec32, _, cnt32 = ctx.score_topk(np.zeros((1, len(Ks))), topk=64, precision=shim.FP32)
+    rec64, _, cnt64 = ctx.score_topk(np.zeros((1, len(Ks))), topk=64, precision=shim.FP64)
+    assert cnt32[0] == cnt64[0] == 64
+    np.testing.assert_array_equal(rec32["tree"], rec64["tree"])
+    np.testing.assert_array_equal(rec32["clust"], rec64["clust"])
+    for c, K in enumerate(Ks):
+        s32, _ = ctx.score_range(0, c, 0, K ** (K - 1), shim.FP32)
+        s64, _ = ctx.score_range(0, c, 0, K ** (K - 1), shim.FP64)
+        assert np.max(np.abs(s32 - s64) / np.abs(s64)) <= FP32_RTOL
