@@ -91,6 +91,8 @@ struct bamse_ctx {
     uint64_t last_cand_cap = 0;   // capacity of the candidate bag of the last enumeration
     int shard_rank = 0, shard_world = 1;
     int plan_rank = 0, plan_world = 1;   // the shard the resident problem's plan / tables were made for
+    std::vector<int32_t> plan_shape;     // what plan_tables was last run for (problem shape + shard + switches)
+    bool plan_valid = false;
     int shard_plan = 1;      // BAMSE_OPT_SHARD_PLAN
     int collect_stats = 0;   // BAMSE_OPT_STATS
     int early_exit = 0;      // BAMSE_OPT_EARLY_EXIT
@@ -659,6 +661,7 @@ int bamse_debug_pair_stats(bamse_ctx* ctx, int K, int s, int r, int64_t* out4) t
         BAMSE_CUDA_TRY(ctx, cudaMemcpy(ctx->d_lut.p, forest_lut().lut.data(), sizeof(int16_t) * FT_LUT_SIZE, cudaMemcpyHostToDevice));
     }
     ctx->have_problem = false;                       // the resident problem may have been planned with another geometry
+    ctx->plan_valid = false;
     ctx->geom_s[K] = s; ctx->geom_r[K] = r;
     const int rc = ensure_pair_state(ctx, K);
     if (rc) return rc;
@@ -844,26 +847,50 @@ int bamse_upload_problem(bamse_ctx* ctx, int P, const double* err, int C, int M,
         for (int k = 0; k < K; ++k)
             for (int m = 0; m < M; ++m) {
                 const size_t i = ((size_t)c * Kmax + k) * M + m;
-                const int64_t a = var_counts[i], b = ref_counts[i];
-                if (a < 0 || b < 0)
+                if (var_counts[i] < 0 || ref_counts[i] < 0)
                     return ctx->fail(BAMSE_EINVAL, "bamse_upload_problem: negative read count at c=%d k=%d m=%d", c,
                                      k, m);
-                var[i] = (double)a; ref[i] = (double)b;
-                // gammaln(a+b+1) - gammaln(a+1) - gammaln(b+1)                  clustering.py:23
-                logc[i] = lgamma((double)(a + b) + 1.0) - lgamma((double)a + 1.0) - lgamma((double)b + 1.0);
             }
     }
-    // log(cf_x), log(1-cf_x) on x = linspace(0,1,512)                          clustering.py:21-23
+    // the host's share of distrib (clustering.py:21-23): the three lgamma terms per count pair and the logs of the
+    // grid, in fp64 with the C library's functions; a few worker threads when there are tens of thousands
     std::vector<double> logcf((size_t)P * L), log1mcf((size_t)P * L);
-    const double step = 1.0 / (double)(L - 1);
-    for (int p = 0; p < P; ++p)
-        for (int x = 0; x < L; ++x) {
-            const double gx = (x == L - 1) ? 1.0 : (double)x * step;              // numpy linspace
-            volatile double scaled = gx * (0.5 - err[p]);                          // no FMA contraction
-            const double cf = scaled + err[p];
-            logcf[(size_t)p * L + x] = log(cf);
-            log1mcf[(size_t)p * L + x] = log(1.0 - cf);
+    {
+        const double step = 1.0 / (double)(L - 1);
+        auto counts_part = [&](int c0, int c1) {
+            for (int c = c0; c < c1; ++c)
+                for (int k = 0; k < K_of_c[c]; ++k)
+                    for (int m = 0; m < M; ++m) {
+                        const size_t i = ((size_t)c * Kmax + k) * M + m;
+                        const int64_t a = var_counts[i], b = ref_counts[i];
+                        var[i] = (double)a; ref[i] = (double)b;
+                        // gammaln(a+b+1) - gammaln(a+1) - gammaln(b+1)          clustering.py:23
+                        logc[i] = lgamma((double)(a + b) + 1.0) - lgamma((double)a + 1.0) - lgamma((double)b + 1.0);
+                    }
+        };
+        auto grid_part = [&](int p0_, int p1_) {
+            for (int p = p0_; p < p1_; ++p)
+                for (int x = 0; x < L; ++x) {
+                    const double gx = (x == L - 1) ? 1.0 : (double)x * step;      // numpy linspace
+                    volatile double scaled = gx * (0.5 - err[p]);                  // no FMA contraction
+                    const double cf = scaled + err[p];
+                    logcf[(size_t)p * L + x] = log(cf);
+                    log1mcf[(size_t)p * L + x] = log(1.0 - cf);
+                }
+        };
+        const size_t work = ncnt * 3 + (size_t)P * L * 2;
+        const int n_thr = work < 20000 ? 1 : (int)std::max(1u, std::min(8u, std::thread::hardware_concurrency()));
+        if (n_thr == 1) { counts_part(0, C); grid_part(0, P); }
+        else {
+            std::vector<std::thread> pool;
+            for (int t = 0; t < n_thr; ++t)
+                pool.emplace_back([&, t]() {
+                    counts_part((int)((int64_t)C * t / n_thr), (int)((int64_t)C * (t + 1) / n_thr));
+                    grid_part((int)((int64_t)P * t / n_thr), (int)((int64_t)P * (t + 1) / n_thr));
+                });
+            for (auto& th : pool) th.join();
         }
+    }
     const size_t nrows = (size_t)P * C * M * Kmax;
     BAMSE_CUDA_TRY(ctx, ctx->d_K.ensure(sizeof(int32_t) * C));
     BAMSE_CUDA_TRY(ctx, ctx->d_p0.ensure(sizeof(double) * C));
@@ -888,8 +915,27 @@ int bamse_upload_problem(bamse_ctx* ctx, int P, const double* err, int C, int M,
     BAMSE_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_logc.p, logc.data(), sizeof(double) * ncnt, cudaMemcpyHostToDevice, s));
     BAMSE_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_logcf.p, logcf.data(), sizeof(double) * P * L, cudaMemcpyHostToDevice, s));
     BAMSE_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_log1mcf.p, log1mcf.data(), sizeof(double) * P * L, cudaMemcpyHostToDevice, s));
-    int rc = plan_tables(ctx);
-    if (rc) return rc;
+    // the plan (geometry, table bases, sharding, data-independent tables) depends on the SHAPE of the problem only:
+    // a same-shaped problem (other counts / error rates: sweeps, bootstraps, the next batch) reuses it
+    std::vector<int32_t> shape = {P, C, M, Kmax, ctx->shard_rank, ctx->shard_world, ctx->shard_plan, pairs_enabled() ? 1 : 0};
+    shape.insert(shape.end(), K_of_c, K_of_c + C);
+    {   // ... and on the environment switches plan_tables reads
+        uint32_t h = 2166136261u;
+        for (const char* name : {"BAMSE_FOREST_S", "BAMSE_FOREST_SH", "BAMSE_PAIR_R", "BAMSE_TABLE_GB", "BAMSE_PROGTAB", "BAMSE_SHARD_PLAN"}) {
+            const char* v = getenv(name);
+            for (const char* q = v ? v : "-"; *q; ++q) { h ^= (unsigned char)*q; h *= 16777619u; }
+            h ^= 0xffu; h *= 16777619u;
+        }
+        shape.push_back((int32_t)h);
+    }
+    int rc = BAMSE_OK;
+    if (!ctx->plan_valid || shape != ctx->plan_shape) {
+        ctx->plan_valid = false;
+        rc = plan_tables(ctx);
+        if (rc) return rc;
+        ctx->plan_shape = shape;
+        ctx->plan_valid = true;
+    }
     rc = launch_table_build(ctx);
     if (rc) return rc;
     BAMSE_CUDA_TRY(ctx, cudaGetLastError());
