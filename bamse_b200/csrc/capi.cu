@@ -134,7 +134,7 @@ struct bamse_ctx {
 };
 
 constexpr int PROGTAB_KMAX = 8;      // K = 8: 2 M programs, 134 MB
-constexpr int PAIRTAB_KMAX = 9;      // K = 9: 43 M entries, 344 MB; above, the cut is computed in the kernel
+constexpr int PAIRTAB_KMAX = 10;     // K = 10: 10^9 entries, 8 GB (kept across uploads); above, the cut is computed in the kernel
 constexpr int TOPK_INTERNAL = BAMSE_TOPK_INTERNAL;   // preselection lists may grow to this size (public topk <= BAMSE_TOPK_MAX)
 
 // A C++ exception (std::bad_alloc of a staging vector, in practice) must not cross the C ABI: the entry
@@ -175,19 +175,18 @@ static int ensure_pair_state(bamse_ctx* ctx, int K) {
     ps.s = ps.r = -1;
     const ForestIndex fi = make_forest_index(K, sK, 1);
     const PairGeom g = make_pair_geom(K, sK, rK);
-    if (fi.nf >= (1 << 24) || g.nt >= (1u << 24)) return ctx->fail(BAMSE_EINTERNAL, "pair geometry of K=%d exceeds 24-bit row ids", K);
+    if (fi.nf >= (1 << PAIR_FG_BITS)) return ctx->fail(BAMSE_EINTERNAL, "pair geometry of K=%d exceeds %u-bit inside row ids", K, PAIR_FG_BITS);
     cudaStream_t st = ctx->stream;
     const uint64_t n_trees = ipow_u64(K, K - 1);
     ps.has_tab = K <= PAIRTAB_KMAX;
-    if (ps.has_tab) BAMSE_CUDA_TRY(ctx, ps.tab.ensure(sizeof(uint64_t) * n_trees));
+    if (const char* e = getenv("BAMSE_PAIRTAB_KMAX")) ps.has_tab = K <= atoi(e);
     DBuf used;
     const size_t used_bytes = ((size_t)g.nt + 15) / 8 * 8;
     cudaError_t e = used.ensure(used_bytes + 8);
     if (e != cudaSuccess) return ctx->fail(BAMSE_ENOMEM, "pair state: %s", cudaGetErrorString(e));
     cudaMemsetAsync(used.p, 0, used_bytes + 8, st);
     unsigned long long* d_nirr = reinterpret_cast<unsigned long long*>(used.as<uint8_t>() + used_bytes);
-    launch_build_pair_table(fi, g, n_trees, ctx->d_lut.as<int16_t>(), ps.has_tab ? ps.tab.as<uint64_t>() : nullptr,
-                            used.as<uint8_t>(), d_nirr, st);
+    launch_build_pair_table(fi, g, n_trees, ctx->d_lut.as<int16_t>(), nullptr, used.as<uint8_t>(), d_nirr, nullptr, st);
     ctx->launches++;
     std::vector<uint8_t> h_used(used_bytes + 8);
     e = cudaMemcpyAsync(h_used.data(), used.p, used_bytes + 8, cudaMemcpyDeviceToHost, st);
@@ -241,9 +240,14 @@ static int ensure_pair_state(bamse_ctx* ctx, int K) {
     BAMSE_CUDA_TRY(ctx, ps.recipes.ensure(sizeof(CtxRecipe) * std::max<size_t>(comp.size(), 1)));
     BAMSE_CUDA_TRY(ctx, cudaMemcpy(ps.map.p, map.data(), sizeof(uint32_t) * map.size(), cudaMemcpyHostToDevice));
     BAMSE_CUDA_TRY(ctx, cudaMemcpy(ps.recipes.p, comp.data(), sizeof(CtxRecipe) * comp.size(), cudaMemcpyHostToDevice));
+    if (ps.nt >= (1u << PAIR_T_BITS)) return ctx->fail(BAMSE_EINTERNAL, "pair geometry of K=%d needs more than %u-bit context row ids", K, PAIR_T_BITS);
     if (ps.has_tab) {
-        launch_remap_pair_table(ps.tab.as<uint64_t>(), n_trees, ps.map.as<uint32_t>(), st);
-        ctx->launches++;
+        if (ps.tab.ensure(sizeof(uint64_t) * n_trees) != cudaSuccess) { cudaGetLastError(); ps.has_tab = false; }   // no room: cut in the kernel
+        else {
+            launch_build_pair_table(fi, g, n_trees, ctx->d_lut.as<int16_t>(), ps.tab.as<uint64_t>(), nullptr, nullptr,
+                                    ps.map.as<uint32_t>(), st);
+            ctx->launches++;
+        }
     }
     BAMSE_CUDA_TRY(ctx, cudaGetLastError());
     ps.n_irregular = n_irr;
@@ -339,7 +343,7 @@ static int plan_tables(bamse_ctx* ctx) {
         int& sK = ctx->geom_s[K];
         int& rK = ctx->geom_r[K];
         if (!pairs_on || K < 2 || sK + rK < K || rK - 1 > sK) rK = 0;
-        if (rK > 0 && (make_forest_index(K, sK, 1).nf >= (1 << 24) || make_pair_geom(K, sK, rK).nt >= (1u << 24))) rK = 0;
+        if (rK > 0 && make_forest_index(K, sK, 1).nf >= (1 << PAIR_FG_BITS)) rK = 0;
         if (rK == 0) sK = program_forest_s(K, sK);     // programs only: nothing above the 16-bit row ids is needed
         ctx->geom_sh[K] = std::min(ctx->geom_sh[K], program_forest_s(K, sK));
     }

@@ -344,36 +344,31 @@ __global__ void __launch_bounds__(FAST_THREADS, BAMSE_BUILD_CTAS) k_ctx_level(Pr
     for (int t = 0; t < 16; ++t) out[lane + 32 * t] = a[L - 1 - lane - 32 * t] + add2;
 }
 
-// Pair table of a cluster count (data independent): the cut of every tree index, the context rows in use.
+// Pair table of a cluster count (data independent), two passes over all tree indices: pass 1 (out == NULL) marks
+// the context rows some regular tree refers to and counts the irregular trees; pass 2 (map != NULL) writes the
+// entries with the compact context row.
 __global__ void __launch_bounds__(128) k_build_pair_table(ForestIndex fi, PairGeom g, uint64_t n_trees,
                                                           const int16_t* __restrict__ lut, uint64_t* __restrict__ out,
-                                                          uint8_t* __restrict__ used, unsigned long long* n_irregular) {
+                                                          uint8_t* __restrict__ used, unsigned long long* n_irregular,
+                                                          const uint32_t* __restrict__ map) {
     const uint64_t tree = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (tree >= n_trees) return;
     int8_t parent[KMAX];
     decode_tree(fi.K, tree, parent);
     uint32_t fg = 0, t = 0;
     const bool reg = classify_tree(fi.K, parent, fi, lut, g, &fg, &t);
+    if (!out) {
+        if (reg) used[t] = 1;
+        else atomicAdd(n_irregular, 1ull);
+        return;
+    }
     uint64_t e = 0;
     if (reg) {
-        used[t] = 1;
-        if (out) {
-            TreeProgram ref;
-            build_program(fi.K, parent, nullptr, &ref);
-            e = pair_entry(fg, t, (uint32_t)ref.scre);
-        }
-    } else atomicAdd(n_irregular, 1ull);
-    if (out) out[tree] = e;
-}
-
-__global__ void __launch_bounds__(256) k_remap_pair_table(uint64_t* __restrict__ tab, uint64_t n_trees,
-                                                          const uint32_t* __restrict__ map) {
-    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_trees) return;
-    const uint64_t e = tab[i];
-    if (!e) return;
-    const uint32_t t = (uint32_t)(e >> 24) & 0xffffffu;
-    tab[i] = (e & ~(0xffffffull << 24)) | ((uint64_t)map[t] << 24);
+        TreeProgram ref;
+        build_program(fi.K, parent, nullptr, &ref);
+        e = pair_entry(fg, map[t], (uint32_t)ref.scre);
+    }
+    out[tree] = e;
 }
 
 __global__ void k_flat_prefix(int P, const unsigned long long* __restrict__ cnt, const unsigned long long* __restrict__ off,
@@ -713,8 +708,7 @@ __global__ void __launch_bounds__(PAIR_THREADS, 6) k_enumerate_pairs(ProblemView
         bool reg = false;
         if (valid) {
             if (pk->pair_tab) {
-                const uint64_t e = __ldg(pk->pair_tab + tree);
-                scre = (uint32_t)(e >> 48); fg = (uint32_t)e & 0xffffffu; tr = (uint32_t)(e >> 24) & 0xffffffu;
+                pair_unpack(__ldg(pk->pair_tab + tree), &fg, &tr, &scre);
                 reg = scre != 0;
             } else if (pk->g.r > 0) {
                 int8_t parent[KMAX];
@@ -856,12 +850,9 @@ void launch_forest_scan_top(const ProblemView& pv, const FastTables& ft, int max
 }
 
 void launch_build_pair_table(const ForestIndex& fi, const PairGeom& g, uint64_t n_trees, const int16_t* d_lut,
-                             uint64_t* out, uint8_t* used, unsigned long long* n_irregular, cudaStream_t s) {
-    k_build_pair_table<<<(unsigned)((n_trees + 127) / 128), 128, 0, s>>>(fi, g, n_trees, d_lut, out, used, n_irregular);
-}
-
-void launch_remap_pair_table(uint64_t* tab, uint64_t n_trees, const uint32_t* d_map, cudaStream_t s) {
-    k_remap_pair_table<<<(unsigned)((n_trees + 255) / 256), 256, 0, s>>>(tab, n_trees, d_map);
+                             uint64_t* out, uint8_t* used, unsigned long long* n_irregular, const uint32_t* d_map,
+                             cudaStream_t s) {
+    k_build_pair_table<<<(unsigned)((n_trees + 127) / 128), 128, 0, s>>>(fi, g, n_trees, d_lut, out, used, n_irregular, d_map);
 }
 
 static size_t fast_smem_bytes(int topk, bool framed = false, int slots = FAST_SLOTS) {

@@ -109,11 +109,12 @@ void launch_enumerate_fast(const ProblemView& pv, const FastTables& ft, const En
 // context tables, level q (max_rows = the largest number of q-node contexts of any cluster count present)
 void launch_ctx_level(const ProblemView& pv, const FastTables& ft, int q, int max_rows, float* T, unsigned long long* stats,
                       cudaStream_t s);
-// pair table of a cluster count: out[tree] = pair_entry (context row in the FULL index space), used[row] = 1 for
-// every context row some regular tree refers to, *n_irregular += irregular trees.  out == NULL: mark only.
+// pair table of a cluster count, two passes: out == NULL: used[row] = 1 for every context row (FULL index space)
+// some regular tree refers to, *n_irregular += irregular trees; out != NULL: out[tree] = pair_entry with the
+// compact context row d_map[row]
 void launch_build_pair_table(const ForestIndex& fi, const PairGeom& g, uint64_t n_trees, const int16_t* d_lut,
-                             uint64_t* out, uint8_t* used, unsigned long long* n_irregular, cudaStream_t s);
-void launch_remap_pair_table(uint64_t* tab, uint64_t n_trees, const uint32_t* d_map, cudaStream_t s);
+                             uint64_t* out, uint8_t* used, unsigned long long* n_irregular, const uint32_t* d_map,
+                             cudaStream_t s);
 int enumerate_pairs_grid_size(int device);
 int enumerate_pairs_workers(int grid);
 // mode 0: tree-major; 1 + 2: sample-major (accumulate per sample into w.part, then sum and rank); the segments of

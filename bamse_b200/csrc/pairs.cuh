@@ -17,8 +17,8 @@
 // by one pointwise product, one suffix sum and one correlation: the same level-by-level build as the inside
 // tables.  Per (parameter set, clustering, sample) the tables hold every forest with <= s nodes and every
 // context with <= r nodes; a tree whose best cut has K - r <= |S| <= s ("regular") costs ONE windowed dot product
-// of two table rows per sample instead of convolutions.  K = 7 (s = 4, r = 4): 15 001 rows serve all 823 543
-// trees; K = 10 (s = 5, r = 5): 1.2 M rows serve 88 % of the 10^9 trees.  The other trees ("irregular") run
+// of two table rows per sample instead of convolutions.  K = 7 (s = 4, r = 4): 7 826 rows in use serve all 117 649
+// trees; K = 10 (s = 5, r = 6): 2.7 M rows serve 98 % of the 10^9 trees.  The other trees ("irregular") run
 // the table-driven programs of forest.cuh.
 //
 // Context row index inside the block of one (p, c, m):  base[q] + rank(R) * q^q + tree_index(tau) * q + local(v),
@@ -159,10 +159,17 @@ struct CtxRecipe {
 };
 static_assert(sizeof(CtxRecipe) == 12, "recipe layout");
 
-// One entry of a per-K pair table (indexed by tree index): FG row | context row << 24 | scre << 48; scre == 0
-// marks an irregular tree.  Row ids stay below 2^24, scre below 2^16 for K <= 9 (8! = 40 320).
+// One entry of a per-K pair table (indexed by tree index): inside row (20 bits) | compact context row (22 bits) << 20
+// | scre (22 bits) << 42; 0 marks an irregular tree (scre >= 1 otherwise).  K = 10: 354 907 inside rows, 2.4 M
+// context rows in use, scre <= 9! = 362 880.
+constexpr uint32_t PAIR_FG_BITS = 20, PAIR_T_BITS = 22, PAIR_SCRE_BITS = 22;
 __host__ __device__ inline uint64_t pair_entry(uint32_t fg_row, uint32_t t_row, uint32_t scre) {
-    return (uint64_t)fg_row | ((uint64_t)t_row << 24) | ((uint64_t)scre << 48);
+    return (uint64_t)fg_row | ((uint64_t)t_row << PAIR_FG_BITS) | ((uint64_t)scre << (PAIR_FG_BITS + PAIR_T_BITS));
+}
+__host__ __device__ inline void pair_unpack(uint64_t e, uint32_t* fg_row, uint32_t* t_row, uint32_t* scre) {
+    *fg_row = (uint32_t)e & ((1u << PAIR_FG_BITS) - 1u);
+    *t_row = (uint32_t)(e >> PAIR_FG_BITS) & ((1u << PAIR_T_BITS) - 1u);
+    *scre = (uint32_t)(e >> (PAIR_FG_BITS + PAIR_T_BITS));
 }
 
 }  // namespace bamse

@@ -295,9 +295,9 @@ def test_committed_bench_lines_follow_the_contract():
     """the bench lines kept under profiles/ carry every key of the bench.py contract."""
     import glob
     import json
-    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "configs", "bench_c*.json")) +
-                   glob.glob(os.path.join(ROOT, "profiles", "scale", "scale_c2_*.json")))
-    assert len(files) >= 6
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "scale", "r02_scale_c*.json")) +
+                   glob.glob(os.path.join(ROOT, "profiles", "scale", "r01", "scale_c2_*.json")))
+    assert len(files) >= 12
     for fn in files:
         d = json.load(open(fn))
         for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",

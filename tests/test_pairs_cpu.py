@@ -97,7 +97,7 @@ def test_pair_cuts_for_large_k(built_library, K):
     nodes and the context <= r nodes (checked through the recipes' node counts), extreme shapes included."""
     lib = cuda_shim.load_library()
     s, r, nf, nt = pair_geometry(lib, K)
-    assert nf < (1 << 24) and nt < (1 << 24)
+    assert nf < (1 << 20)
     rec = recipes(lib, K, s, nf)
     rng = np.random.default_rng(K)
     trees = [orc.decode_tree(K, int(rng.integers(0, K ** (K - 1)))) for _ in range(600)]
