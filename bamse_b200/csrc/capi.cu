@@ -119,6 +119,7 @@ struct bamse_ctx {
         f.FG = d_FG.as<float>(); f.FSG = d_FSG.as<float>(); f.FH = d_FH.as<float>();
         f.T = d_T.as<float>(); f.pk = d_pk.as<PairK>();
         f.pcm_list = d_pcm.as<int32_t>(); f.n_pcm = n_pcm; f.grid_blocks = 1;
+        f.shard_rank = plan_rank; f.shard_world = plan_world;
         f.tb = d_tb.as<TableBase>(); f.lut = d_lut.as<int16_t>();
         f.recipes = d_recipe_ptrs.as<const ForestRecipe*>();
         f.level_order = d_order_ptrs.as<const uint32_t*>();
@@ -369,6 +370,7 @@ static int plan_tables(bamse_ctx* ctx) {
                 t.fi = make_forest_index(K, ctx->geom_s[K], ctx->geom_sh[K]);
                 t.s_prog = program_forest_s(K, ctx->geom_s[K]);
                 t.mine = ctx->owner.empty() || ctx->owner[(size_t)p * C + c] < 0 || ctx->owner[(size_t)p * C + c] == ctx->shard_rank;
+                t.split = (!ctx->owner.empty() && ctx->owner[(size_t)p * C + c] < 0 && ctx->geom_r[K] > 0) ? 1 : 0;
                 t.fg_row = (uint32_t)fg_rows; t.fsg_row = (uint32_t)fsg_rows; t.fh_row = (uint32_t)fh_rows; t.t_row = (uint32_t)t_rows;
                 // scanned messages: of every forest the programs may push (<= s_prog nodes) and of the children
                 // forests the inside recipes read (< s nodes)
@@ -1146,8 +1148,11 @@ static int enumerate_dev(bamse_ctx* ctx, const double* d_const, const double* d_
                 const int own = ctx->owner.empty() ? -1 : ctx->owner[(size_t)p * C + c];
                 // upper bound of this rank's trees of (p, c): an interleaved share, the whole range, or nothing
                 const uint64_t mine = own < 0 ? (T + ctx->shard_world - 1) / ctx->shard_world : (own == ctx->shard_rank ? T : 0);
-                if ((mask_pairs >> K) & 1u) { trees_pairs += mine; irr_cap += std::min<uint64_t>(mine, ctx->pairs[K].n_irregular); }
-                else trees_prog += mine;
+                if ((mask_pairs >> K) & 1u) {
+                    // a split (p, c) is walked in full by the pair kernel of every rank (node-set sharding)
+                    trees_pairs += (own < 0 && !ctx->owner.empty()) ? T : mine;
+                    irr_cap += std::min<uint64_t>(mine + 1, ctx->pairs[K].n_irregular);
+                } else trees_prog += mine;
             }
         }
         flat_off[P] = irr_cap;
@@ -1178,7 +1183,7 @@ static int enumerate_dev(bamse_ctx* ctx, const double* d_const, const double* d_
     if (fresh_scalars) BAMSE_CUDA_TRY(ctx, cudaMemsetAsync(scal, 0, sizeof(uint64_t) * 16, s));
     else {
         BAMSE_CUDA_TRY(ctx, cudaMemsetAsync(scal, 0, sizeof(uint64_t) * 4, s));
-        BAMSE_CUDA_TRY(ctx, cudaMemsetAsync(scal + 10, 0, sizeof(uint64_t) * 6, s));
+        BAMSE_CUDA_TRY(ctx, cudaMemsetAsync(scal + 9, 0, sizeof(uint64_t) * 7, s));   // [9] trees taken by the pair kernel
     }
     if (topk > 0) BAMSE_CUDA_TRY(ctx, ctx->d_cand.ensure(sizeof(bamse_record) * (size_t)cand_cap));
     unsigned long long* flat_meta = nullptr;         // [P + 1] region offsets, [P] counts, [P + 1] running sums
@@ -1205,13 +1210,13 @@ static int enumerate_dev(bamse_ctx* ctx, const double* d_const, const double* d_
     } else {
         if (mask_prog || !mask_pairs) {
             launch_build_segments(P, C, ctx->d_K.as<int32_t>(), d_const, d_thr, d_begin, d_end, slack_abs, slack_rel,
-                                  chunk, 1, ctx->shard_rank, ctx->shard_world, mask_pairs ? mask_prog : 0xffffffffu, d_owner,
+                                  chunk, 1, ctx->shard_rank, ctx->shard_world, mask_pairs ? mask_prog : 0xffffffffu, 0, d_owner,
                                   ctx->d_segs.as<Segment>(), scal, scal + 1, s);
             ctx->launches++;
         }
         if (mask_pairs) {
             launch_build_segments(P, C, ctx->d_K.as<int32_t>(), d_const, d_thr, d_begin, d_end, slack_abs, slack_rel,
-                                  chunk2, reps2, ctx->shard_rank, ctx->shard_world, mask_pairs, d_owner,
+                                  chunk2, reps2, ctx->shard_rank, ctx->shard_world, mask_pairs, d_owner ? 1 : 0, d_owner,
                                   ctx->d_segs2.as<Segment>(), scal + 10, scal + 11, s);
             ctx->launches++;
         }
@@ -1226,6 +1231,7 @@ static int enumerate_dev(bamse_ctx* ctx, const double* d_const, const double* d_
     w.dense_logscre = d_dense_logscre;
     w.stats = reinterpret_cast<unsigned long long*>(scal + 4);
     w.samples_done = reinterpret_cast<unsigned long long*>(scal + 8);
+    w.trees_done = reinterpret_cast<unsigned long long*>(scal + 9);
     w.lists = nullptr;
     if (precision == BAMSE_FP32) {
         BAMSE_CUDA_TRY(ctx, ctx->d_lists.ensure(sizeof(bamse_record) * (size_t)workers * (size_t)(topk > 0 ? topk : 1)));
@@ -1340,6 +1346,9 @@ int bamse_score_range(bamse_ctx* ctx, int p, int c, uint64_t tree_begin, int64_t
     if (tree_begin > T || (uint64_t)n > T - tree_begin)
         return ctx->fail(BAMSE_EINVAL, "bamse_score_range: range exceeds K^(K-1)=%llu", (unsigned long long)T);
     if (n == 0) return BAMSE_OK;
+    if (precision == BAMSE_FP32 && !ctx->owner.empty() && ctx->owner[(size_t)p * ctx->C + c] != ctx->shard_rank)
+        return ctx->fail(BAMSE_ESTATE, "bamse_score_range: under the sharding plan this rank does not hold all tables of "
+                                       "(p=%d, c=%d); upload the problem unsharded for dense ranges", p, c);
     BAMSE_CUDA_TRY(ctx, ctx->d_dense0.ensure(sizeof(double) * n));
     BAMSE_CUDA_TRY(ctx, ctx->d_dense1.ensure(sizeof(double) * n));
     Segment seg;
@@ -1402,16 +1411,22 @@ int bamse_score_topk(bamse_ctx* ctx, const double* clust_const, const double* th
         BAMSE_CUDA_TRY(ctx, ctx->d_thr.ensure(sizeof(double) * P * C));
         BAMSE_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_thr.p, threshold, sizeof(double) * P * C, cudaMemcpyHostToDevice, s));
     }
-    int64_t evals = 0;
+    int64_t evals = 0, evals_prog = 0;
+    bool evals_split_pending = false;
     for (int p = 0; p < P; ++p)
         for (int c = 0; c < C; ++c) {
             const int K = ctx->K_of_c[c];
             const uint64_t T = ipow_u64(K, K - 1);
             uint64_t b = tree_begin ? tree_begin[c] : 0, e = tree_end ? std::min<uint64_t>(tree_end[c], T) : T;
             const int own = ctx->owner.empty() ? -1 : ctx->owner[(size_t)p * C + c];
-            if (own >= 0) { if (own == ctx->shard_rank && b < e) evals += (int64_t)(e - b); }
+            int64_t n = 0;
+            if (own >= 0) { if (own == ctx->shard_rank && b < e) n = (int64_t)(e - b); }
             else if (b < e && e - b > (uint64_t)ctx->shard_rank)
-                evals += (int64_t)((e - b - ctx->shard_rank + ctx->shard_world - 1) / ctx->shard_world);
+                n = (int64_t)((e - b - ctx->shard_rank + ctx->shard_world - 1) / ctx->shard_world);
+            evals += n;
+            // trees that go through the pair kernel are counted there when some (p, c) is split by node sets
+            if (!(precision == BAMSE_FP32 && ctx->geom_r[K] > 0)) evals_prog += n;
+            if (precision == BAMSE_FP32 && ctx->geom_r[K] > 0 && own < 0 && !ctx->owner.empty()) evals_split_pending = true;
         }
     if (tree_begin) {
         BAMSE_CUDA_TRY(ctx, ctx->d_begin.ensure(sizeof(uint64_t) * C));
@@ -1457,6 +1472,12 @@ int bamse_score_topk(bamse_ctx* ctx, const double* clust_const, const double* th
                              (unsigned long long)bag[0], (unsigned long long)ctx->last_cand_cap);
         if (bag[1] != 0)
             return ctx->fail(BAMSE_EINTERNAL, "bamse_score_topk: the list of irregular trees overflowed its capacity");
+        if (precision == BAMSE_FP32 && evals_split_pending) {
+            // the share of a split (p, c) is decided by the pair kernel (node sets): take its own count
+            uint64_t taken = 0;
+            BAMSE_CUDA_TRY(ctx, cudaMemcpy(&taken, ctx->d_scalars.as<uint64_t>() + 9, sizeof taken, cudaMemcpyDeviceToHost));
+            ctx->last_evals = evals_prog + (int64_t)taken;
+        }
         // worst selected total and list fill per parameter set, before the re-score reorders anything
         std::vector<double> t_last(P, -INFINITY);
         std::vector<int> n_sel(P, 0);

@@ -206,6 +206,9 @@ __global__ void __launch_bounds__(FAST_THREADS, BAMSE_BUILD_CTAS) k_forest_level
     // rows of a level in the order "convolutions first": the warps of a CTA get rows of the same kind
     const int row = (int)ft.level_order[tb->fi.K][tb->fi.base[n] + i];
     const ForestRecipe rec = ft.recipes[tb->fi.K][row];
+    // split (p, c): a top-level row is read only by the rank that scores the packs on its node set (when the
+    // programs may push it too -- s_prog == s -- every rank keeps all rows)
+    if (tb->split && n == tb->fi.s && tb->s_prog < n && node_set_owner(rec.mask, ft.shard_world) != ft.shard_rank) return;
     const size_t frow = (size_t)tb->fg_row + (size_t)m * tb->fi.nf;
     const size_t srow = (size_t)tb->fsg_row + (size_t)m * tb->nfsg;
     const float add2 = (float)((pv.p0[c] - 6.2383246250395077847550890931236) * 1.4426950408889634074);
@@ -316,6 +319,9 @@ __global__ void __launch_bounds__(FAST_THREADS, BAMSE_BUILD_CTAS) k_ctx_level(Pr
     if (i >= pk->lbase[q + 1] - pk->lbase[q]) return;
     const uint32_t row = pk->lbase[q] + i;
     const CtxRecipe rec = pk->recipes[row];
+    // split (p, c): a top-level context is read only by the rank that scores the packs on the complement
+    if (tb->split && q == pk->g.r &&
+        node_set_owner(((1u << tb->fi.K) - 1u) & ~(uint32_t)rec.mask, ft.shard_world) != ft.shard_rank) return;
     const size_t trow = (size_t)tb->t_row + (size_t)m * pk->nt;
     const float add2 = (float)((pv.p0[c] - 6.2383246250395077847550890931236) * 1.4426950408889634074);
     warp_init_guards(ws, lane);
@@ -666,7 +672,7 @@ __global__ void __launch_bounds__(PAIR_THREADS, 6) k_enumerate_pairs(ProblemView
     const uint64_t total_all = *w.total_chunks;
     const uint64_t total = MODE == 2 ? total_all / (uint64_t)reps : total_all;
     const uint64_t slots = total_all / (uint64_t)reps * 32ull;      // tree slots of the launch (sample-major)
-    unsigned st_groups = 0, st_samples = 0;
+    unsigned st_groups = 0, st_samples = 0, st_trees = 0;
 
     auto flush = [&]() {
         if (lane == 0 && ntop > 0) {
@@ -722,9 +728,18 @@ __global__ void __launch_bounds__(PAIR_THREADS, 6) k_enumerate_pairs(ProblemView
                 }
             }
         }
+        // a (p, c) split over all ranks: every rank walks all tree indices (8 bytes each), takes the regular trees
+        // whose pack sits on one of its node sets and every world-th irregular tree
+        bool mine = true;
+        if (tb->split && valid) {
+            if (reg) mine = node_set_owner(ft.recipes[seg.K][fg].mask, ft.shard_world) == ft.shard_rank;
+            else mine = (int)(tree % (uint64_t)ft.shard_world) == ft.shard_rank;
+        }
+        reg = reg && mine;
+        if (MODE != 1 || m_one == 0) st_trees += (valid && mine) ? 1u : 0u;
         // irregular trees: to the flat list of this parameter set (warp-aggregated append), once
         if (MODE == 0 || (MODE == 1 && m_one == 0)) {
-            const bool irr = valid && !reg;
+            const bool irr = valid && mine && !reg;
             const unsigned irr_mask = __ballot_sync(0xffffffffu, irr);
             if (irr_mask) {
                 unsigned long long base = 0;
@@ -803,6 +818,8 @@ __global__ void __launch_bounds__(PAIR_THREADS, 6) k_enumerate_pairs(ProblemView
     if (MODE != 2) {
         if (w.stats && lane == 0) atomicAdd(w.stats + 0, 4ull * st_groups + st_samples);
         if (w.samples_done && lane == 0) atomicAdd(w.samples_done, (unsigned long long)st_samples);
+        st_trees = __reduce_add_sync(0xffffffffu, st_trees);
+        if (w.trees_done && lane == 0 && st_trees) atomicAdd(w.trees_done, (unsigned long long)st_trees);
     }
 }
 

@@ -41,7 +41,7 @@ __global__ void __launch_bounds__(256) k_build_segments(int P, int C, const int3
                                                         const double* __restrict__ cconst, const double* __restrict__ thr,
                                                         const uint64_t* __restrict__ begin, const uint64_t* __restrict__ end,
                                                         double slack_abs, double slack_rel, int chunk, int reps, int shard_rank,
-                                                        int shard_world, uint32_t k_mask, const int32_t* __restrict__ owner,
+                                                        int shard_world, uint32_t k_mask, int split_full, const int32_t* __restrict__ owner,
                                                         Segment* __restrict__ segs,
                                                         uint64_t* __restrict__ total_chunks, uint64_t* __restrict__ total_trees) {
     // one thread per (p, c) fills its segment, then thread 0 turns chunk counts into prefix sums
@@ -58,7 +58,7 @@ __global__ void __launch_bounds__(256) k_build_segments(int P, int C, const int3
         // sharding plan: owner < 0 (or no plan) = interleaved over all ranks (indices b + rank, b + rank + world,
         // ... below e), owner == rank = this rank scores the whole range, any other owner = nothing here
         const int own = owner ? owner[i] : -1;
-        const int rank = own < 0 ? shard_rank : 0, world = own < 0 ? shard_world : 1;
+        const int rank = (own < 0 && !split_full) ? shard_rank : 0, world = (own < 0 && !split_full) ? shard_world : 1;
         const uint64_t span = (own >= 0 && own != shard_rank) || !((k_mask >> K) & 1u) ? 0 : e - b;
         s.stride = world;
         s.tree_begin = b + (uint64_t)rank;
@@ -86,10 +86,11 @@ __global__ void __launch_bounds__(256) k_build_segments(int P, int C, const int3
 
 void launch_build_segments(int P, int C, const int32_t* d_K_of_c, const double* d_const, const double* d_thr,
                            const uint64_t* d_begin, const uint64_t* d_end, double slack_abs, double slack_rel,
-                           int chunk, int reps, int shard_rank, int shard_world, uint32_t k_mask, const int32_t* d_owner,
+                           int chunk, int reps, int shard_rank, int shard_world, uint32_t k_mask, int split_full,
+                           const int32_t* d_owner,
                            Segment* d_segs, uint64_t* d_total_chunks, uint64_t* d_total_trees, cudaStream_t s) {
     k_build_segments<<<1, 256, 0, s>>>(P, C, d_K_of_c, d_const, d_thr, d_begin, d_end, slack_abs, slack_rel, chunk,
-                                      reps, shard_rank, shard_world, k_mask, d_owner, d_segs, d_total_chunks, d_total_trees);
+                                      reps, shard_rank, shard_world, k_mask, split_full, d_owner, d_segs, d_total_chunks, d_total_trees);
 }
 
 // --------------------------------------------------------------------- top-k helper

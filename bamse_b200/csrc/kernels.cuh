@@ -69,6 +69,7 @@ struct EnumWork {
     int flat_mode;
     bamse_record* lists2;                 // the pair kernel's per-warp lists
     float* part;                          // sample-major pair path: per-sample log2 results [M][tree slots]
+    unsigned long long* trees_done;       // trees this rank took in k_enumerate_pairs (regular + irregular)
 };
 
 void launch_tables(const ProblemView& pv, const double* d_var, const double* d_ref, const double* d_logc,
@@ -77,7 +78,8 @@ void launch_tables(const ProblemView& pv, const double* d_var, const double* d_r
 void launch_build_segments(int P, int C, const int32_t* d_K_of_c, const double* d_const, const double* d_thr,
                            const uint64_t* d_begin, const uint64_t* d_end, double slack_abs, double slack_rel,
                            int chunk, int reps /* chunks per `chunk` trees */, int shard_rank, int shard_world,
-                           uint32_t k_mask /* cluster counts that take part */,
+                           uint32_t k_mask /* cluster counts that take part */, int split_full /* 1: a (p, c) split over
+                           the ranks gets its whole range on every rank (node-set sharding inside the pair kernel) */,
                            const int32_t* d_owner /* [P][C] sharding plan or NULL */, Segment* d_segs,
                            uint64_t* d_total_chunks, uint64_t* d_total_trees, cudaStream_t s);
 int enumerate_grid_size(int precision, int device);

@@ -150,12 +150,23 @@ __host__ __device__ inline bool classify_tree(int K, const int8_t* parent, const
     return true;
 }
 
+// Node-set sharding of a (parameter set, clustering) that is split over all ranks: the rank that scores the
+// regular trees whose pack sits on the node set `mask` -- and therefore builds the top-level inside rows on that
+// set and the top-level context rows on its complement (top-level rows are never ingredients of other rows; the
+// lower levels are built everywhere).  Round robin over the combinatorial rank of the set among the sets of its size.
+__host__ __device__ inline int node_set_owner(uint32_t mask, int world) {
+    int rank = 0, i = 0;
+    for (uint32_t mm = mask; mm; mm &= mm - 1, ++i) rank += binom_small(BAMSE_CTZ(mm), i + 1);
+    return rank % world;
+}
+
 // How a context row is produced (host-generated, one array per (K, s, r)).
 struct CtxRecipe {
     int32_t parent_row;    // context of the marked node's parent (fewer nodes), -1: the marked node is the root
     int32_t h_row;         // FG row of the marked node's children forest inside the context, -1: none
     int8_t v;              // label of the marked node
-    int8_t pad[3];
+    int8_t pad;
+    uint16_t mask;         // node set of the context
 };
 static_assert(sizeof(CtxRecipe) == 12, "recipe layout");
 

@@ -41,7 +41,7 @@ inline CtxRecipe ctx_recipe_of_row(const ForestIndex& fi, const PairGeom& g, uin
         if (gp[w] == v) desc |= 1u << lab[t];
     }
     CtxRecipe r;
-    r.v = (int8_t)v; r.pad[0] = r.pad[1] = r.pad[2] = 0;
+    r.v = (int8_t)v; r.pad = 0; r.mask = (uint16_t)mask;
     r.h_row = desc ? forest_row(fi, fl.lut.data(), desc, gp) : -1;
     r.parent_row = gp[v] >= 0 ? (int32_t)ctx_row(g, mask & ~(desc | (1u << v)), gp, gp[v]) : -1;
     return r;

@@ -49,6 +49,7 @@ struct TableBase {
     uint32_t t_row;      // first row of T of (p, c, m = 0); sample m starts PairK::nt rows later
     int32_t s_prog;      // the table-driven programs pack forests of <= s_prog <= fi.s nodes (16-bit row ids)
     int32_t mine;        // 0: another rank owns this (p, c) under the sharding plan -- no tables here
+    int32_t split;       // 1: this (p, c) is split over all ranks (node-set sharding of the pair path, pairs.cuh)
     ForestIndex fi;      // geometry of the inside tables
 };
 
@@ -81,6 +82,7 @@ struct FastTables {
     const int32_t* pcm_list;   // [n_pcm] the (p * C + c) * M + m of the tables this rank builds (sharding plan)
     int n_pcm;
     int grid_blocks;           // table kernels: row blocks per (p, c, m) of this launch
+    int shard_rank, shard_world;
 };
 
 // ----------------------------------------------------------------------------- warp ops

@@ -250,3 +250,34 @@ def test_trivial_cluster_counts_in_a_mixed_problem(ctx, shim):
         s32, _ = ctx.score_range(0, c, 0, K ** (K - 1), shim.FP32)
         s64, _ = ctx.score_range(0, c, 0, K ** (K - 1), shim.FP64)
         assert np.max(np.abs(s32 - s64) / np.abs(s64)) <= FP32_RTOL
+
+
+@pytest.mark.parametrize("K,world", [(8, 3), (9, 2), (7, 8)])
+def test_one_big_clustering_is_split_by_node_sets(shim, K, world):
+    """a problem that is ONE clustering: the plan splits it over all ranks; the pair path shards by the pack's node
+    set (every rank builds only its share of the top-level table rows), the irregular trees by interleaved index.
+    Shares add up to every tree exactly once and the merged top-k equals the unsharded one."""
+    from bamse_b200.multigpu import merge_records
+    rng = np.random.default_rng(1000 + K)
+    var, ref = _problem(rng, K, 2, 150)
+    const = np.zeros((1, 1))
+    T = K ** (K - 1)
+    with shim.Context(0) as one:
+        one.upload_problem([0.003], [K], var[None], ref[None])
+        want, _, _ = one.score_topk(const, topk=9, precision=shim.FP32)
+        assert one.last_eval_count == T
+    parts, evals = [], 0
+    for r in range(world):
+        with shim.Context(0) as c:
+            c.set_shard(r, world)
+            c.upload_problem([0.003], [K], var[None], ref[None])
+            assert c.shard_plan().tolist() == [[-1]]
+            rec, _, _ = c.score_topk(const, topk=9, precision=shim.FP32)
+            evals += c.last_eval_count
+            parts.append(rec)
+            with pytest.raises(shim.BamseCudaError):
+                c.score_range(0, 0, 0, 10, shim.FP32)      # dense fp32 ranges need all tables on one rank
+    assert evals == T
+    got = merge_records(np.stack(parts), 9)
+    np.testing.assert_array_equal(got["tree"], want["tree"])
+    np.testing.assert_allclose(got["total"], want["total"], rtol=1e-12)
