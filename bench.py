@@ -130,7 +130,9 @@ def hbm_evidence(algorithmic_bytes, traffic, kernel_s):
     """Why the roofline is not an HBM one: DRAM bytes of the kernel (committed ncu capture) over its measured
     duration, against the measured copy bandwidth of this pool's B200s (MEASURED_PEAKS.json, else the
     profiling guide's fallback)."""
-    out = {"algorithmic_bytes_per_launch": algorithmic_bytes, "note": "HBM idle: inputs are KBs per launch"}
+    out = {"algorithmic_bytes_per_launch": algorithmic_bytes,
+           "note": "inputs are KBs per step; the DRAM traffic is the derived tables (written once, read by the next level "
+                   "and the enumeration), a few percent of the HBM peak: the XU pipe binds"}
     peak, src = 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -612,18 +614,21 @@ def main():
                                 "across trees and only terms within 2^-26 of an output's maximum are exponentiated, "
                                 "so frac exceeds 1 by orders of magnitude; xu_pipe_frac is the XU pipe utilisation "
                                 "of what actually executed (table builders + enumeration kernels, event-timed)"}
-        traffic = None
+        # DRAM traffic of the step's table-building kernels (1 launch of each per step), from the committed
+        # ncu --set full capture of this configuration (profiles/r02_traffic.json); null for other configurations
+        traffic, traffic_detail = None, None
         try:
-            with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+            with open(os.path.join(ROOT, "profiles", "r02_traffic.json")) as f:
                 tj = json.load(f)
-            if args.config == tj.get("config") and world == 1 and kname.startswith(tj["kernel"].split("<")[0]):
-                traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]     # per launch, from the committed ncu capture
+            if args.config == tj.get("config") and world == tj.get("n_gpus", 1) and args.precision == "fp32":
+                traffic = int(tj["dram_bytes_read"] + tj["dram_bytes_write"])
+                traffic_detail = {"dominant_kernel": tj["dominant_kernel"], "per_kernel": tj["kernels"], "source": tj["source"]}
         except Exception:
             pass
         roofline = {"bound": bound, "achieved": achieved, "peak": peak, "unit": unit, "frac": achieved / peak,
                     "traffic": traffic, "peak_source": peaks["source"], "kernel": kname,
                     "kernel_ms_per_launch": 1e3 * kernel_s, "executed": executed,
-                    "hbm": hbm_evidence(int(h2d), traffic, kernel_s)}
+                    "hbm": hbm_evidence(int(h2d), traffic, kernel_s), "traffic_detail": traffic_detail}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "f32" if prec == cuda_shim.FP32 else "f64",
