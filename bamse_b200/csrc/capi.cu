@@ -59,7 +59,7 @@ struct bamse_ctx {
     // pair path (pairs.cuh), per cluster count: pair table, context map / compact recipes; kept across uploads
     // while the geometry of that K is unchanged
     struct PairState {
-        DBuf tab, map, recipes;
+        DBuf tab, map, recipes, sorted_tree, sorted_entry;
         int s = -1, r = -1;
         bool has_tab = false;
         uint32_t nt = 0, lbase[PR_RMAX + 2] = {0};
@@ -239,8 +239,10 @@ static int ensure_pair_state(bamse_ctx* ctx, int K) {
     ps.nt = (uint32_t)comp.size();
     BAMSE_CUDA_TRY(ctx, ps.map.ensure(sizeof(uint32_t) * std::max<size_t>(map.size(), 1)));
     BAMSE_CUDA_TRY(ctx, ps.recipes.ensure(sizeof(CtxRecipe) * std::max<size_t>(comp.size(), 1)));
-    BAMSE_CUDA_TRY(ctx, cudaMemcpy(ps.map.p, map.data(), sizeof(uint32_t) * map.size(), cudaMemcpyHostToDevice));
-    BAMSE_CUDA_TRY(ctx, cudaMemcpy(ps.recipes.p, comp.data(), sizeof(CtxRecipe) * comp.size(), cudaMemcpyHostToDevice));
+    // (copies on the ctx stream: a blocking cudaMemcpy from pageable memory may return before the DMA has landed
+    //  and is not ordered against this non-blocking stream)
+    BAMSE_CUDA_TRY(ctx, cudaMemcpyAsync(ps.map.p, map.data(), sizeof(uint32_t) * map.size(), cudaMemcpyHostToDevice, st));
+    BAMSE_CUDA_TRY(ctx, cudaMemcpyAsync(ps.recipes.p, comp.data(), sizeof(CtxRecipe) * comp.size(), cudaMemcpyHostToDevice, st));
     if (ps.nt >= (1u << PAIR_T_BITS)) return ctx->fail(BAMSE_EINTERNAL, "pair geometry of K=%d needs more than %u-bit context row ids", K, PAIR_T_BITS);
     if (ps.has_tab) {
         if (ps.tab.ensure(sizeof(uint64_t) * n_trees) != cudaSuccess) { cudaGetLastError(); ps.has_tab = false; }   // no room: cut in the kernel
@@ -250,6 +252,36 @@ static int ensure_pair_state(bamse_ctx* ctx, int K) {
             ctx->launches++;
         }
     }
+    // the same table in the order of the inside rows (counting sort; BAMSE_PAIR_SORT=0 disables)
+    ps.sorted_tree.release(); ps.sorted_entry.release();
+    const char* no_sort = getenv("BAMSE_PAIR_SORT");
+    if (ps.has_tab && n_trees < (1ull << 32) && !(no_sort && atoi(no_sort) == 0)) {
+        DBuf hist;
+        bool ok = hist.ensure(sizeof(unsigned) * (size_t)fi.nf) == cudaSuccess &&
+                  ps.sorted_tree.ensure(sizeof(uint32_t) * n_trees) == cudaSuccess &&
+                  ps.sorted_entry.ensure(sizeof(uint64_t) * n_trees) == cudaSuccess;
+        if (ok) {
+            cudaMemsetAsync(hist.p, 0, sizeof(unsigned) * (size_t)fi.nf, st);
+            launch_pair_hist(ps.tab.as<uint64_t>(), n_trees, hist.as<unsigned>(), st);
+            std::vector<unsigned> h((size_t)fi.nf);
+            ok = cudaMemcpyAsync(h.data(), hist.p, sizeof(unsigned) * h.size(), cudaMemcpyDeviceToHost, st) == cudaSuccess &&
+                 cudaStreamSynchronize(st) == cudaSuccess;
+            if (ok) {
+                uint64_t acc = 0;
+                for (size_t i = 0; i < h.size(); ++i) { const unsigned c = h[i]; h[i] = (unsigned)acc; acc += c; }
+                ok = acc == n_trees && cudaMemcpyAsync(hist.p, h.data(), sizeof(unsigned) * h.size(), cudaMemcpyHostToDevice, st) == cudaSuccess;
+            }
+            if (ok) {
+                launch_pair_scatter(ps.tab.as<uint64_t>(), n_trees, hist.as<unsigned>(), ps.sorted_tree.as<uint32_t>(),
+                                    ps.sorted_entry.as<uint64_t>(), st);
+                ok = cudaStreamSynchronize(st) == cudaSuccess;
+                ctx->launches += 2;
+            }
+        }
+        hist.release();
+        if (!ok) { cudaGetLastError(); ps.sorted_tree.release(); ps.sorted_entry.release(); }   // no room: index order
+    }
+    BAMSE_CUDA_TRY(ctx, cudaStreamSynchronize(st));   // the host vectors above die at return
     BAMSE_CUDA_TRY(ctx, cudaGetLastError());
     ps.n_irregular = n_irr;
     ps.s = sK; ps.r = rK;
@@ -328,7 +360,7 @@ static int plan_tables(bamse_ctx* ctx) {
     cudaStream_t s = ctx->stream;
     if (!ctx->d_lut.p) {
         BAMSE_CUDA_TRY(ctx, ctx->d_lut.ensure(sizeof(int16_t) * FT_LUT_SIZE));
-        BAMSE_CUDA_TRY(ctx, cudaMemcpy(ctx->d_lut.p, forest_lut().lut.data(), sizeof(int16_t) * FT_LUT_SIZE, cudaMemcpyHostToDevice));
+        BAMSE_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_lut.p, forest_lut().lut.data(), sizeof(int16_t) * FT_LUT_SIZE, cudaMemcpyHostToDevice, s));
     }
     // BAMSE_TABLE_GB: table budget (default 60 % of the device memory); BAMSE_FOREST_S / _SH / BAMSE_PAIR_R override
     const char* env_s = getenv("BAMSE_FOREST_S");
@@ -428,18 +460,19 @@ static int plan_tables(bamse_ctx* ctx) {
     BAMSE_CUDA_TRY(ctx, ctx->d_FSG.ensure(sizeof(float) * std::max<size_t>(fsg_rows, 1) * L));
     BAMSE_CUDA_TRY(ctx, ctx->d_T.ensure(sizeof(float) * std::max<size_t>(t_rows, 1) * L));
     BAMSE_CUDA_TRY(ctx, ctx->d_tb.ensure(sizeof(TableBase) * tbs.size()));
-    BAMSE_CUDA_TRY(ctx, cudaMemcpy(ctx->d_tb.p, tbs.data(), sizeof(TableBase) * tbs.size(), cudaMemcpyHostToDevice));
+    BAMSE_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_tb.p, tbs.data(), sizeof(TableBase) * tbs.size(), cudaMemcpyHostToDevice, s));
     {   // the table kernels run over the (p, c, m) triples of this rank only
         std::vector<int32_t> pcm;
         for (int pc = 0; pc < P * C; ++pc)
             if (tbs[(size_t)pc].mine) for (int m = 0; m < M; ++m) pcm.push_back(pc * M + m);
         ctx->n_pcm = (int)pcm.size();
         BAMSE_CUDA_TRY(ctx, ctx->d_pcm.ensure(sizeof(int32_t) * std::max<size_t>(pcm.size(), 1)));
-        BAMSE_CUDA_TRY(ctx, cudaMemcpy(ctx->d_pcm.p, pcm.data(), sizeof(int32_t) * pcm.size(), cudaMemcpyHostToDevice));
+        BAMSE_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_pcm.p, pcm.data(), sizeof(int32_t) * pcm.size(), cudaMemcpyHostToDevice, s));
+        BAMSE_CUDA_TRY(ctx, cudaStreamSynchronize(s));              // pcm dies here
     }
     if (!ctx->owner.empty()) {
         BAMSE_CUDA_TRY(ctx, ctx->d_owner.ensure(sizeof(int32_t) * ctx->owner.size()));
-        BAMSE_CUDA_TRY(ctx, cudaMemcpy(ctx->d_owner.p, ctx->owner.data(), sizeof(int32_t) * ctx->owner.size(), cudaMemcpyHostToDevice));
+        BAMSE_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_owner.p, ctx->owner.data(), sizeof(int32_t) * ctx->owner.size(), cudaMemcpyHostToDevice, s));
     }
     {
         const ForestRecipe* rptrs[KMAX + 1];
@@ -455,9 +488,10 @@ static int plan_tables(bamse_ctx* ctx) {
                 const std::vector<ForestRecipe> rec = make_forest_recipes(fiK);
                 const std::vector<uint32_t> ord = make_level_order(fiK, rec);
                 BAMSE_CUDA_TRY(ctx, r.buf.ensure(sizeof(ForestRecipe) * rec.size()));
-                BAMSE_CUDA_TRY(ctx, cudaMemcpy(r.buf.p, rec.data(), sizeof(ForestRecipe) * rec.size(), cudaMemcpyHostToDevice));
+                BAMSE_CUDA_TRY(ctx, cudaMemcpyAsync(r.buf.p, rec.data(), sizeof(ForestRecipe) * rec.size(), cudaMemcpyHostToDevice, s));
                 BAMSE_CUDA_TRY(ctx, r.order.ensure(sizeof(uint32_t) * ord.size()));
-                BAMSE_CUDA_TRY(ctx, cudaMemcpy(r.order.p, ord.data(), sizeof(uint32_t) * ord.size(), cudaMemcpyHostToDevice));
+                BAMSE_CUDA_TRY(ctx, cudaMemcpyAsync(r.order.p, ord.data(), sizeof(uint32_t) * ord.size(), cudaMemcpyHostToDevice, s));
+                BAMSE_CUDA_TRY(ctx, cudaStreamSynchronize(s));      // rec / ord die here (once per K and geometry)
                 r.s = ctx->geom_s[K];
             }
             rptrs[K] = r.buf.as<ForestRecipe>();
@@ -471,14 +505,17 @@ static int plan_tables(bamse_ctx* ctx) {
                 pk.map = ps.map.as<uint32_t>();
                 pk.recipes = ps.recipes.as<CtxRecipe>();
                 pk.pair_tab = ps.has_tab ? ps.tab.as<uint64_t>() : nullptr;
+                pk.sorted_tree = ps.sorted_tree.as<uint32_t>();
+                pk.sorted_entry = ps.sorted_entry.as<uint64_t>();
             }
         }
         BAMSE_CUDA_TRY(ctx, ctx->d_recipe_ptrs.ensure(sizeof rptrs));
-        BAMSE_CUDA_TRY(ctx, cudaMemcpy(ctx->d_recipe_ptrs.p, rptrs, sizeof rptrs, cudaMemcpyHostToDevice));
+        BAMSE_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_recipe_ptrs.p, rptrs, sizeof rptrs, cudaMemcpyHostToDevice, s));
         BAMSE_CUDA_TRY(ctx, ctx->d_order_ptrs.ensure(sizeof optrs));
-        BAMSE_CUDA_TRY(ctx, cudaMemcpy(ctx->d_order_ptrs.p, optrs, sizeof optrs, cudaMemcpyHostToDevice));
+        BAMSE_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_order_ptrs.p, optrs, sizeof optrs, cudaMemcpyHostToDevice, s));
         BAMSE_CUDA_TRY(ctx, ctx->d_pk.ensure(sizeof pks));
-        BAMSE_CUDA_TRY(ctx, cudaMemcpy(ctx->d_pk.p, pks, sizeof pks, cudaMemcpyHostToDevice));
+        BAMSE_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_pk.p, pks, sizeof pks, cudaMemcpyHostToDevice, s));
+        BAMSE_CUDA_TRY(ctx, cudaStreamSynchronize(s));              // the pointer tables die here
     }
     {   // program tables for the small K of this problem (K^(K-1) rows of 64 bytes; K = 8: 134 MB)
         const char* off = getenv("BAMSE_PROGTAB");          // BAMSE_PROGTAB=0: always decode in the kernel
@@ -505,8 +542,10 @@ static int plan_tables(bamse_ctx* ctx) {
             ctx->have_progtabs = true;
         }
         BAMSE_CUDA_TRY(ctx, ctx->d_progtabs.ensure(sizeof ptrs));
-        BAMSE_CUDA_TRY(ctx, cudaMemcpy(ctx->d_progtabs.p, ptrs, sizeof ptrs, cudaMemcpyHostToDevice));
+        BAMSE_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_progtabs.p, ptrs, sizeof ptrs, cudaMemcpyHostToDevice, s));
+        BAMSE_CUDA_TRY(ctx, cudaStreamSynchronize(s));
     }
+    BAMSE_CUDA_TRY(ctx, cudaStreamSynchronize(s));   // the host arrays above (table bases, pointer tables) die at return
     return BAMSE_OK;
 }
 
@@ -630,7 +669,7 @@ void bamse_destroy(bamse_ctx* ctx) {
                     &ctx->d_flat_meta, &ctx->d_lists2, &ctx->d_segs2, &ctx->d_owner, &ctx->d_part, &ctx->d_pcm};
     for (DBuf* b : bufs) b->release();
     for (auto& t : ctx->progtab) t.buf.release();
-    for (auto& t : ctx->pairs) { t.tab.release(); t.map.release(); t.recipes.release(); }
+    for (auto& t : ctx->pairs) { t.tab.release(); t.map.release(); t.recipes.release(); t.sorted_tree.release(); t.sorted_entry.release(); }
     for (auto& r : ctx->recipes) { r.buf.release(); r.order.release(); }
     ctx->d_order_ptrs.release();
     ctx->d_progtabs.release();
@@ -664,7 +703,7 @@ int bamse_debug_pair_stats(bamse_ctx* ctx, int K, int s, int r, int64_t* out4) t
         return ctx->fail(BAMSE_EINVAL, "bamse_debug_pair_stats: bad geometry");
     if (!ctx->d_lut.p) {
         BAMSE_CUDA_TRY(ctx, ctx->d_lut.ensure(sizeof(int16_t) * FT_LUT_SIZE));
-        BAMSE_CUDA_TRY(ctx, cudaMemcpy(ctx->d_lut.p, forest_lut().lut.data(), sizeof(int16_t) * FT_LUT_SIZE, cudaMemcpyHostToDevice));
+        BAMSE_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_lut.p, forest_lut().lut.data(), sizeof(int16_t) * FT_LUT_SIZE, cudaMemcpyHostToDevice, ctx->stream));
     }
     ctx->have_problem = false;                       // the resident problem may have been planned with another geometry
     ctx->plan_valid = false;
@@ -1356,6 +1395,7 @@ int bamse_score_range(bamse_ctx* ctx, int p, int c, uint64_t tree_begin, int64_t
     seg.p = p; seg.c = c; seg.K = K; seg.stride = 1;
     seg.tree_begin = tree_begin; seg.n_trees = (uint64_t)n;
     seg.first_chunk = 0; seg.clust_const = 0.0; seg.threshold = -INFINITY;
+    seg.whole = 0; seg.pad = 0;
     int rc = enumerate_dev(ctx, nullptr, nullptr, nullptr, nullptr, 0, precision, 0.0, 0.0, nullptr,
                            ctx->d_dense0.as<double>(), ctx->d_dense1.as<double>(), &seg);
     if (rc) return rc;

@@ -377,6 +377,36 @@ __global__ void __launch_bounds__(128) k_build_pair_table(ForestIndex fi, PairGe
     out[tree] = e;
 }
 
+// counting sort of a pair table by inside row: histogram, (host) prefix, scatter
+__global__ void __launch_bounds__(256) k_pair_hist(const uint64_t* __restrict__ tab, uint64_t n_trees, unsigned* __restrict__ hist) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_trees) return;
+    uint32_t fg, t, scre;
+    pair_unpack(tab[i], &fg, &t, &scre);
+    atomicAdd(hist + fg, 1u);
+}
+
+__global__ void __launch_bounds__(256) k_pair_scatter(const uint64_t* __restrict__ tab, uint64_t n_trees, unsigned* __restrict__ cursor,
+                                                      uint32_t* __restrict__ sorted_tree, uint64_t* __restrict__ sorted_entry) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_trees) return;
+    const uint64_t e = tab[i];
+    uint32_t fg, t, scre;
+    pair_unpack(e, &fg, &t, &scre);
+    const unsigned pos = atomicAdd(cursor + fg, 1u);
+    sorted_tree[pos] = (uint32_t)i;
+    sorted_entry[pos] = e;
+}
+
+void launch_pair_hist(const uint64_t* tab, uint64_t n_trees, unsigned* hist, cudaStream_t s) {
+    k_pair_hist<<<(unsigned)((n_trees + 255) / 256), 256, 0, s>>>(tab, n_trees, hist);
+}
+
+void launch_pair_scatter(const uint64_t* tab, uint64_t n_trees, unsigned* cursor, uint32_t* sorted_tree, uint64_t* sorted_entry,
+                         cudaStream_t s) {
+    k_pair_scatter<<<(unsigned)((n_trees + 255) / 256), 256, 0, s>>>(tab, n_trees, cursor, sorted_tree, sorted_entry);
+}
+
 __global__ void k_flat_prefix(int P, const unsigned long long* __restrict__ cnt, const unsigned long long* __restrict__ off,
                               unsigned long long* __restrict__ prefix) {
     if (threadIdx.x || blockIdx.x) return;
@@ -707,13 +737,19 @@ __global__ void __launch_bounds__(PAIR_THREADS, 6) k_enumerate_pairs(ProblemView
         const uint64_t off = blk * 32ull + (uint64_t)lane;
         const uint64_t slot = seg.first_chunk / (uint64_t)reps * 32ull + off;
         const bool valid = off < seg.n_trees;
-        const uint64_t tree = seg.tree_begin + off * (uint64_t)seg.stride;
+        uint64_t tree = seg.tree_begin + off * (uint64_t)seg.stride;
         const TableBase* tb = ft.tb + (seg.p * pv.C + seg.c);
         const PairK* pk = ft.pk + seg.K;
         uint32_t fg = 0, tr = 0, scre = 0;
         bool reg = false;
+        // a whole index range goes in the order of the inside rows (the dense debug outputs keep the index order)
+        const bool sorted = pk->sorted_tree && seg.stride == 1 && seg.tree_begin == 0 && seg.whole && !w.dense_score;
         if (valid) {
-            if (pk->pair_tab) {
+            if (sorted) {
+                tree = __ldg(pk->sorted_tree + off);
+                pair_unpack(__ldg(pk->sorted_entry + off), &fg, &tr, &scre);
+                reg = scre != 0;
+            } else if (pk->pair_tab) {
                 pair_unpack(__ldg(pk->pair_tab + tree), &fg, &tr, &scre);
                 reg = scre != 0;
             } else if (pk->g.r > 0) {

@@ -64,6 +64,8 @@ __global__ void __launch_bounds__(256) k_build_segments(int P, int C, const int3
         s.tree_begin = b + (uint64_t)rank;
         s.n_trees = span > (uint64_t)rank ? (span - rank + world - 1) / world : 0;
         s.first_chunk = (s.n_trees + (uint64_t)chunk - 1) / (uint64_t)chunk * (uint64_t)reps;   // count for now
+        s.whole = (s.stride == 1 && s.tree_begin == 0 && s.n_trees == T) ? 1 : 0;
+        s.pad = 0;
         s.clust_const = cconst ? cconst[i] : 0.0;
         double th = thr ? thr[i] : -CUDART_INF;
         if (th > -CUDART_INF) th -= slack_abs + slack_rel * fabs(th);

@@ -28,6 +28,8 @@ struct Segment {
     uint64_t first_chunk;    // prefix sum of chunk counts
     double clust_const;      // cluster_prior + maxlikelihood        (clustering.py:183)
     double threshold;        // candidate score + log scre (minus slack), -inf = keep all
+    int32_t whole;           // 1: the segment is the complete index range [0, K^(K-1)) of its clustering
+    int32_t pad;
 };
 
 struct EnumWork {
@@ -122,6 +124,9 @@ int enumerate_pairs_workers(int grid);
 // mode 0: tree-major; 1 + 2: sample-major (accumulate per sample into w.part, then sum and rank); the segments of
 // modes 1 / 2 carry M chunks per 32 trees (launch_build_segments with reps = M)
 void launch_enumerate_pairs(const ProblemView& pv, const FastTables& ft, const EnumWork& w, int grid, int mode, cudaStream_t s);
+void launch_pair_hist(const uint64_t* tab, uint64_t n_trees, unsigned* hist, cudaStream_t s);
+void launch_pair_scatter(const uint64_t* tab, uint64_t n_trees, unsigned* cursor, uint32_t* sorted_tree, uint64_t* sorted_entry,
+                         cudaStream_t s);
 void launch_flat_prefix(int P, const unsigned long long* cnt, const unsigned long long* off, unsigned long long* prefix,
                         cudaStream_t s);
 void launch_score_items_fast(const ProblemView& pv, const FastTables& ft, const ScoreItem* d_items, int64_t n,

@@ -63,6 +63,10 @@ struct PairK {
     const uint32_t* map;           // [g.nt] full row -> compact row (0xffffffff: unused)
     const CtxRecipe* recipes;      // [nt] compact, parent_row compact
     const uint64_t* pair_tab;      // [K^(K-1)] pair_entry per tree index (context row compact), NULL: cut in the kernel
+    // the same entries ordered by inside row (counting sort): the lanes of a warp then share their inside row, whose
+    // loads become warp-uniform (the pair kernel is bound by L1 wavefronts).  Used for whole index ranges.
+    const uint32_t* sorted_tree;   // [K^(K-1)] tree index, NULL: none
+    const uint64_t* sorted_entry;  // [K^(K-1)]
 };
 
 struct FastTables {
