@@ -59,8 +59,8 @@ struct bamse_ctx {
     // pair path (pairs.cuh), per cluster count: pair table, context map / compact recipes; kept across uploads
     // while the geometry of that K is unchanged
     struct PairState {
-        DBuf tab, map, recipes, sorted_tree, sorted_entry;
-        int s = -1, r = -1;
+        DBuf tab, map, recipes, sorted_tree, sorted_entry, irr_progs;
+        int s = -1, r = -1, sh = -1;
         bool has_tab = false;
         uint32_t nt = 0, lbase[PR_RMAX + 2] = {0};
         uint64_t n_irregular = 0;
@@ -171,9 +171,9 @@ static bool pairs_enabled() {
 // per ctx and geometry.
 static int ensure_pair_state(bamse_ctx* ctx, int K) {
     bamse_ctx::PairState& ps = ctx->pairs[K];
-    const int sK = ctx->geom_s[K], rK = ctx->geom_r[K];
-    if (ps.s == sK && ps.r == rK) return BAMSE_OK;
-    ps.s = ps.r = -1;
+    const int sK = ctx->geom_s[K], rK = ctx->geom_r[K], shK = ctx->geom_sh[K];
+    if (ps.s == sK && ps.r == rK && ps.sh == shK) return BAMSE_OK;
+    ps.s = ps.r = ps.sh = -1;
     const ForestIndex fi = make_forest_index(K, sK, 1);
     const PairGeom g = make_pair_geom(K, sK, rK);
     if (fi.nf >= (1 << PAIR_FG_BITS)) return ctx->fail(BAMSE_EINTERNAL, "pair geometry of K=%d exceeds %u-bit inside row ids", K, PAIR_FG_BITS);
@@ -187,7 +187,7 @@ static int ensure_pair_state(bamse_ctx* ctx, int K) {
     if (e != cudaSuccess) return ctx->fail(BAMSE_ENOMEM, "pair state: %s", cudaGetErrorString(e));
     cudaMemsetAsync(used.p, 0, used_bytes + 8, st);
     unsigned long long* d_nirr = reinterpret_cast<unsigned long long*>(used.as<uint8_t>() + used_bytes);
-    launch_build_pair_table(fi, g, n_trees, ctx->d_lut.as<int16_t>(), nullptr, used.as<uint8_t>(), d_nirr, nullptr, st);
+    launch_build_pair_table(fi, g, n_trees, ctx->d_lut.as<int16_t>(), nullptr, used.as<uint8_t>(), d_nirr, nullptr, fi, nullptr, st);
     ctx->launches++;
     std::vector<uint8_t> h_used(used_bytes + 8);
     e = cudaMemcpyAsync(h_used.data(), used.p, used_bytes + 8, cudaMemcpyDeviceToHost, st);
@@ -247,9 +247,21 @@ static int ensure_pair_state(bamse_ctx* ctx, int K) {
     if (ps.has_tab) {
         if (ps.tab.ensure(sizeof(uint64_t) * n_trees) != cudaSuccess) { cudaGetLastError(); ps.has_tab = false; }   // no room: cut in the kernel
         else {
-            launch_build_pair_table(fi, g, n_trees, ctx->d_lut.as<int16_t>(), ps.tab.as<uint64_t>(), nullptr, nullptr,
-                                    ps.map.as<uint32_t>(), st);
+            // the irregular trees' programs with the table (K = 10: 20 M x 64 bytes), unless they are too many
+            ps.irr_progs.release();
+            DBuf cursor;
+            const ForestIndex fi_prog = make_forest_index(K, program_forest_s(K, sK), shK);
+            const bool want_progs = n_irr > 0 && n_irr * sizeof(FastProgram) <= (6ull << 30) &&
+                                    cursor.ensure(sizeof(unsigned long long)) == cudaSuccess &&
+                                    ps.irr_progs.ensure(sizeof(FastProgram) * n_irr) == cudaSuccess;
+            if (want_progs) cudaMemsetAsync(cursor.p, 0, sizeof(unsigned long long), st);
+            else { cudaGetLastError(); ps.irr_progs.release(); }
+            launch_build_pair_table(fi, g, n_trees, ctx->d_lut.as<int16_t>(), ps.tab.as<uint64_t>(), nullptr,
+                                    want_progs ? cursor.as<unsigned long long>() : nullptr, ps.map.as<uint32_t>(), fi_prog,
+                                    want_progs ? ps.irr_progs.as<FastProgram>() : nullptr, st);
             ctx->launches++;
+            BAMSE_CUDA_TRY(ctx, cudaStreamSynchronize(st));
+            cursor.release();
         }
     }
     // the same table in the order of the inside rows (counting sort; BAMSE_PAIR_SORT=0 disables)
@@ -284,7 +296,7 @@ static int ensure_pair_state(bamse_ctx* ctx, int K) {
     BAMSE_CUDA_TRY(ctx, cudaStreamSynchronize(st));   // the host vectors above die at return
     BAMSE_CUDA_TRY(ctx, cudaGetLastError());
     ps.n_irregular = n_irr;
-    ps.s = sK; ps.r = rK;
+    ps.s = sK; ps.r = rK; ps.sh = shK;
     return BAMSE_OK;
 }
 
@@ -505,6 +517,7 @@ static int plan_tables(bamse_ctx* ctx) {
                 pk.map = ps.map.as<uint32_t>();
                 pk.recipes = ps.recipes.as<CtxRecipe>();
                 pk.pair_tab = ps.has_tab ? ps.tab.as<uint64_t>() : nullptr;
+                pk.irr_progs = ps.irr_progs.as<FastProgram>();
                 pk.sorted_tree = ps.sorted_tree.as<uint32_t>();
                 pk.sorted_entry = ps.sorted_entry.as<uint64_t>();
             }
@@ -669,7 +682,7 @@ void bamse_destroy(bamse_ctx* ctx) {
                     &ctx->d_flat_meta, &ctx->d_lists2, &ctx->d_segs2, &ctx->d_owner, &ctx->d_part, &ctx->d_pcm};
     for (DBuf* b : bufs) b->release();
     for (auto& t : ctx->progtab) t.buf.release();
-    for (auto& t : ctx->pairs) { t.tab.release(); t.map.release(); t.recipes.release(); t.sorted_tree.release(); t.sorted_entry.release(); }
+    for (auto& t : ctx->pairs) { t.tab.release(); t.map.release(); t.recipes.release(); t.sorted_tree.release(); t.sorted_entry.release(); t.irr_progs.release(); }
     for (auto& r : ctx->recipes) { r.buf.release(); r.order.release(); }
     ctx->d_order_ptrs.release();
     ctx->d_progtabs.release();
@@ -707,6 +720,11 @@ int bamse_debug_pair_stats(bamse_ctx* ctx, int K, int s, int r, int64_t* out4) t
     }
     ctx->have_problem = false;                       // the resident problem may have been planned with another geometry
     ctx->plan_valid = false;
+    {
+        int s0 = 1, sh0 = 1, r0 = 0;
+        default_forest_geometry(K, &s0, &sh0, &r0);
+        ctx->geom_sh[K] = std::min(sh0, program_forest_s(K, s));
+    }
     ctx->geom_s[K] = s; ctx->geom_r[K] = r;
     const int rc = ensure_pair_state(ctx, K);
     if (rc) return rc;

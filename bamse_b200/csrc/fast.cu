@@ -356,7 +356,8 @@ __global__ void __launch_bounds__(FAST_THREADS, BAMSE_BUILD_CTAS) k_ctx_level(Pr
 __global__ void __launch_bounds__(128) k_build_pair_table(ForestIndex fi, PairGeom g, uint64_t n_trees,
                                                           const int16_t* __restrict__ lut, uint64_t* __restrict__ out,
                                                           uint8_t* __restrict__ used, unsigned long long* n_irregular,
-                                                          const uint32_t* __restrict__ map) {
+                                                          const uint32_t* __restrict__ map, ForestIndex fi_prog,
+                                                          FastProgram* __restrict__ irr_progs) {
     const uint64_t tree = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (tree >= n_trees) return;
     int8_t parent[KMAX];
@@ -373,6 +374,14 @@ __global__ void __launch_bounds__(128) k_build_pair_table(ForestIndex fi, PairGe
         TreeProgram ref;
         build_program(fi.K, parent, nullptr, &ref);
         e = pair_entry(fg, map[t], (uint32_t)ref.scre);
+    } else if (irr_progs) {
+        // an irregular tree: its table-driven program, once and for all; the entry (scre field 0) carries its slot
+        const unsigned long long slot = atomicAdd(n_irregular, 1ull);
+        FastProgram prog;
+        memset(&prog, 0, sizeof prog);
+        build_program_forest(fi.K, parent, nullptr, fi_prog, lut, &prog);
+        irr_progs[slot] = prog;
+        e = (uint64_t)slot;
     }
     out[tree] = e;
 }
@@ -383,6 +392,7 @@ __global__ void __launch_bounds__(256) k_pair_hist(const uint64_t* __restrict__ 
     if (i >= n_trees) return;
     uint32_t fg, t, scre;
     pair_unpack(tab[i], &fg, &t, &scre);
+    if (!scre) fg = 0;                                // an irregular tree (its entry holds a program slot): bin 0
     atomicAdd(hist + fg, 1u);
 }
 
@@ -393,6 +403,7 @@ __global__ void __launch_bounds__(256) k_pair_scatter(const uint64_t* __restrict
     const uint64_t e = tab[i];
     uint32_t fg, t, scre;
     pair_unpack(e, &fg, &t, &scre);
+    if (!scre) fg = 0;
     const unsigned pos = atomicAdd(cursor + fg, 1u);
     sorted_tree[pos] = (uint32_t)i;
     sorted_entry[pos] = e;
@@ -519,11 +530,15 @@ k_enumerate_fast(ProblemView pv, FastTables ft, EnumWork w) {
         const uint64_t remain = seg.n_trees - off;
         const int n = flat ? 1 : (remain < (uint64_t)w.chunk ? (int)remain : w.chunk);
         const FastProgram* tab = w.prog_tabs ? w.prog_tabs[seg.K] : nullptr;
+        const PairK* pkf = ft.pk + seg.K;
         for (int i = 0; i < n; ++i) {
             const uint64_t tree = seg.tree_begin + (off + i) * (uint64_t)seg.stride;
-            if (tab) {
+            const FastProgram* src = tab ? tab + tree : nullptr;
+            if (flat && pkf->irr_progs && pkf->pair_tab)         // the list holds irregular trees only: their slot is in the entry
+                src = pkf->irr_progs + (__ldg(pkf->pair_tab + tree) & ((1ull << (PAIR_FG_BITS + PAIR_T_BITS)) - 1ull));
+            if (src) {
                 if (lane < 16)
-                    reinterpret_cast<uint32_t*>(&ws->prog)[lane] = __ldg(reinterpret_cast<const uint32_t*>(tab + tree) + lane);
+                    reinterpret_cast<uint32_t*>(&ws->prog)[lane] = __ldg(reinterpret_cast<const uint32_t*>(src) + lane);
             } else if (lane == 0) {
                 const ForestIndex fip = program_index(ft.tb[seg.p * pv.C + seg.c]);
                 build_tree_program(seg.K, tree, &ws->prog, &fip, ft.lut);
@@ -904,8 +919,9 @@ void launch_forest_scan_top(const ProblemView& pv, const FastTables& ft, int max
 
 void launch_build_pair_table(const ForestIndex& fi, const PairGeom& g, uint64_t n_trees, const int16_t* d_lut,
                              uint64_t* out, uint8_t* used, unsigned long long* n_irregular, const uint32_t* d_map,
-                             cudaStream_t s) {
-    k_build_pair_table<<<(unsigned)((n_trees + 127) / 128), 128, 0, s>>>(fi, g, n_trees, d_lut, out, used, n_irregular, d_map);
+                             const ForestIndex& fi_prog, FastProgram* irr_progs, cudaStream_t s) {
+    k_build_pair_table<<<(unsigned)((n_trees + 127) / 128), 128, 0, s>>>(fi, g, n_trees, d_lut, out, used, n_irregular, d_map,
+                                                                         fi_prog, irr_progs);
 }
 
 static size_t fast_smem_bytes(int topk, bool framed = false, int slots = FAST_SLOTS) {

@@ -118,6 +118,8 @@ void launch_ctx_level(const ProblemView& pv, const FastTables& ft, int q, int ma
 // compact context row d_map[row]
 void launch_build_pair_table(const ForestIndex& fi, const PairGeom& g, uint64_t n_trees, const int16_t* d_lut,
                              uint64_t* out, uint8_t* used, unsigned long long* n_irregular, const uint32_t* d_map,
+                             const ForestIndex& fi_prog /* geometry of the programs */, FastProgram* irr_progs /* NULL: none;
+                             else the program of every irregular tree, slot = entry & (2^42 - 1), *n_irregular = slot cursor */,
                              cudaStream_t s);
 int enumerate_pairs_grid_size(int device);
 int enumerate_pairs_workers(int grid);

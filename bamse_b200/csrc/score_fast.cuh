@@ -65,6 +65,8 @@ struct PairK {
     const uint64_t* pair_tab;      // [K^(K-1)] pair_entry per tree index (context row compact), NULL: cut in the kernel
     // the same entries ordered by inside row (counting sort): the lanes of a warp then share their inside row, whose
     // loads become warp-uniform (the pair kernel is bound by L1 wavefronts).  Used for whole index ranges.
+    const FastProgram* irr_progs;  // programs of the irregular trees, indexed by the low 42 bits of their pair-table
+                                   // entry (scre field 0); NULL: decode / per-K program table
     const uint32_t* sorted_tree;   // [K^(K-1)] tree index, NULL: none
     const uint64_t* sorted_entry;  // [K^(K-1)]
 };
