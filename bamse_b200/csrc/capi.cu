@@ -59,7 +59,9 @@ struct bamse_ctx {
     // pair path (pairs.cuh), per cluster count: pair table, context map / compact recipes; kept across uploads
     // while the geometry of that K is unchanged
     struct PairState {
-        DBuf tab, map, recipes, sorted_tree, sorted_entry, irr_progs;
+        DBuf tab, map, recipes, sorted_tree, sorted_entry, irr_progs, mask_owner;
+        std::vector<unsigned long long> mask_trees;      // regular trees per pack node set (data independent)
+        int owner_world = -1;                            // the world size mask_owner was balanced for
         int s = -1, r = -1, sh = -1;
         bool has_tab = false;
         uint32_t nt = 0, lbase[PR_RMAX + 2] = {0};
@@ -187,7 +189,7 @@ static int ensure_pair_state(bamse_ctx* ctx, int K) {
     if (e != cudaSuccess) return ctx->fail(BAMSE_ENOMEM, "pair state: %s", cudaGetErrorString(e));
     cudaMemsetAsync(used.p, 0, used_bytes + 8, st);
     unsigned long long* d_nirr = reinterpret_cast<unsigned long long*>(used.as<uint8_t>() + used_bytes);
-    launch_build_pair_table(fi, g, n_trees, ctx->d_lut.as<int16_t>(), nullptr, used.as<uint8_t>(), d_nirr, nullptr, fi, nullptr, st);
+    launch_build_pair_table(fi, g, n_trees, ctx->d_lut.as<int16_t>(), nullptr, used.as<uint8_t>(), d_nirr, nullptr, fi, nullptr, nullptr, st);
     ctx->launches++;
     std::vector<uint8_t> h_used(used_bytes + 8);
     e = cudaMemcpyAsync(h_used.data(), used.p, used_bytes + 8, cudaMemcpyDeviceToHost, st);
@@ -256,12 +258,20 @@ static int ensure_pair_state(bamse_ctx* ctx, int K) {
                                     ps.irr_progs.ensure(sizeof(FastProgram) * n_irr) == cudaSuccess;
             if (want_progs) cudaMemsetAsync(cursor.p, 0, sizeof(unsigned long long), st);
             else { cudaGetLastError(); ps.irr_progs.release(); }
+            DBuf mhist;                                 // regular trees per pack node set, for the node-set sharding
+            const size_t n_masks = (size_t)1 << K;
+            const bool want_hist = mhist.ensure(sizeof(unsigned long long) * n_masks) == cudaSuccess;
+            if (want_hist) cudaMemsetAsync(mhist.p, 0, sizeof(unsigned long long) * n_masks, st);
             launch_build_pair_table(fi, g, n_trees, ctx->d_lut.as<int16_t>(), ps.tab.as<uint64_t>(), nullptr,
                                     want_progs ? cursor.as<unsigned long long>() : nullptr, ps.map.as<uint32_t>(), fi_prog,
-                                    want_progs ? ps.irr_progs.as<FastProgram>() : nullptr, st);
+                                    want_progs ? ps.irr_progs.as<FastProgram>() : nullptr,
+                                    want_hist ? mhist.as<unsigned long long>() : nullptr, st);
             ctx->launches++;
+            ps.mask_trees.assign(want_hist ? n_masks : 0, 0ull);
+            if (want_hist) BAMSE_CUDA_TRY(ctx, cudaMemcpyAsync(ps.mask_trees.data(), mhist.p, sizeof(unsigned long long) * n_masks, cudaMemcpyDeviceToHost, st));
             BAMSE_CUDA_TRY(ctx, cudaStreamSynchronize(st));
-            cursor.release();
+            ps.owner_world = -1;
+            cursor.release(); mhist.release();
         }
     }
     // the same table in the order of the inside rows (counting sort; BAMSE_PAIR_SORT=0 disables)
@@ -518,6 +528,31 @@ static int plan_tables(bamse_ctx* ctx) {
                 pk.recipes = ps.recipes.as<CtxRecipe>();
                 pk.pair_tab = ps.has_tab ? ps.tab.as<uint64_t>() : nullptr;
                 pk.irr_progs = ps.irr_progs.as<FastProgram>();
+                pk.mask_owner = nullptr;
+                if (!ctx->owner.empty() && ctx->shard_world > 1 && !ps.mask_trees.empty()) {
+                    // node sets to ranks, heaviest first to the least loaded rank (trees per set from the pair table)
+                    bamse_ctx::PairState& pw = ctx->pairs[K];
+                    if (pw.owner_world != ctx->shard_world) {
+                        const int W = ctx->shard_world;
+                        const size_t n_masks = pw.mask_trees.size();
+                        std::vector<uint32_t> order(n_masks);
+                        for (size_t i = 0; i < n_masks; ++i) order[i] = (uint32_t)i;
+                        std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return pw.mask_trees[a] > pw.mask_trees[b]; });
+                        std::vector<double> load(W, 0.0);
+                        std::vector<uint8_t> own(n_masks, 0);
+                        for (uint32_t m : order) {
+                            int r_min = 0;
+                            for (int r2 = 1; r2 < W; ++r2) if (load[r2] < load[r_min]) r_min = r2;
+                            own[m] = (uint8_t)r_min;
+                            load[r_min] += (double)pw.mask_trees[m] + 1.0;
+                        }
+                        BAMSE_CUDA_TRY(ctx, pw.mask_owner.ensure(n_masks));
+                        BAMSE_CUDA_TRY(ctx, cudaMemcpyAsync(pw.mask_owner.p, own.data(), n_masks, cudaMemcpyHostToDevice, s));
+                        BAMSE_CUDA_TRY(ctx, cudaStreamSynchronize(s));
+                        pw.owner_world = W;
+                    }
+                    pk.mask_owner = pw.mask_owner.as<uint8_t>();
+                }
                 pk.sorted_tree = ps.sorted_tree.as<uint32_t>();
                 pk.sorted_entry = ps.sorted_entry.as<uint64_t>();
             }
@@ -682,7 +717,7 @@ void bamse_destroy(bamse_ctx* ctx) {
                     &ctx->d_flat_meta, &ctx->d_lists2, &ctx->d_segs2, &ctx->d_owner, &ctx->d_part, &ctx->d_pcm};
     for (DBuf* b : bufs) b->release();
     for (auto& t : ctx->progtab) t.buf.release();
-    for (auto& t : ctx->pairs) { t.tab.release(); t.map.release(); t.recipes.release(); t.sorted_tree.release(); t.sorted_entry.release(); t.irr_progs.release(); }
+    for (auto& t : ctx->pairs) { t.tab.release(); t.map.release(); t.recipes.release(); t.sorted_tree.release(); t.sorted_entry.release(); t.irr_progs.release(); t.mask_owner.release(); }
     for (auto& r : ctx->recipes) { r.buf.release(); r.order.release(); }
     ctx->d_order_ptrs.release();
     ctx->d_progtabs.release();
@@ -1330,6 +1365,8 @@ static int enumerate_dev(bamse_ctx* ctx, const double* d_const, const double* d_
         wp.total_chunks = scal + 10;
         wp.next_chunk = reinterpret_cast<unsigned long long*>(scal + 12);
         wp.part = ctx->d_part.as<float>();
+        // chunks per visit of the work counter: ~64 visits per warp
+        wp.grab = (int)std::min<uint64_t>(64, std::max<uint64_t>(1, chunks_pairs * (uint64_t)reps2 / ((uint64_t)workers2 * 64)));
         if (sample_major) {
             launch_enumerate_pairs(ctx->view(), ctx->fast(), wp, ctx->grid_pairs, 1, s);
             EnumWork wr = wp;                          // second pass: its own chunk counter

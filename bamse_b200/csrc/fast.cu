@@ -208,7 +208,7 @@ __global__ void __launch_bounds__(FAST_THREADS, BAMSE_BUILD_CTAS) k_forest_level
     const ForestRecipe rec = ft.recipes[tb->fi.K][row];
     // split (p, c): a top-level row is read only by the rank that scores the packs on its node set (when the
     // programs may push it too -- s_prog == s -- every rank keeps all rows)
-    if (tb->split && n == tb->fi.s && tb->s_prog < n && node_set_owner(rec.mask, ft.shard_world) != ft.shard_rank) return;
+    if (tb->split && n == tb->fi.s && tb->s_prog < n && set_owner(ft.pk + tb->fi.K, rec.mask, ft.shard_world) != ft.shard_rank) return;
     const size_t frow = (size_t)tb->fg_row + (size_t)m * tb->fi.nf;
     const size_t srow = (size_t)tb->fsg_row + (size_t)m * tb->nfsg;
     const float add2 = (float)((pv.p0[c] - 6.2383246250395077847550890931236) * 1.4426950408889634074);
@@ -321,7 +321,7 @@ __global__ void __launch_bounds__(FAST_THREADS, BAMSE_BUILD_CTAS) k_ctx_level(Pr
     const CtxRecipe rec = pk->recipes[row];
     // split (p, c): a top-level context is read only by the rank that scores the packs on the complement
     if (tb->split && q == pk->g.r &&
-        node_set_owner(((1u << tb->fi.K) - 1u) & ~(uint32_t)rec.mask, ft.shard_world) != ft.shard_rank) return;
+        set_owner(pk, ((1u << tb->fi.K) - 1u) & ~(uint32_t)rec.mask, ft.shard_world) != ft.shard_rank) return;
     const size_t trow = (size_t)tb->t_row + (size_t)m * pk->nt;
     const float add2 = (float)((pv.p0[c] - 6.2383246250395077847550890931236) * 1.4426950408889634074);
     warp_init_guards(ws, lane);
@@ -357,13 +357,14 @@ __global__ void __launch_bounds__(128) k_build_pair_table(ForestIndex fi, PairGe
                                                           const int16_t* __restrict__ lut, uint64_t* __restrict__ out,
                                                           uint8_t* __restrict__ used, unsigned long long* n_irregular,
                                                           const uint32_t* __restrict__ map, ForestIndex fi_prog,
-                                                          FastProgram* __restrict__ irr_progs) {
+                                                          FastProgram* __restrict__ irr_progs,
+                                                          unsigned long long* __restrict__ mask_hist) {
     const uint64_t tree = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (tree >= n_trees) return;
     int8_t parent[KMAX];
     decode_tree(fi.K, tree, parent);
-    uint32_t fg = 0, t = 0;
-    const bool reg = classify_tree(fi.K, parent, fi, lut, g, &fg, &t);
+    uint32_t fg = 0, t = 0, pack = 0;
+    const bool reg = classify_tree(fi.K, parent, fi, lut, g, &fg, &t, &pack);
     if (!out) {
         if (reg) used[t] = 1;
         else atomicAdd(n_irregular, 1ull);
@@ -374,6 +375,7 @@ __global__ void __launch_bounds__(128) k_build_pair_table(ForestIndex fi, PairGe
         TreeProgram ref;
         build_program(fi.K, parent, nullptr, &ref);
         e = pair_entry(fg, map[t], (uint32_t)ref.scre);
+        if (mask_hist) atomicAdd(mask_hist + pack, 1ull);
     } else if (irr_progs) {
         // an irregular tree: its table-driven program, once and for all; the entry (scre field 0) carries its slot
         const unsigned long long slot = atomicAdd(n_irregular, 1ull);
@@ -728,10 +730,18 @@ __global__ void __launch_bounds__(PAIR_THREADS, 6) k_enumerate_pairs(ProblemView
         }
     };
 
+    // `grab` consecutive chunks per visit of the global counter: with 10^8 chunks (K = 10) one atomic per chunk on
+    // one address costs ~1 ns each, on every rank -- a fixed cost that does not shrink with the number of GPUs
+    const unsigned long long grab = w.grab > 1 ? (unsigned long long)w.grab : 1ull;
+    unsigned long long chunk_base = 0, chunk_left = 0;
     for (;;) {
-        unsigned long long chunk = 0;
-        if (lane == 0) chunk = atomicAdd(w.next_chunk, 1ull);
-        chunk = __shfl_sync(0xffffffffu, chunk, 0);
+        if (chunk_left == 0) {
+            if (lane == 0) chunk_base = atomicAdd(w.next_chunk, grab);
+            chunk_base = __shfl_sync(0xffffffffu, chunk_base, 0);
+            chunk_left = grab;
+        }
+        const unsigned long long chunk = chunk_base++;
+        --chunk_left;
         if (chunk >= total) break;
         const uint64_t key = MODE == 2 ? chunk * (uint64_t)reps : chunk;
         int lo = 0, hi = w.n_segs - 1;
@@ -783,7 +793,7 @@ __global__ void __launch_bounds__(PAIR_THREADS, 6) k_enumerate_pairs(ProblemView
         // whose pack sits on one of its node sets and every world-th irregular tree
         bool mine = true;
         if (tb->split && valid) {
-            if (reg) mine = node_set_owner(ft.recipes[seg.K][fg].mask, ft.shard_world) == ft.shard_rank;
+            if (reg) mine = set_owner(pk, ft.recipes[seg.K][fg].mask, ft.shard_world) == ft.shard_rank;
             else mine = (int)(tree % (uint64_t)ft.shard_world) == ft.shard_rank;
         }
         reg = reg && mine;
@@ -919,9 +929,9 @@ void launch_forest_scan_top(const ProblemView& pv, const FastTables& ft, int max
 
 void launch_build_pair_table(const ForestIndex& fi, const PairGeom& g, uint64_t n_trees, const int16_t* d_lut,
                              uint64_t* out, uint8_t* used, unsigned long long* n_irregular, const uint32_t* d_map,
-                             const ForestIndex& fi_prog, FastProgram* irr_progs, cudaStream_t s) {
+                             const ForestIndex& fi_prog, FastProgram* irr_progs, unsigned long long* mask_hist, cudaStream_t s) {
     k_build_pair_table<<<(unsigned)((n_trees + 127) / 128), 128, 0, s>>>(fi, g, n_trees, d_lut, out, used, n_irregular, d_map,
-                                                                         fi_prog, irr_progs);
+                                                                         fi_prog, irr_progs, mask_hist);
 }
 
 static size_t fast_smem_bytes(int topk, bool framed = false, int slots = FAST_SLOTS) {

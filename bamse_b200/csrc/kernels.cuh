@@ -72,6 +72,7 @@ struct EnumWork {
     bamse_record* lists2;                 // the pair kernel's per-warp lists
     float* part;                          // sample-major pair path: per-sample log2 results [M][tree slots]
     unsigned long long* trees_done;       // trees this rank took in k_enumerate_pairs (regular + irregular)
+    int grab;                             // k_enumerate_pairs: chunks taken per visit of the work counter
 };
 
 void launch_tables(const ProblemView& pv, const double* d_var, const double* d_ref, const double* d_logc,
@@ -120,7 +121,7 @@ void launch_build_pair_table(const ForestIndex& fi, const PairGeom& g, uint64_t 
                              uint64_t* out, uint8_t* used, unsigned long long* n_irregular, const uint32_t* d_map,
                              const ForestIndex& fi_prog /* geometry of the programs */, FastProgram* irr_progs /* NULL: none;
                              else the program of every irregular tree, slot = entry & (2^42 - 1), *n_irregular = slot cursor */,
-                             cudaStream_t s);
+                             unsigned long long* mask_hist /* NULL or [2^K]: regular trees per pack node set */, cudaStream_t s);
 int enumerate_pairs_grid_size(int device);
 int enumerate_pairs_workers(int grid);
 // mode 0: tree-major; 1 + 2: sample-major (accumulate per sample into w.part, then sum and rank); the segments of

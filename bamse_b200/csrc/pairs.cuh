@@ -101,7 +101,7 @@ __host__ __device__ inline uint32_t ctx_row(const PairGeom& g, uint32_t mask, co
 // more than r nodes.
 __host__ __device__ inline bool classify_tree(int K, const int8_t* parent, const ForestIndex& fi,
                                               const int16_t* __restrict__ lut, const PairGeom& g, uint32_t* fg_row,
-                                              uint32_t* t_row) {
+                                              uint32_t* t_row, uint32_t* pack_mask = nullptr) {
     if (K < 2) return false;
     int8_t size[KMAX], depth[KMAX], order[KMAX];
     uint16_t sub[KMAX];
@@ -145,6 +145,7 @@ __host__ __device__ inline bool classify_tree(int K, const int8_t* parent, const
             target -= size[kids[i]];
         }
     }
+    if (pack_mask) *pack_mask = pack;
     *fg_row = (uint32_t)forest_row(fi, lut, pack, parent);
     *t_row = ctx_row(g, ((1u << K) - 1u) & ~pack, parent, best_v);
     return true;

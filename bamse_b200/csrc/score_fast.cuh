@@ -65,6 +65,8 @@ struct PairK {
     const uint64_t* pair_tab;      // [K^(K-1)] pair_entry per tree index (context row compact), NULL: cut in the kernel
     // the same entries ordered by inside row (counting sort): the lanes of a warp then share their inside row, whose
     // loads become warp-uniform (the pair kernel is bound by L1 wavefronts).  Used for whole index ranges.
+    const uint8_t* mask_owner;     // [2^K] node-set sharding of split clusterings: the rank of every pack node set,
+                                   // balanced by the number of trees per set (NULL: round robin, node_set_owner)
     const FastProgram* irr_progs;  // programs of the irregular trees, indexed by the low 42 bits of their pair-table
                                    // entry (scre field 0); NULL: decode / per-K program table
     const uint32_t* sorted_tree;   // [K^(K-1)] tree index, NULL: none
@@ -90,6 +92,10 @@ struct FastTables {
     int grid_blocks;           // table kernels: row blocks per (p, c, m) of this launch
     int shard_rank, shard_world;
 };
+
+__device__ __forceinline__ int set_owner(const PairK* pk, uint32_t mask, int world) {
+    return pk->mask_owner ? (int)pk->mask_owner[mask] : node_set_owner(mask, world);
+}
 
 // ----------------------------------------------------------------------------- warp ops
 __device__ __forceinline__ float ex2f(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
