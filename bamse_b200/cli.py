@@ -89,10 +89,12 @@ def main(argv=None):
     # The reference prunes with a heuristic branch-and-bound; this scorer searches all K^(K-1) labeled rooted
     # trees of every clustering exactly.  Say what that means before starting (K = 11: 2.6e10, K = 12: 7.4e11).
     n_trees_total = sum(int(c.As.shape[0]) ** (int(c.As.shape[0]) - 1) for c in clusts)
-    rate = 2.0e7                                    # full-scoring trees/s of one B200 on config 2; the early exit
-    print('analysing %d clusterings on the GPU: %.3g labeled rooted trees, at most ~%s at %.0e trees/s/GPU '
-          '(typically 5-10x less with the exact early exit)'
-          % (len(clusts), n_trees_total, _fmt_duration(n_trees_total / rate), rate))
+    # K <= 10 is table driven (one windowed dot product per tree and sample: 1e8 - 1e9 trees/s per B200, measured on
+    # the BASELINE configurations); K = 11, 12 still cost about one convolution per tree and sample (~2e7 trees/s)
+    n_small = sum(int(c.As.shape[0]) ** (int(c.As.shape[0]) - 1) for c in clusts if int(c.As.shape[0]) <= 10)
+    eta = (n_small / 2.0e8 + (n_trees_total - n_small) / 2.0e7) / max(1, args.gpus)
+    print('analysing %d clusterings on %d GPU(s): %.3g labeled rooted trees, roughly %s (exhaustive and exact; the '
+          'reference prunes heuristically)' % (len(clusts), max(1, args.gpus), n_trees_total, _fmt_duration(eta)))
     if n_trees_total > args.tree_budget:
         raise SystemExit("bamse: %.3g trees exceed --tree-budget %.3g (clusterings with K >= 11 take hours per "
                          "clustering); lower -nc / -n or raise --tree-budget explicitly" % (n_trees_total, args.tree_budget))

@@ -54,6 +54,16 @@ __host__ __device__ inline uint64_t ipow_u64(int base, int e) {
 
 }  // namespace bamse
 
+// -DBAMSE_DEBUG_BOUNDS (make DEBUG=1 -> libbamse_cuda_dbg.so): every table-row / list index the kernels compute is
+// checked against its extent and a violation traps (the launch fails with "unspecified launch failure", the tests
+// fail loudly).  compute-sanitizer is closed on the GPU pool this was developed on; running the GPU test suite on
+// the checked build (profiles/bounds_check.sh) is the substitute for its memcheck pass.
+#ifdef BAMSE_DEBUG_BOUNDS
+#define BAMSE_BOUND(cond) do { if (!(cond)) asm volatile("trap;"); } while (0)
+#else
+#define BAMSE_BOUND(cond) do { } while (0)
+#endif
+
 #define BAMSE_CUDA_TRY(ctx, expr)                                                        \
     do {                                                                                 \
         cudaError_t _e = (expr);                                                         \

@@ -154,6 +154,7 @@ __device__ inline double warp_eval_tree(const ProblemView& pv, const FastTables&
             const int op = fast_op(ws->prog, i);
             const int arg = ws->prog.arg[i];
             if (op == FOP_PUSH_G || op == FOP_PUSH_SG) {
+                BAMSE_BOUND(sp < (int)(sizeof(ws->vec) / sizeof(ws->vec[0])) && arg < (op == FOP_PUSH_G ? nf : tb->nfsg));
                 float* dst = ws->vec[sp] + GUARD;
                 warp_load_vec(dst, op == FOP_PUSH_G ? ft.FG + (frow + (size_t)arg) * L : ft.FSG + (srow + (size_t)arg) * L, lane);
                 ++sp;
@@ -172,7 +173,9 @@ __device__ inline double warp_eval_tree(const ProblemView& pv, const FastTables&
         const float* tab = nullptr;                  // FIN_LSE: plain log-sum-exp
         if (fin == FIN_DOT_D) tab = ft.D2 + base + (size_t)ws->prog.fin_r * L;
         else if (fin == FIN_DOT_SD) tab = ft.SD2 + base + (size_t)ws->prog.fin_r * L;
-        else if (fin == FIN_DOT_FH)
+        BAMSE_BOUND(fin != FIN_DOT_FH || (int)ws->prog.fin_arg < nfh);
+        BAMSE_BOUND(sp == 1);
+        if (fin == FIN_DOT_FH)
             tab = ft.FH + ((size_t)fh_row + ((size_t)m * Kc + ws->prog.fin_r) * nfh + ws->prog.fin_arg) * L;
         float res2 = warp_log2dot(ws->vec[0] + GUARD, tab, lane);
         if (fin == FIN_LSE || fin == FIN_DOT_D) res2 -= LOG2_L;
@@ -206,6 +209,8 @@ __global__ void __launch_bounds__(FAST_THREADS, BAMSE_BUILD_CTAS) k_forest_level
     // rows of a level in the order "convolutions first": the warps of a CTA get rows of the same kind
     const int row = (int)ft.level_order[tb->fi.K][tb->fi.base[n] + i];
     const ForestRecipe rec = ft.recipes[tb->fi.K][row];
+    BAMSE_BOUND(row >= tb->fi.base[n] && row < tb->fi.base[n + 1] && (rec.kind == 1 ? (int)rec.b < tb->fi.base[n] && (int)rec.b < tb->nfsg
+                                                                                      : (int)rec.a < tb->fi.base[n] && (int)rec.b < tb->fi.base[n]));
     // split (p, c): a top-level row is read only by the rank that scores the packs on its node set (when the
     // programs may push it too -- s_prog == s -- every rank keeps all rows)
     if (tb->split && n == tb->fi.s && tb->s_prog < n && set_owner(ft.pk + tb->fi.K, rec.mask, ft.shard_world) != ft.shard_rank) return;
@@ -319,6 +324,7 @@ __global__ void __launch_bounds__(FAST_THREADS, BAMSE_BUILD_CTAS) k_ctx_level(Pr
     if (i >= pk->lbase[q + 1] - pk->lbase[q]) return;
     const uint32_t row = pk->lbase[q] + i;
     const CtxRecipe rec = pk->recipes[row];
+    BAMSE_BOUND(row < pk->nt && rec.parent_row < (int32_t)pk->lbase[q] && rec.h_row < tb->fi.nf && rec.v >= 0 && rec.v < tb->fi.K);
     // split (p, c): a top-level context is read only by the rank that scores the packs on the complement
     if (tb->split && q == pk->g.r &&
         set_owner(pk, ((1u << tb->fi.K) - 1u) & ~(uint32_t)rec.mask, ft.shard_world) != ft.shard_rank) return;
@@ -516,8 +522,10 @@ k_enumerate_fast(ProblemView pv, FastTables ft, EnumWork w) {
                 const int mid = (lo + hi + 1) >> 1;
                 if (w.flat_prefix[mid] <= chunk) lo = mid; else hi = mid - 1;
             }
+            BAMSE_BOUND(w.flat_off[lo] + (chunk - w.flat_prefix[lo]) < w.flat_off[lo + 1]);
             const unsigned long long ent = w.flat[w.flat_off[lo] + (chunk - w.flat_prefix[lo])];
             lo = (int)(ent >> 40);
+            BAMSE_BOUND(lo < w.n_segs);
             flat_tree = ent & ((1ull << 40) - 1ull);
         } else {
             while (lo < hi) {
@@ -816,6 +824,8 @@ __global__ void __launch_bounds__(PAIR_THREADS, 6) k_enumerate_pairs(ProblemView
         const float* g = ft.FG + ((size_t)tb->fg_row + fg) * L;
         const float* t = ft.T + ((size_t)tb->t_row + tr) * L;
         const size_t gstep = (size_t)tb->fi.nf * L, tstep = (size_t)pk->nt * L;
+        BAMSE_BOUND(!reg || ((int)fg < tb->fi.nf && tr < pk->nt && tb->mine));
+        BAMSE_BOUND(MODE == 0 || !reg || slot < slots);
         if (MODE == 1) {
             if (reg) {
                 w.part[(size_t)m_one * slots + slot] = lane_log2dot(g + (size_t)m_one * gstep, t + (size_t)m_one * tstep, st_groups);
