@@ -310,6 +310,43 @@ static int ensure_pair_state(bamse_ctx* ctx, int K) {
     return BAMSE_OK;
 }
 
+// The assignment itself (pure host arithmetic; bamse_debug_shard_plan exposes it to the CPU tests): longest
+// processing time first over whole (p, c) pairs, with the j most expensive pairs split over all ranks instead (a
+// split pair costs its table build on every rank and 1/W of its enumeration), j chosen to minimise the makespan.
+static std::vector<int32_t> plan_owners(int P, int C, const int32_t* K_of_c, int W, const double* build_k, const double* enum_k) {
+    const int n = P * C;
+    std::vector<int> order(n);
+    for (int i = 0; i < n; ++i) order[i] = i;
+    auto cost = [&](int i) { const int K = K_of_c[i % C]; return build_k[K] + enum_k[K]; };
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return cost(a) > cost(b); });
+    int best_j = 0;
+    double best_span = -1.0;
+    std::vector<double> load(W);
+    const int j_max = std::min(n, 4 * W + 8);
+    for (int j = 0; j <= j_max; ++j) {
+        double base = 0.0;
+        for (int t = 0; t < j; ++t) { const int K = K_of_c[order[t] % C]; base += build_k[K] + enum_k[K] / W; }
+        for (int r = 0; r < W; ++r) load[r] = base;
+        for (int t = j; t < n; ++t) {
+            int r_min = 0;
+            for (int r = 1; r < W; ++r) if (load[r] < load[r_min]) r_min = r;
+            load[r_min] += cost(order[t]);
+        }
+        double span = 0.0;
+        for (int r = 0; r < W; ++r) span = std::max(span, load[r]);
+        if (best_span < 0.0 || span < best_span * (1.0 - 1e-9)) { best_span = span; best_j = j; }
+    }
+    std::vector<int32_t> owner(n, -1);
+    for (int r = 0; r < W; ++r) load[r] = 0.0;
+    for (int t = best_j; t < n; ++t) {
+        int r_min = 0;
+        for (int r = 1; r < W; ++r) if (load[r] < load[r_min]) r_min = r;
+        load[r_min] += cost(order[t]);
+        owner[order[t]] = r_min;
+    }
+    return owner;
+}
+
 // Sharding plan (multi-GPU): which rank scores which (parameter set, clustering).  Tables are per (p, c), so a
 // pair that one rank owns entirely costs its table build once; a pair split over all ranks (interleaved tree
 // indices) costs the build on EVERY rank.  Longest-processing-time assignment of whole pairs, with the j most
@@ -342,36 +379,7 @@ static void make_shard_plan(bamse_ctx* ctx) {
             enum_k[K] = T * (K <= 6 ? 0.1 : 0.25 * (K - 5));
         }
     }
-    const int n = P * C;
-    std::vector<int> order(n);
-    for (int i = 0; i < n; ++i) order[i] = i;
-    auto cost = [&](int i) { const int K = ctx->K_of_c[i % C]; return build_k[K] + enum_k[K]; };
-    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return cost(a) > cost(b); });
-    int best_j = 0;
-    double best_span = -1.0;
-    std::vector<double> load(W);
-    const int j_max = std::min(n, 4 * W + 8);
-    for (int j = 0; j <= j_max; ++j) {
-        double base = 0.0;
-        for (int t = 0; t < j; ++t) { const int K = ctx->K_of_c[order[t] % C]; base += build_k[K] + enum_k[K] / W; }
-        for (int r = 0; r < W; ++r) load[r] = base;
-        for (int t = j; t < n; ++t) {
-            int r_min = 0;
-            for (int r = 1; r < W; ++r) if (load[r] < load[r_min]) r_min = r;
-            load[r_min] += cost(order[t]);
-        }
-        double span = 0.0;
-        for (int r = 0; r < W; ++r) span = std::max(span, load[r]);
-        if (best_span < 0.0 || span < best_span * (1.0 - 1e-9)) { best_span = span; best_j = j; }
-    }
-    ctx->owner.assign(n, -1);
-    for (int r = 0; r < W; ++r) load[r] = 0.0;
-    for (int t = best_j; t < n; ++t) {
-        int r_min = 0;
-        for (int r = 1; r < W; ++r) if (load[r] < load[r_min]) r_min = r;
-        load[r_min] += cost(order[t]);
-        ctx->owner[order[t]] = r_min;
-    }
+    ctx->owner = plan_owners(P, C, ctx->K_of_c.data(), W, build_k, enum_k);
 }
 
 // Geometry of every cluster count present (stepped down until the tables fit the budget), pair states, table
@@ -744,6 +752,15 @@ int bamse_set_shard(bamse_ctx* ctx, int rank, int world) {
 }
 
 int bamse_fast_variant(const bamse_ctx* ctx) { return ctx ? ctx->use_framed : -1; }
+
+int bamse_debug_shard_plan(int P, int C, const int32_t* K_of_c, int world, const double* build_cost, const double* enum_cost,
+                           int32_t* out_owner) try {
+    if (P < 1 || C < 1 || world < 1 || !K_of_c || !build_cost || !enum_cost || !out_owner) return BAMSE_EINVAL;
+    for (int c = 0; c < C; ++c) if (K_of_c[c] < 1 || K_of_c[c] > KMAX) return BAMSE_EINVAL;
+    const std::vector<int32_t> owner = plan_owners(P, C, K_of_c, world, build_cost, enum_cost);
+    for (size_t i = 0; i < owner.size(); ++i) out_owner[i] = owner[i];
+    return BAMSE_OK;
+} catch (...) { return on_exception(nullptr, "bamse_debug_shard_plan"); }
 
 int bamse_debug_pair_stats(bamse_ctx* ctx, int K, int s, int r, int64_t* out4) try {
     CTX_CHECK(ctx);

@@ -108,6 +108,8 @@ def load_library():
     lib.bamse_debug_ctx_recipes.argtypes = [i32, i32, i32, c_p]
     lib.bamse_debug_classify.restype = i32
     lib.bamse_debug_classify.argtypes = [i32, c_p, i32, i32, c_p]
+    lib.bamse_debug_shard_plan.restype = i32
+    lib.bamse_debug_shard_plan.argtypes = [i32, i32, c_p, i32, c_p, c_p, c_p]
     lib.bamse_debug_pair_stats.restype = i32
     lib.bamse_debug_pair_stats.argtypes = [c_p, i32, i32, i32, c_p]
     if lib.bamse_abi_version() != 1:
@@ -122,7 +124,7 @@ EXPORTED_SYMBOLS = [
     "bamse_score_list", "bamse_score_range", "bamse_score_topk", "bamse_enumerate_topk_dev",
     "bamse_merge_topk_dev", "bamse_kernel_time", "bamse_table_time", "bamse_kernel_stats",
     "bamse_debug_forest_geometry", "bamse_debug_forest_recipes", "bamse_debug_program",
-    "bamse_debug_pair_geometry", "bamse_debug_ctx_recipes", "bamse_debug_classify", "bamse_debug_pair_stats",
+    "bamse_debug_pair_geometry", "bamse_debug_ctx_recipes", "bamse_debug_classify", "bamse_debug_pair_stats", "bamse_debug_shard_plan",
 ]
 
 

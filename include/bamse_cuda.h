@@ -226,6 +226,10 @@ int bamse_debug_program(int k, const int8_t* parent, const int8_t* nodes, int Kc
 int bamse_debug_pair_geometry(int K, int32_t* s, int32_t* r, int32_t* out_nf, int32_t* out_nt);
 int bamse_debug_ctx_recipes(int K, int s, int r, int32_t* out);
 int bamse_debug_classify(int K, const int8_t* parent, int s, int r, int32_t* out);
+/* The assignment step of the sharding plan as a pure function (no GPU): build_cost / enum_cost are indexed by cluster
+ * count [0 .. BAMSE_KMAX]; out_owner [P][C] = owning rank or -1 (split over all ranks). */
+int bamse_debug_shard_plan(int P, int C, const int32_t* K_of_c, int world, const double* build_cost,
+                           const double* enum_cost, int32_t* out_owner);
 /* Needs the GPU (cuts all K^(K-1) trees on the device): out4 = {inside rows, context rows of the full index space,
  * context rows in use, irregular trees} of the pair geometry (s, r).  Invalidates the resident problem. */
 int bamse_debug_pair_stats(bamse_ctx* ctx, int K, int s, int r, int64_t* out4);

@@ -259,6 +259,47 @@ def test_fraction_solver_against_an_independent_solve():
     assert worst_f <= 1e-9 and worst_x <= 2e-4, (worst_f, worst_x)
 
 
+def test_shard_plan_assignment():
+    """the assignment step of the multi-GPU sharding plan (pure host arithmetic behind bamse_set_shard +
+    bamse_upload_problem): whole (parameter set, clustering) pairs by longest processing time, the most expensive
+    ones split over all ranks (-1) when that lowers the estimated makespan; deterministic."""
+    import ctypes
+    lib = cuda_shim.load_library()
+
+    def plan(P, Ks, W, build, enum):
+        Ks = np.asarray(Ks, dtype=np.int32)
+        b = np.zeros(13)
+        e = np.zeros(13)
+        for k, v in build.items():
+            b[k] = v
+        for k, v in enum.items():
+            e[k] = v
+        out = np.zeros(P * len(Ks), dtype=np.int32)
+        assert lib.bamse_debug_shard_plan(P, len(Ks), Ks.ctypes.data_as(ctypes.c_void_p), W, b.ctypes.data_as(ctypes.c_void_p),
+                                          e.ctypes.data_as(ctypes.c_void_p), out.ctypes.data_as(ctypes.c_void_p)) == 0
+        return out.reshape(P, len(Ks)), b, e
+
+    # config-2-like: 49 + 26 + 4 clusterings, tables dominate -> whole pairs, 7 of the K = 6 ones on the fullest rank
+    Ks = [6] * 49 + [5] * 26 + [4] * 4
+    own, b, e = plan(1, Ks, 8, {6: 1000.0, 5: 150.0, 4: 40.0}, {6: 31.0, 5: 2.5, 4: 0.3})
+    assert (own >= 0).all() and set(own.ravel()) == set(range(8))
+    loads = np.zeros(8)
+    for c, K in enumerate(Ks):
+        loads[own[0, c]] += b[K] + e[K]
+    assert loads.max() <= 7 * 1031.0 + 1e-9 and loads.max() / loads.mean() < 1.15
+    own2, _, _ = plan(1, Ks, 8, {6: 1000.0, 5: 150.0, 4: 40.0}, {6: 31.0, 5: 2.5, 4: 0.3})
+    np.testing.assert_array_equal(own, own2)
+    # config-4-like: three huge clusterings on 8 ranks, enumeration dominates -> all split
+    own, _, _ = plan(1, [10, 10, 10], 8, {10: 2.0e6}, {10: 3.0e7})
+    assert (own == -1).all()
+    # one rank: everything is owned by rank 0
+    own, _, _ = plan(2, [5, 6], 1, {5: 1.0, 6: 2.0}, {5: 1.0, 6: 1.0})
+    assert (own == 0).all()
+    # a sweep: 64 parameter sets x 3 clusterings on 8 ranks -> 24 pairs per rank, nothing split
+    own, _, _ = plan(64, [3, 4, 5], 8, {3: 1.0, 4: 5.0, 5: 30.0}, {3: 0.1, 4: 0.3, 5: 2.5})
+    assert (own >= 0).all() and np.bincount(own.ravel(), minlength=8).tolist() == [24] * 8
+
+
 def test_workloads_are_reproducible():
     """the BASELINE.json configurations as work lists: seeded, same clusterings every time."""
     from bamse_b200 import workloads
