@@ -411,17 +411,19 @@ static int plan_tables(bamse_ctx* ctx) {
         ctx->geom_sh[K] = std::min(ctx->geom_sh[K], program_forest_s(K, sK));
     }
     double budget = 0.0;
-    {
-        size_t free_b = 0, total_b = 0;
-        BAMSE_CUDA_TRY(ctx, cudaMemGetInfo(&free_b, &total_b));
-        budget = 0.6 * (double)total_b;
-        if (const char* g = getenv("BAMSE_TABLE_GB")) budget = atof(g) * 1e9;
-    }
     std::vector<TableBase> tbs((size_t)P * C);
     size_t fg_rows = 0, fsg_rows = 0, fh_rows = 0, t_rows = 0;
     for (;;) {
         for (int K = 1; K <= KMAX; ++K)
             if (k_present[K] && ctx->geom_r[K] > 0) { const int rc = ensure_pair_state(ctx, K); if (rc) return rc; }
+        {   // 60 % of the device, but never more than what is free once the data-independent tables of the cluster
+            // counts present (pair tables: 21 GB at K = 10) are in place; the table buffers held now are re-used
+            size_t free_b = 0, total_b = 0;
+            BAMSE_CUDA_TRY(ctx, cudaMemGetInfo(&free_b, &total_b));
+            const double held = (double)(ctx->d_FG.cap + ctx->d_FSG.cap + ctx->d_T.cap + ctx->d_FH.cap);
+            budget = std::min(0.6 * (double)total_b, 0.9 * ((double)free_b + held));
+            if (const char* g = getenv("BAMSE_TABLE_GB")) budget = atof(g) * 1e9;
+        }
         make_shard_plan(ctx);
         fg_rows = fsg_rows = fh_rows = t_rows = 0;
         double per_k[KMAX + 1] = {0.0};
