@@ -1,8 +1,8 @@
 """Multi-GPU plumbing.
 
 Two ways to use several GPUs of one box, both on the library's sharding plan (bamse_set_shard before the
-upload: whole (parameter set, clustering) pairs per rank by estimated cost, the most expensive ones split by
-interleaved tree index) and the same deterministic merge of the per-rank top-k records:
+upload: whole (parameter set, clustering) pairs per rank by estimated cost, the most expensive ones split over all
+ranks: by pack node sets on the pair path, by interleaved tree index otherwise) and the same deterministic merge of the per-rank top-k records:
 
 * one process (rank) per GPU under torchrun, one NCCL all-gather of each rank's records (bench.py);
   torch.distributed is only the transport (NCCL over NVLink on the GPU box, gloo in the CPU tests);

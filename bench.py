@@ -276,7 +276,8 @@ def config_dict(args, work, world):
             "param_sets": len(work["errs"]), "samples": work["M"],
             "evals_per_step": work["n_evals_per_param"] * len(work["errs"]),
             "parallelism": "x%d: whole (parameter set, clustering) pairs per rank by estimated cost, the most expensive "
-                           "ones split by interleaved tree index; one all-gather of the top-k records" % world,
+                           "ones split over all ranks (by pack node sets on the pair path, by interleaved tree index "
+                           "otherwise); one all-gather of the top-k records" % world,
             "l2": "256 MiB write between steps inside the timed region; every step rebuilds its tables (GBs) from the counts"}
 
 
@@ -350,7 +351,7 @@ def main():
             c._apply_order(s[o:o + n] if n else [])
     Ks, var, ref, Kmax = _pack_problem(clusts)
     # ---- shard BEFORE the upload: the library plans which rank owns which (parameter set, clustering) -- whole
-    #      pairs where it can, interleaved tree indices for the most expensive ones -- and builds tables only
+    #      pairs where it can, the most expensive ones split (pack node sets / interleaved tree indices) -- and builds tables only
     #      for what this rank scores (bamse_set_shard + BAMSE_OPT_SHARD_PLAN)
     ctx.set_shard(rank, world)
     if args.emulate_shard_of > 1 and world == 1:

@@ -94,7 +94,8 @@ int bamse_fast_variant(const bamse_ctx* ctx);
 #define BAMSE_OPT_EARLY_EXIT 1
 /* BAMSE_OPT_SHARD_PLAN (default 1): with a shard (rank, world > 1) set BEFORE bamse_upload_problem, whole
  * (parameter set, clustering) pairs are assigned to ranks by estimated cost (tables are built only where they are
- * needed) and only the most expensive pairs are split over all ranks by interleaved tree index; 0 = split
+ * needed) and only the most expensive pairs are split over all ranks (by pack node sets on the pair path, by interleaved tree
+ * index otherwise); 0 = split
  * everything.  Every rank computes the same plan.  The plan belongs to the resident problem: changing the shard
  * afterwards requires a new upload (scoring calls fail with BAMSE_ESTATE until then).
  * BAMSE_OPT_STATS (default 0): the table-building kernels also count their executed work (bamse_kernel_stats). */
