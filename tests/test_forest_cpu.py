@@ -185,3 +185,73 @@ def test_program_bounds_for_large_k(built_library, K):
         for t in trees[-5:] + trees[:3]:
             want = orc.tree_score_samples(t, D[:, None, :], p0)[0]
             assert tab.run(program(lib, t, None, K, s, sh)) == pytest.approx(want, rel=1e-9)
+
+
+def _step_down(s, sh):
+    """reduce_forest_geometry (bamse_b200/csrc/forest_host.h): the next smaller geometry, or None."""
+    if sh > 1 and sh >= s - 1:
+        return s, sh - 1
+    if s > 2:
+        return s - 1, min(sh, s - 1)
+    if sh > 1:
+        return s, sh - 1
+    return None
+
+
+@pytest.mark.parametrize("K", list(range(3, 13)))
+def test_stepped_down_geometries_stay_within_the_kernel_limits(built_library, K):
+    """Under memory pressure (BAMSE_TABLE_GB, or a problem larger than the device) plan_tables walks the geometry
+    of a cluster count down to (s, sh) = (2, 1).  On every rung the programs must still fit the kernel: at most
+    forest_slots_needed live vectors (the kernel traps above its slot count), at most 20 operations, 16-bit row
+    ids.  All trees for K <= 6, 20 000 random ones + the extreme shapes above (exhaustive runs of this check up to
+    K = 8, 1.5 M random trees per rung for K = 9 ... 12, gave the same maxima: 2 vectors up to (K <= 8, any s),
+    (K <= 10, s >= 3); 3 vectors at K >= 9 with s = 2 and at K >= 11 -- a fourth would need a 19-node tree)."""
+    lib = cuda_shim.load_library()
+    T = K ** (K - 1)
+    rng = np.random.default_rng(100 + K)
+    idx = range(T) if T <= 8000 else [int(x) for x in rng.integers(0, T, size=20000)]
+    trees = [orc.decode_tree(K, i) for i in idx]
+    trees += [[-1] + list(range(K - 1)), [-1] + [0] * (K - 1), [-1, 0] + [1] * (K - 2),
+              [-1] + [i // 2 for i in range(K - 1)], [-1] + [max(0, i - 1) if i % 2 else max(0, i - 2) for i in range(K - 1)]]
+    if K >= 9:      # the smallest tree that keeps three vectors alive at s = 2: two 4-node "need two" subtrees under a root
+        trees.append(([-1, 0, 1, 1, 2, 0, 5, 5, 6] + [0] * (K - 9))[:K])
+    s, sh, nf, nfh, slots = geometry(lib, K)
+    rungs = [(s, sh)]
+    while _step_down(*rungs[-1]):
+        rungs.append(_step_down(*rungs[-1]))
+    assert rungs[-1] == (2, 1) or K <= 3
+    seen_sp = {}
+    for s, sh in rungs:
+        s2, sh2, nf, nfh, slots = geometry(lib, K, s, sh)
+        assert (s2, sh2) == (s, sh) and nf <= 65535
+        worst_sp = worst_ops = 0
+        for t in trees:
+            prog = program(lib, t, None, K, s, sh)
+            worst_sp, worst_ops = max(worst_sp, prog["max_sp"]), max(worst_ops, len(prog["ops"]))
+            assert all(0 <= a < nf for op, a in prog["ops"] if op in (FOP_PUSH_G, FOP_PUSH_SG))
+            assert prog["fin"] != FIN_DOT_FH or prog["fin_arg"] < nfh
+        assert worst_sp <= slots <= 3 and worst_ops <= 20, (K, s, sh, worst_sp, slots, worst_ops)
+        seen_sp[(s, sh)] = worst_sp
+    if K >= 9:
+        assert seen_sp[(2, 1)] == 3
+
+
+@pytest.mark.parametrize("K,s,sh", [(7, 2, 1), (8, 2, 1), (8, 3, 1), (9, 2, 1)])
+def test_programs_of_the_smallest_geometries_reproduce_the_oracle(built_library, K, s, sh):
+    """the rungs only memory pressure reaches: a stratified sample of trees, program == oracle (1e-9 relative)."""
+    lib = cuda_shim.load_library()
+    s, sh, nf, nfh, slots = geometry(lib, K, s, sh)
+    rec = recipes(lib, K, s, nf)
+    D = _tables(K, 7 * K + s)
+    p0 = orc.prior_const(K)
+    tab = Tables(D, p0, rec, nfh)
+    T = K ** (K - 1)
+    trees = [orc.decode_tree(K, i) for i in list(range(0, T, max(1, T // 40))) + [T - 1]]
+    trees += [[-1] + [i // 2 for i in range(K - 1)], [-1, 0] + [1] * (K - 2)]
+    if K >= 9:
+        trees.append([-1, 0, 1, 1, 2, 0, 5, 5, 6][:K])
+    for t in trees:
+        prog = program(lib, t, None, K, s, sh)
+        want = orc.tree_score_samples(t, D[:, None, :], p0)[0]
+        assert tab.run(prog) == pytest.approx(want, rel=1e-9), (K, s, sh, t, prog)
+        assert prog["scre"] == orc.canon_weight(t)[1] and prog["max_sp"] <= slots
