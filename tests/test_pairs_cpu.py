@@ -59,7 +59,8 @@ class Contexts(object):
         return t
 
 
-@pytest.mark.parametrize("K,s,r", [(2, 1, 1), (3, 2, 1), (4, 2, 2), (5, 3, 3), (5, 3, 2), (6, 4, 3), (6, 3, 3), (7, 4, 4), (8, 4, 4)])
+@pytest.mark.parametrize("K,s,r", [(2, 1, 1), (3, 2, 1), (4, 2, 2), (5, 3, 3), (5, 3, 2), (6, 4, 3), (6, 3, 3), (6, 3, 4), (7, 4, 4),
+                                   (7, 4, 3), (8, 4, 4)])
 def test_pairs_reproduce_the_oracle(built_library, K, s, r):
     """all trees for K <= 5, a stratified sample above: log sum 2^(FG[pack] + T[context]) == oracle score."""
     lib = cuda_shim.load_library()
@@ -85,7 +86,7 @@ def test_pairs_reproduce_the_oracle(built_library, K, s, r):
         want = orc.tree_score_samples(tree, D[:, None, :], p0)[0]
         got = logsumexp(tab.FG[fg] + ctxs.row(t))
         assert got == pytest.approx(want, rel=1e-9), (K, s, r, i, tree, fg, t)
-    if (K, s, r) in ((2, 1, 1), (3, 2, 1), (4, 2, 2), (5, 3, 3), (6, 4, 3), (7, 4, 4)):
+    if (K, s, r) in ((2, 1, 1), (3, 2, 1), (4, 2, 2), (5, 3, 3), (6, 4, 3), (6, 3, 4), (7, 4, 4)):
         assert n_reg == len(idx)                          # these geometries cut every tree
     else:
         assert n_reg > 0.85 * len(idx)
@@ -110,6 +111,76 @@ def test_pair_cuts_for_large_k(built_library, K):
             n_pack = bin(int(rec[fg][4])).count("1")
             assert K - r <= n_pack <= s and 0 <= tr < nt
     assert n_reg > 0.8 * len(trees)
+
+
+class LazyTables(object):
+    """inside rows FG / FSG on demand (memoised recursion over the recipes): what a handful of trees needs out of
+    the 10^5 rows of K >= 8."""
+
+    def __init__(self, D, p0, rec):
+        self.D, self.p0, self.rec = D, p0, rec
+        self._fg, self._fsg = {}, {}
+
+    def fg(self, i):
+        if i not in self._fg:
+            kind, u, a, b, mask = (int(x) for x in self.rec[i])
+            if kind == 0:
+                v = orc.log_cumsum(self.D[u]) + self.p0
+            elif kind == 1:
+                v = self.D[u] + self.fsg(b)
+            else:
+                v = orc.log_convolve(self.fg(a), self.fg(b))
+            self._fg[i] = v
+        return self._fg[i]
+
+    def fsg(self, i):
+        if i not in self._fsg:
+            self._fsg[i] = orc.log_cumsum(self.fg(i)) + self.p0
+        return self._fsg[i]
+
+    class _View(object):
+        def __init__(self, owner):
+            self.owner = owner
+
+        def __getitem__(self, i):
+            return self.owner.fg(int(i))
+
+    @property
+    def FG(self):
+        return LazyTables._View(self)
+
+
+@pytest.mark.parametrize("K", [8, 9, 10])
+def test_pairs_at_the_default_geometry_of_large_k_reproduce_the_oracle(built_library, K):
+    """K = 8 (4, 5), K = 9 and 10 (5, 6) -- the cluster counts of BASELINE configs 3 and 4: the cut of a tree
+    (host instance of classify_tree), the inside row of its pack and the context row of the rest, built here in
+    fp64 from the recipes the kernels follow (only the rows these trees need), reproduce the oracle's score.
+    Random trees + the extreme shapes; K = 10 also meets irregular trees (2 %), which are skipped here (their
+    programs are checked in test_forest_cpu.py)."""
+    lib = cuda_shim.load_library()
+    s, r, nf, nt = pair_geometry(lib, K)
+    assert (s, r) == {8: (4, 5), 9: (5, 6), 10: (5, 6)}[K]
+    rec = recipes(lib, K, s, nf)
+    crec = ctx_recipes(lib, K, s, r, nt)
+    D = _tables(K, 31 * K)
+    p0 = orc.prior_const(K)
+    tab = LazyTables(D, p0, rec)
+    ctxs = Contexts(D, p0, tab.FG, crec)
+    rng = np.random.default_rng(900 + K)
+    trees = [orc.decode_tree(K, int(rng.integers(0, K ** (K - 1)))) for _ in range(36)]
+    trees += [[-1] + list(range(K - 1)), [-1] + [0] * (K - 1), [-1, 0] + [1] * (K - 2), [-1] + [i // 2 for i in range(K - 1)],
+              [K - 1] + [-1] + [1] * (K - 3) + [K - 2]]
+    n_reg = 0
+    for tree in trees:
+        reg, fg, t = classify(lib, tree, s, r)
+        if not reg:
+            continue
+        n_reg += 1
+        assert 0 <= fg < nf and 0 <= t < nt
+        want = orc.tree_score_samples(tree, D[:, None, :], p0)[0]
+        got = logsumexp(tab.FG[fg] + ctxs.row(t))
+        assert got == pytest.approx(want, rel=1e-9), (K, s, r, tree, fg, t)
+    assert n_reg >= len(trees) - (4 if K == 10 else 0)
 
 
 def test_default_geometry_is_consistent(built_library):
