@@ -51,10 +51,24 @@ def _problem():
     return var, ref
 
 
-def _answers(shim, var, ref):
+def _level_constants(shim, var, ref):
+    """per-clustering constants that bring the best trees of the three clusterings within 0.1 of each other, so
+    that the global top-k mixes the clusterings (best total of clustering c alone, by three top-1 calls)."""
+    const = np.zeros((1, len(KS)))
     with shim.Context(0) as ctx:
         ctx.upload_problem([0.003], KS, var, ref)
-        const = np.array([[0.0, 40.0, -15.0]])
+        for c in range(len(KS)):
+            end = BEGIN.copy()
+            end[c] = END[c]                           # every other range is empty
+            rec, _, cnt = ctx.score_topk(np.zeros((1, len(KS))), None, BEGIN, end, topk=1, precision=shim.FP32)
+            assert cnt[0] == 1 and int(rec[0, 0]["clust"]) == c
+            const[0, c] = -float(rec[0, 0]["total"]) + (0.0, 0.05, -0.05)[c]
+    return const
+
+
+def _answers(shim, var, ref, const):
+    with shim.Context(0) as ctx:
+        ctx.upload_problem([0.003], KS, var, ref)
         rec, par, cnt = ctx.score_topk(const, None, BEGIN, END, topk=10, precision=shim.FP32)
         assert ctx.last_topk_verified
         evals = ctx.last_eval_count
@@ -72,15 +86,16 @@ def test_fallback_routes_return_the_default_answers(shim, monkeypatch):
              "BAMSE_FOREST_S", "BAMSE_FOREST_SH", "BAMSE_PAIRS")
     for name in names:
         monkeypatch.delenv(name, raising=False)
-    want = _answers(shim, var, ref)
+    const = _level_constants(shim, var, ref)
+    want = _answers(shim, var, ref, const)
     assert want["cnt"][0] == 10 and want["evals"] == int(np.sum(END - BEGIN))
     assert np.max(np.abs(want["s32"] - want["s64"]) / np.abs(want["s64"])) <= FP32_RTOL
     assert np.max(np.abs(want["s7"] - want["s7_64"]) / np.abs(want["s7_64"])) <= FP32_RTOL
-    assert len({int(c) for c in want["rec"][0]["clust"]}) >= 2          # the constants mix the clusterings
+    assert int(want["rec"][0, 0]["clust"]) == 1 and len({int(c) for c in want["rec"][0]["clust"]}) >= 2   # mixed
     for env in VARIANTS:
         for name, value in env.items():
             monkeypatch.setenv(name, value)
-        got = _answers(shim, var, ref)
+        got = _answers(shim, var, ref, const)
         for name in env:
             monkeypatch.delenv(name)
         assert got["evals"] == want["evals"], env
