@@ -351,3 +351,23 @@ def test_committed_bench_lines_follow_the_contract():
         assert set(("bound", "achieved", "peak", "unit", "frac", "traffic")) <= set(d["roofline"])
         assert d["gpu_launches"] > 0 and d["value"] > 0 and d["e2e"]["value"] > 0
         assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+
+
+def test_the_binding_printed_in_integration_md_matches_the_library(built_library):
+    """INTEGRATION.md section 2 prints the ctypes module a maintainer of the reference would add.  It must load
+    against the built library as printed: every symbol it binds is exported, its record dtype is the ABI's, and
+    without a GPU its constructor reports the library's own error (no CPU fallback) instead of crashing."""
+    import re
+    with open(os.path.join(ROOT, "INTEGRATION.md")) as f:
+        text = f.read()
+    block = re.search(r"```python\n(# bamse_cuda\.py.*?)```", text, re.S).group(1)
+    assert 'ctypes.CDLL("libbamse_cuda.so")' in block
+    ns = {}
+    exec(compile(block.replace('"libbamse_cuda.so"', repr(built_library)), "INTEGRATION.md", "exec"), ns)
+    assert ns["RECORD"] == cuda_shim.RECORD_DTYPE and ns["RECORD"].itemsize == 32
+    for name in re.findall(r"_lib\.(bamse_\w+)", block):
+        assert hasattr(ns["_lib"], name), name
+    if not has_cuda():
+        with pytest.raises(RuntimeError) as e:
+            ns["Scorer"](0)
+        assert "no CPU fallback" in str(e.value)
