@@ -96,6 +96,43 @@ def gen_scores():
     dump("tree_scores.json", cases)
 
 
+def gen_scores_edges():
+    """round 2: the inputs of tests/test_gpu_edges.py through the UNMODIFIED reference -- clusters without variant
+    reads / without any reads / without reference reads (all 64 trees), error rates 1e-6 and 0.499, one sample
+    and 64 samples, K = 1 and K = 2.  Closes the chain reference == oracle (here) == CUDA (test_gpu_edges.py) at
+    the edges of the domain."""
+    import bamse_oracle as orc
+    cases = []
+
+    def add(tag, As, Bs, err, tree_indices):
+        K = As.shape[0]
+        D, P = ref_tables(As, Bs, err, K)
+        for i in tree_indices:
+            tree = orc.decode_tree(K, int(i))
+            s = cl.tree_integrate_multisample(tree, D, P)
+            cases.append(dict(id="%s-%d" % (tag, i), var=As.tolist(), ref=Bs.tolist(), err=err, K_prior=K, tree=tree,
+                              tree_index=int(i), nodes=list(range(K)), per_sample=[float(x) for x in s],
+                              total=float(np.sum(s)), scre=int(tt.canonizeF(tree)['scre'])))
+
+    var = np.array([[120, 80, 95], [0, 0, 0], [30, 0, 12], [7, 55, 3]], dtype=np.int64)
+    ref_ = np.array([[380, 420, 405], [250, 310, 275], [170, 0, 188], [193, 0, 197]], dtype=np.int64)
+    add("zero", var, ref_, 0.002, range(64))
+    rng = np.random.default_rng(499)          # test_error_rates_at_both_ends_in_one_sweep
+    var = rng.integers(0, 400, size=(4, 2)).astype(np.int64)
+    ref_ = rng.integers(300, 900, size=(4, 2)).astype(np.int64)
+    for e in (1e-6, 0.499):
+        add("err%g" % e, var, ref_, e, range(0, 64, 3))
+    rng = np.random.default_rng(64)           # test_one_sample_and_the_maximum_number_of_samples
+    for M in (1, 64):
+        var = rng.integers(0, 200, size=(3, M)).astype(np.int64)
+        ref_ = rng.integers(100, 400, size=(3, M)).astype(np.int64)
+        add("M%d" % M, var, ref_, 0.003, range(9) if M == 1 else (0, 4, 8))
+    add("K2", np.array([[40, 10], [5, 30]]), np.array([[160, 190], [195, 170]]), 0.003, range(2))
+    add("K1", np.array([[22, 31]]), np.array([[178, 169]]), 0.003, range(1))
+    add("allzero", np.zeros((3, 2), dtype=np.int64), np.zeros((3, 2), dtype=np.int64), 0.003, range(9))
+    dump("tree_scores_edges.json", cases)
+
+
 # ------------------------------------------------------------- 2. vector operators
 def gen_vectors():
     rng = np.random.default_rng(7)
@@ -355,4 +392,6 @@ if __name__ == "__main__":
         gen_scores_highk()
     if "search_big" in which:
         gen_search_big()
+    if "edges" in which:
+        gen_scores_edges()
     print("done in %.1fs" % (time.time() - t0))

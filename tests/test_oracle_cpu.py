@@ -186,3 +186,25 @@ def test_search_path_on_bamse_dat_and_k5():
             assert o.full_score(k["tree"]) == pytest.approx(k["score"] + math.log(k["scre"]), rel=1e-12)
             assert o.full_score(k["tree"]) >= thr - 1e-9 * abs(thr)
             assert o.total_score(k["tree"]) == pytest.approx(k["totalscore"], rel=1e-12)
+
+
+def test_tree_scores_at_the_edges_of_the_domain_match_reference():
+    """round 2: reference-produced scores for the inputs of tests/test_gpu_edges.py (tests/golden/
+    tree_scores_edges.json): zero variant / reference / total reads, e = 1e-6 and 0.499, M = 1 and 64, K = 1, 2,
+    all counts zero.  reference == oracle here, oracle == CUDA there."""
+    from conftest import load_golden
+    cases = load_golden("tree_scores_edges.json")
+    assert len(cases) >= 120
+    seen = set()
+    for case in cases:
+        seen.add(case["id"].split("-")[0])
+        As = np.array(case["var"])
+        Bs = np.array(case["ref"])
+        K, M = As.shape
+        assert np.all(np.isfinite(case["per_sample"]))
+        D = np.array([[orc.distrib(As[k, m], Bs[k, m], case["err"]) for m in range(M)] for k in range(K)])
+        s = orc.tree_score_samples(case["tree"], D, orc.prior_const(K))
+        np.testing.assert_allclose(s, case["per_sample"], rtol=1e-12, atol=1e-12, err_msg=case["id"])
+        assert orc.canon_weight(case["tree"])[1] == case["scre"]
+        assert orc.decode_tree(K, case["tree_index"]) == case["tree"]
+    assert {"zero", "err1e", "err0.499", "M1", "M64", "K2", "K1", "allzero"} <= seen
