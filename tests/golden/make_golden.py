@@ -96,6 +96,36 @@ def gen_scores():
     dump("tree_scores.json", cases)
 
 
+def gen_scores_configs():
+    """round 2: reference-produced scores at the SHAPES of BASELINE.json's configurations -- the aggregated tables
+    of the largest clustering of each of bench.py's workloads c1 .. c5 (K = 4 / 6 / 7 / 10 / 5 clusters, M = 3 /
+    10 / 20 / 5 / 10 samples; c5 at the first and the last error rate of its sweep), the chain, the star and three
+    random labeled rooted trees each."""
+    sys.path.insert(0, ROOT)
+    import bamse_oracle as orc
+    from bamse_b200 import workloads
+    cases = []
+    for name in ("c1", "c2", "c3", "c4", "c5"):
+        work = workloads.build(name)
+        c = max(work["clusts"], key=lambda x: x.As.shape[0])
+        As, Bs = np.array(c.As), np.array(c.Bs)
+        K = As.shape[0]
+        rng = np.random.default_rng(abs(hash(name)) % 1000 if False else {"c1": 1, "c2": 2, "c3": 3, "c4": 4, "c5": 5}[name])
+        trees = [[-1] + list(range(K - 1)), [-1] + [0] * (K - 1)] + \
+                [orc.decode_tree(K, int(rng.integers(0, K ** (K - 1)))) for _ in range(3)]
+        errs = [work["errs"][0]] if len(work["errs"]) == 1 else [work["errs"][0], work["errs"][-1]]
+        for e in errs:
+            D, P = ref_tables(As, Bs, e, K)
+            for j, tree in enumerate(trees):
+                t0 = time.time()
+                sc = cl.tree_integrate_multisample(tree, D, P)
+                cases.append(dict(id="%s-e%g-t%d" % (name, e, j), config=name, var=As.tolist(), ref=Bs.tolist(), err=float(e),
+                                  K_prior=K, tree=tree, nodes=list(range(K)), per_sample=[float(x) for x in sc],
+                                  total=float(np.sum(sc)), scre=int(tt.canonizeF(tree)['scre'])))
+                print(cases[-1]["id"], K, As.shape[1], "%.1fs" % (time.time() - t0), cases[-1]["total"])
+    dump("tree_scores_configs.json", cases)
+
+
 def gen_scores_edges():
     """round 2: the inputs of tests/test_gpu_edges.py through the UNMODIFIED reference -- clusters without variant
     reads / without any reads / without reference reads (all 64 trees), error rates 1e-6 and 0.499, one sample
@@ -394,4 +424,6 @@ if __name__ == "__main__":
         gen_search_big()
     if "edges" in which:
         gen_scores_edges()
+    if "configs" in which:
+        gen_scores_configs()
     print("done in %.1fs" % (time.time() - t0))

@@ -311,6 +311,13 @@ def test_workloads_are_reproducible():
     c2 = workloads.build("c2")
     assert c2["n_evals_per_param"] == 397530 and len(c2["clusts"]) == 79 and c2["M"] == 10
     assert len(workloads.CONFIGS["c5"]["errs"]) == 64
+    # the reference-produced goldens at the configurations' shapes (tests/golden/tree_scores_configs.json) were
+    # taken on exactly these tables: the largest clustering of the work list
+    from conftest import load_golden
+    gold = {c["config"]: c for c in load_golden("tree_scores_configs.json")}
+    for name, work in (("c1", a), ("c2", c2)):
+        big = max(work["clusts"], key=lambda x: x.As.shape[0])
+        assert np.array_equal(np.array(gold[name]["var"]), big.As) and np.array_equal(np.array(gold[name]["ref"]), big.Bs)
 
 
 def test_algorithmic_op_count_uses_the_mean_leaf_count():

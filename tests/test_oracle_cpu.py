@@ -208,3 +208,25 @@ def test_tree_scores_at_the_edges_of_the_domain_match_reference():
         assert orc.canon_weight(case["tree"])[1] == case["scre"]
         assert orc.decode_tree(K, case["tree_index"]) == case["tree"]
     assert {"zero", "err1e", "err0.499", "M1", "M64", "K2", "K1", "allzero"} <= seen
+
+
+def test_tree_scores_at_the_shapes_of_the_baseline_configs_match_reference():
+    """round 2: reference-produced scores on the aggregated tables of the largest clustering of each bench.py
+    workload c1 .. c5 (K = 4 / 6 / 7 / 10 / 5, M = 3 / 10 / 20 / 5 / 10; c5 at both ends of its error-rate sweep):
+    chain, star and three random trees each (tests/golden/tree_scores_configs.json)."""
+    from conftest import load_golden
+    cases = load_golden("tree_scores_configs.json")
+    assert {c["config"] for c in cases} == {"c1", "c2", "c3", "c4", "c5"} and len(cases) == 30
+    shapes = {c["config"]: np.array(c["var"]).shape for c in cases}
+    assert shapes == {"c1": (4, 3), "c2": (6, 10), "c3": (7, 20), "c4": (10, 5), "c5": (5, 10)}
+    tables = {}
+    for case in cases:
+        As, Bs = np.array(case["var"]), np.array(case["ref"])
+        K, M = As.shape
+        key = (case["config"], case["err"])
+        if key not in tables:
+            tables[key] = np.array([[orc.distrib(As[k, m], Bs[k, m], case["err"]) for m in range(M)] for k in range(K)])
+        s = orc.tree_score_samples(case["tree"], tables[key], orc.prior_const(K))
+        np.testing.assert_allclose(s, case["per_sample"], rtol=1e-12, atol=0, err_msg=case["id"])
+        assert float(np.sum(s)) == pytest.approx(case["total"], rel=1e-13)
+        assert orc.canon_weight(case["tree"])[1] == case["scre"]
