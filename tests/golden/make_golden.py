@@ -96,6 +96,33 @@ def gen_scores():
     dump("tree_scores.json", cases)
 
 
+def gen_simdata():
+    """round 2: the reference's own synthetic generator (simdata.py:18-31, imported unmodified with matplotlib /
+    seaborn stubbed out -- they are only used by its plotting helpers) at the (K_true, M, N, seed) of the five
+    bench workloads and two more: the topology list handed in, the tree drawn, and digests of assign / As / Bs."""
+    import hashlib
+    import pickle
+    import types
+    for name in ("matplotlib", "matplotlib.pyplot", "seaborn"):
+        sys.modules.setdefault(name, types.ModuleType(name))
+    sys.path.insert(0, "/root/reference")
+    import simdata as rsim
+    with open("/root/reference/AllTrees.txt", "rb") as f:
+        T, S = pickle.load(f, encoding="latin1")
+    digest = lambda a: hashlib.sha256(np.ascontiguousarray(a, dtype=np.int64).tobytes()).hexdigest()
+    cases = []
+    for K, M, N, seed, cov, err in [(4, 3, 50, 12345, 200, 0.003), (6, 10, 500, 2, 200, 0.003), (7, 20, 2000, 3, 200, 0.003),
+                                    (9, 5, 1000, 4, 200, 0.003), (5, 10, 500, 5, 200, 0.003), (3, 2, 40, 77, 10000, 0.001),
+                                    (8, 4, 300, 8, 60, 0.01)]:
+        np.random.seed(seed)
+        d = rsim.sim_data_readcounts(K, M, T, N, coverage=cov, error=err)
+        cases.append(dict(K=K, M=M, N=N, seed=seed, coverage=cov, error=err,
+                          topologies=[[int(x) for x in t] for t in T[K]], tree=[int(x) for x in d["tree"]],
+                          assign=digest(d["assign"]), As=digest(d["As"]), Bs=digest(d["Bs"]),
+                          As_head=np.asarray(d["As"])[:3].tolist(), vaf_sum=float(np.sum(d["vaf"]))))
+    dump("simdata.json", cases)
+
+
 def gen_scores_configs():
     """round 2: reference-produced scores at the SHAPES of BASELINE.json's configurations -- the aggregated tables
     of the largest clustering of each of bench.py's workloads c1 .. c5 (K = 4 / 6 / 7 / 10 / 5 clusters, M = 3 /
@@ -426,4 +453,6 @@ if __name__ == "__main__":
         gen_scores_edges()
     if "configs" in which:
         gen_scores_configs()
+    if "simdata" in which:
+        gen_simdata()
     print("done in %.1fs" % (time.time() - t0))

@@ -378,3 +378,25 @@ def test_the_binding_printed_in_integration_md_matches_the_library(built_library
         with pytest.raises(RuntimeError) as e:
             ns["Scorer"](0)
         assert "no CPU fallback" in str(e.value)
+
+
+def test_synthetic_generator_draws_what_the_reference_draws():
+    """bamse_b200/simdata.py against tests/golden/simdata.json = the reference's own sim_data_readcounts
+    (simdata.py:18-31) at the (K_true, M, N, seed) of the bench workloads: given the same topology list the
+    same tree is drawn and assign / As / Bs are identical (digests), i.e. the legacy global RNG is consumed in
+    the same order."""
+    import hashlib
+    from conftest import load_golden
+    from bamse_b200 import simdata
+    digest = lambda a: hashlib.sha256(np.ascontiguousarray(a, dtype=np.int64).tobytes()).hexdigest()
+    cases = load_golden("simdata.json")
+    assert len(cases) == 7
+    for g in cases:
+        np.random.seed(g["seed"])
+        d = simdata.sim_data_readcounts(g["K"], g["M"], {g["K"]: g["topologies"]}, g["N"], coverage=g["coverage"], error=g["error"])
+        assert [int(x) for x in d["tree"]] == g["tree"]
+        assert digest(d["assign"]) == g["assign"] and digest(d["As"]) == g["As"] and digest(d["Bs"]) == g["Bs"]
+        assert d["As"][:3].tolist() == g["As_head"] and float(np.sum(d["vaf"])) == pytest.approx(g["vaf_sum"], rel=1e-13)
+        # the same SET of topologies as our own enumerator (AllTrees.txt is not shipped)
+        from bamse_b200.tree_tools import unlabeled_rooted_trees
+        assert len(unlabeled_rooted_trees(g["K"])) == len(g["topologies"])
