@@ -96,6 +96,51 @@ def gen_scores():
     dump("tree_scores.json", cases)
 
 
+def gen_candidates():
+    """round 2: the reference's candidate generation -- `unique_Kmeans_clustering` (bamse.py:18-27) and the model
+    selection loop (bamse.py:75-90), taken from the reference's bamse.py AS SOURCE TEXT (the file is a script, not a
+    module) and executed here against the reference's own clustering / tree_tools -- on bamse.dat and on the
+    config-1 simdata input, with numpy's global RNG seeded (sklearn's random_state=None draws from it)."""
+    import ast
+    import contextlib
+    import io
+    import pandas as pd
+    from sklearn.cluster import KMeans
+    src = open("/root/reference/bamse.py").read()
+    lines = src.split("\n")
+    fn = [n for n in ast.parse(src).body if isinstance(n, ast.FunctionDef) and n.name == "unique_Kmeans_clustering"][0]
+    fn_src = "\n".join(lines[fn.lineno - 1:fn.end_lineno])
+    first = next(i for i, l in enumerate(lines) if l.startswith("clusterings = []"))
+    last = next(i for i, l in enumerate(lines) if "clusts += list(unique_Kmeans_clustering" in l)
+    loop_src = "\n".join(lines[first:last + 1])
+    assert first + 1 == 74 and last + 1 == 90, (first, last)
+    table = pd.read_table("/root/reference/bamse.dat")
+    names = sorted({c[:-4] for c in table.columns if c.endswith(".var")})
+    dat = (table[[x + ".var" for x in names]].values, table[[x + ".ref" for x in names]].values)
+    sys.path.insert(0, ROOT)
+    from bamse_b200 import simdata as our_sim          # pinned to the reference's generator by simdata.json
+    d = our_sim.simulate(4, 3, 50, 12345)
+    cases = []
+    for tag, (As, Bs), max_clusts, n_trees, err, seed in [("bamse.dat", dat, 6, 10, 0.001, 11), ("bamse.dat-nc4", dat, 4, 5, 0.003, 12),
+                                                          ("c1", (d["As"], d["Bs"]), 5, 10, 0.001, 13346)]:
+        ns = dict(np=np, KMeans=KMeans, clustering=cl.clustering, reorder_assignmens=tt.reorder_assignmens)
+        exec(compile(fn_src, "bamse.py", "exec"), ns)
+        max_clusts = min(len(As), max_clusts)
+        pf = cl.part_func(len(As), max_clusts)
+        ns.update(X={"As": As, "Bs": Bs}, max_clusts=max_clusts, pf=pf, err=err, n_trees=n_trees)
+        np.random.seed(seed)
+        with contextlib.redirect_stdout(io.StringIO()):
+            exec(compile(loop_src, "bamse.py", "exec"), ns)
+        cases.append(dict(id=tag, var=np.asarray(As).tolist(), ref=np.asarray(Bs).tolist(), max_clusts=int(max_clusts), n_trees=n_trees,
+                          err=err, seed=seed, pf=[float(x) for x in pf], raw_scores=[float(x) for x in ns["raw_scores"]],
+                          candidate_numbers=[int(x) for x in ns["candidate_numbers"]],
+                          assignments=[[int(a) for a in c.assign] for c in ns["clusts"]],
+                          cluster_prior=[float(c.cluster_prior) for c in ns["clusts"]],
+                          maxlikelihood=[float(c.maxlikelihood) for c in ns["clusts"]]))
+        print(tag, cases[-1]["candidate_numbers"], len(cases[-1]["assignments"]))
+    dump("candidates.json", cases)
+
+
 def gen_simdata():
     """round 2: the reference's own synthetic generator (simdata.py:18-31, imported unmodified with matplotlib /
     seaborn stubbed out -- they are only used by its plotting helpers) at the (K_true, M, N, seed) of the five
@@ -455,4 +500,6 @@ if __name__ == "__main__":
         gen_scores_configs()
     if "simdata" in which:
         gen_simdata()
+    if "candidates" in which:
+        gen_candidates()
     print("done in %.1fs" % (time.time() - t0))

@@ -400,3 +400,23 @@ def test_synthetic_generator_draws_what_the_reference_draws():
         # the same SET of topologies as our own enumerator (AllTrees.txt is not shipped)
         from bamse_b200.tree_tools import unlabeled_rooted_trees
         assert len(unlabeled_rooted_trees(g["K"])) == len(g["topologies"])
+
+
+def test_candidate_generation_follows_the_reference_script():
+    """workloads.candidate_clusterings / unique_Kmeans_clustering against tests/golden/candidates.json = the
+    reference's own bamse.py:18-27 and :74-90 executed on bamse.dat and on the config-1 input with numpy's global
+    RNG seeded: same partition-function row, same clusterings in the same order (i.e. the same RNG draws, the
+    same use of the argsort indices as cluster counts), same prior / maxlikelihood constants."""
+    from conftest import load_golden
+    from bamse_b200 import workloads
+    cases = load_golden("candidates.json")
+    assert [c["id"] for c in cases] == ["bamse.dat", "bamse.dat-nc4", "c1"]
+    for g in cases:
+        As, Bs = np.array(g["var"]), np.array(g["ref"])
+        np.random.seed(g["seed"])
+        clusts, pf = workloads.candidate_clusterings(As, Bs, g["max_clusts"], g["n_trees"], g["err"])
+        np.testing.assert_allclose(pf, g["pf"], rtol=0, atol=0)
+        assert [[int(a) for a in c.assign] for c in clusts] == g["assignments"], g["id"]
+        np.testing.assert_allclose([c.cluster_prior for c in clusts], g["cluster_prior"], rtol=1e-13)
+        np.testing.assert_allclose([c.maxlikelihood for c in clusts], g["maxlikelihood"], rtol=1e-13)
+        assert sorted({int(c.As.shape[0]) for c in clusts}) == sorted({k for k in g["candidate_numbers"] if k >= 1})
