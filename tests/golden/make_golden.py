@@ -96,6 +96,31 @@ def gen_scores():
     dump("tree_scores.json", cases)
 
 
+def gen_remove_zeros():
+    """round 2: tree_tools.remove_zeros (tree_tools.py:159-175, with collapse_node / collapse_assign) of the unmodified
+    reference on random trees with random empty clones (numpy-array trees, as bamse.py hands them over): the tree,
+    the assignment and the clone proportions after collapsing every empty single-child node."""
+    import copy
+    rng = np.random.default_rng(159)
+    cases = []
+    for K in (2, 3, 4, 5, 6, 7, 8):
+        for rep in range(8):
+            tree = np.array(random_tree(rng, K))
+            props = rng.uniform(0.05, 0.4, size=(K, 3))
+            empty = [int(x) for x in np.nonzero(rng.uniform(size=K) < 0.4)[0]]
+            for n in empty:
+                props[n] = rng.choice([0.0, 0.0002], size=3)
+            assign = rng.integers(0, K, size=3 * K)
+            t = {"tree": tree.copy(), "assign": assign.copy(), "clone_proportions": props.copy()}
+            out = tt.remove_zeros(copy.deepcopy(t))
+            cases.append(dict(tree_in=tree.tolist(), assign_in=assign.tolist(), props_in=props.tolist(), empty=empty,
+                              tree_out=[int(x) for x in out["tree"]], assign_out=[int(x) for x in out["assign"]],
+                              props_out=np.asarray(out["clone_proportions"]).tolist(),
+                              Bmatrix=np.asarray(out["Bmatrix"]).tolist()))
+    print(sum(1 for c in cases if len(c["tree_out"]) < len(c["tree_in"])), "of", len(cases), "cases collapse something")
+    dump("remove_zeros.json", cases)
+
+
 def gen_candidates():
     """round 2: the reference's candidate generation -- `unique_Kmeans_clustering` (bamse.py:18-27) and the model
     selection loop (bamse.py:75-90), taken from the reference's bamse.py AS SOURCE TEXT (the file is a script, not a
@@ -502,4 +527,6 @@ if __name__ == "__main__":
         gen_simdata()
     if "candidates" in which:
         gen_candidates()
+    if "remove_zeros" in which:
+        gen_remove_zeros()
     print("done in %.1fs" % (time.time() - t0))

@@ -420,3 +420,20 @@ def test_candidate_generation_follows_the_reference_script():
         np.testing.assert_allclose([c.cluster_prior for c in clusts], g["cluster_prior"], rtol=1e-13)
         np.testing.assert_allclose([c.maxlikelihood for c in clusts], g["maxlikelihood"], rtol=1e-13)
         assert sorted({int(c.As.shape[0]) for c in clusts}) == sorted({k for k in g["candidate_numbers"] if k >= 1})
+
+
+def test_remove_zeros_against_reference_golden():
+    """tree_tools.remove_zeros against tests/golden/remove_zeros.json = the reference's own remove_zeros
+    (tree_tools.py:159-175) on 56 random trees with random empty clones, 19 of which collapse at least one node
+    (chains of empty nodes, an empty root with one child, empty leaves and empty branching nodes that must stay)."""
+    from conftest import load_golden
+    cases = load_golden("remove_zeros.json")
+    assert len(cases) == 56 and sum(1 for c in cases if len(c["tree_out"]) < len(c["tree_in"])) >= 15
+    for c in cases:
+        t = {"tree": np.array(c["tree_in"]), "assign": np.array(c["assign_in"]), "clone_proportions": np.array(c["props_in"])}
+        out = tree_tools.remove_zeros(t)
+        assert [int(x) for x in out["tree"]] == c["tree_out"], c
+        assert [int(x) for x in out["assign"]] == c["assign_out"], c
+        np.testing.assert_array_equal(np.asarray(out["clone_proportions"]), np.array(c["props_out"]))
+        np.testing.assert_array_equal(np.asarray(out["Bmatrix"]), np.array(c["Bmatrix"]))
+        np.testing.assert_allclose(np.asarray(out["Amatrix"]).dot(np.array(c["Bmatrix"])), np.eye(len(c["tree_out"])), atol=1e-12)
