@@ -500,6 +500,45 @@ def gen_outputs():
     dump("out_spec.json", spec)
 
 
+def gen_outputs_more():
+    """round 2: the reference's writers on a spread of tree dicts (K = 1 .. 8 clones, 1 .. 6 samples, random trees with
+    any root, absent subclones, the colour lists of bamse.py:59-61) -> tests/golden/outputs_more.json holds the three
+    files of every case.  asciitree's drawer is ours, as in gen_outputs."""
+    import tempfile
+    sys.path.insert(0, ROOT)
+    from bamse_b200.tree_io import LeftAligned
+    ref.tree_io.LeftAligned = LeftAligned
+    cluster_colors = ["plum", "lightyellow", "palegreen", "pink", "paleturquoise", "tan", "moccasin", "lightcyan3", "oldlace",
+                      "palevioletred", "olivedrab1", "lightgray", "steelblue1"]
+    sample_colors = ["red", "firebrick4", "brown4", "darkgoldenrod4", "deeppink1", "darkgreen", "cyan4", "darkorchid", "blue", "dimgray"]
+    rng = np.random.default_rng(77)
+    cases, failed = [], []
+    for K, M in [(1, 1), (1, 3), (2, 2), (3, 1), (3, 4), (4, 2), (4, 6), (5, 3), (5, 5), (6, 2), (7, 3), (7, 6), (8, 4), (8, 1)]:
+        tree = random_tree(rng, K)
+        B = tt.get_matrix(tree)[0]
+        sm = rng.dirichlet(np.ones(K + 1), size=M)[:, :K].T
+        if K >= 3:
+            sm[int(rng.integers(0, K)), :] = 0.0
+        if K >= 5:
+            sm[int(rng.integers(0, K)), int(rng.integers(0, M))] = 0.0
+        spec = dict(tree=tree, root=tree.index(-1), assign=[int(x) for x in rng.integers(0, K, 10 * K)], vaf=B.dot(sm).tolist(),
+                    clone_proportions=sm.tolist(), totalscore=float(-rng.uniform(10, 1e5)),
+                    sample_names=["S%d" % (i + 1) for i in range(M)], sample_colors=sample_colors, cluster_colors=cluster_colors)
+        t = dict(tree=np.array(spec["tree"]), root=spec["root"], assign=np.array(spec["assign"]), vaf=np.array(spec["vaf"]),
+                 clone_proportions=np.array(spec["clone_proportions"]), totalscore=spec["totalscore"], sample_names=spec["sample_names"])
+        with tempfile.TemporaryDirectory() as d:
+            a, b, c = (os.path.join(d, n) for n in ("t.dot", "s.dot", "o.txt"))
+            try:
+                ref.tree_io.write_dot_files(t, sample_colors, cluster_colors, a, b)
+                ref.tree_io.write_text_output([t], c)
+            except Exception as e:
+                failed.append((K, M, repr(e)))
+                continue
+            cases.append(dict(spec=spec, subclones=open(a).read(), samples=open(b).read(), text=open(c).read()))
+    print(len(cases), "cases;", "the reference itself raised on:", failed)
+    dump("outputs_more.json", cases)
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["scores", "vectors", "canon", "constants", "search", "outputs"]
     t0 = time.time()
@@ -529,4 +568,6 @@ if __name__ == "__main__":
         gen_candidates()
     if "remove_zeros" in which:
         gen_remove_zeros()
+    if "outputs_more" in which:
+        gen_outputs_more()
     print("done in %.1fs" % (time.time() - t0))

@@ -437,3 +437,24 @@ def test_remove_zeros_against_reference_golden():
         np.testing.assert_array_equal(np.asarray(out["clone_proportions"]), np.array(c["props_out"]))
         np.testing.assert_array_equal(np.asarray(out["Bmatrix"]), np.array(c["Bmatrix"]))
         np.testing.assert_allclose(np.asarray(out["Amatrix"]).dot(np.array(c["Bmatrix"])), np.eye(len(c["tree_out"])), atol=1e-12)
+
+
+def test_writers_are_byte_compatible_on_a_spread_of_trees(tmp_path):
+    """tests/golden/outputs_more.json: the reference's own write_dot_files / write_text_output on 14 tree dicts
+    (K = 1 .. 8 clones, 1 .. 6 samples, any root, absent subclones); ours writes the same bytes."""
+    from conftest import load_golden
+    from bamse_b200 import tree_io
+    cases = load_golden("outputs_more.json")
+    assert len(cases) == 14
+    for i, g in enumerate(cases):
+        spec = g["spec"]
+        tree = dict(tree=np.array(spec["tree"]), root=spec["root"], assign=np.array(spec["assign"]),
+                    vaf=np.array(spec["vaf"]), clone_proportions=np.array(spec["clone_proportions"]),
+                    totalscore=spec["totalscore"], sample_names=spec["sample_names"])
+        a, b, c = (str(tmp_path / ("%d_%s" % (i, n))) for n in ("t.dot", "s.dot", "o.txt"))
+        tree_io.write_dot_files(tree, spec["sample_colors"], spec["cluster_colors"], a, b)
+        tree_io.write_text_output([tree], c)
+        K, M = len(spec["tree"]), len(spec["sample_names"])
+        assert open(a).read() == g["subclones"], (K, M)
+        assert open(b).read() == g["samples"], (K, M)
+        assert open(c).read() == g["text"], (K, M)
