@@ -2,7 +2,9 @@
 (imported from /root/reference through oracle/ref_shim.py).  Run in the build
 container only (the GPU box has no /root/reference):
 
-    python tests/golden/make_golden.py
+    python tests/golden/make_golden.py                      # scores vectors canon constants search outputs
+    python tests/golden/make_golden.py highk search_big     # round 2: K = 8..12, bamse.dat / K = 5 search (minutes)
+    python tests/golden/make_golden.py edges configs simdata candidates remove_zeros outputs_more
 
 Everything is seeded; re-running reproduces the committed files bit for bit
 (up to json float repr, which round-trips fp64 exactly).
