@@ -188,3 +188,26 @@ def test_default_geometry_is_consistent(built_library):
     for K in range(1, 13):
         s, r, nf, nt = pair_geometry(lib, K)
         assert r == 0 or (s + r >= K and r - 1 <= s)
+
+
+@pytest.mark.parametrize("K,s,r,ctx_used,ctx_full,irregular", [(5, 3, 3, 85, 315, 0), (5, 3, 2, 45, 45, 60), (6, 3, 4, 846, 4446, 0),
+                                                               (6, 3, 3, 606, 606, 360), (7, 4, 4, 2821, 9996, 0),
+                                                               (7, 4, 3, 1036, 1036, 13230), (8, 4, 5, 40552, 194552, 0),
+                                                               (8, 4, 4, 19552, 19552, 166320)])
+def test_host_cut_of_every_tree_reproduces_the_gpu_counts(built_library, K, s, r, ctx_used, ctx_full, irregular):
+    """profiles/r02_pair_geometry.txt was counted on the GPU by cutting ALL K^(K-1) trees (k_build_pair_table); the
+    host instance of the same code (decode_tree + classify_tree) over all trees gives the same number of irregular
+    trees and of context rows in use -- host and device agree on the cut of every tree.  (K = 9 and K = 10 by
+    profiles/host_cut_stats.py: profiles/r02_host_cut_stats.txt.)"""
+    import importlib.util
+    import os
+    here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("host_cut_stats", os.path.join(here, "profiles", "host_cut_stats.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    got = mod.stats(K, s, r)
+    assert (got["context_rows_used"], got["context_rows_full"], got["irregular"]) == (ctx_used, ctx_full, irregular)
+    line = "K=%2d s=%d r=%d  trees %11d  inside rows %8d  context rows %9d of %9d  irregular %10d" % (
+        K, s, r, K ** (K - 1), got["inside_rows"], ctx_used, ctx_full, irregular)
+    with open(os.path.join(here, "profiles", "r02_pair_geometry.txt")) as f:
+        assert any(l.startswith(line) for l in f), line
