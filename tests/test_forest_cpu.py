@@ -255,3 +255,23 @@ def test_programs_of_the_smallest_geometries_reproduce_the_oracle(built_library,
         want = orc.tree_score_samples(t, D[:, None, :], p0)[0]
         assert tab.run(prog) == pytest.approx(want, rel=1e-9), (K, s, sh, t, prog)
         assert prog["scre"] == orc.canon_weight(t)[1] and prog["max_sp"] <= slots
+
+
+@pytest.mark.parametrize("K", [2, 3, 4, 5, 6, 7])
+def test_host_canon_weight_of_every_tree(built_library, K):
+    """the canonizeF weight the device code carries (`scre` of the program built by the host instance of
+    build_program_forest) equals the oracle's canon_weight for EVERY labeled rooted tree of K <= 7 clusters
+    (117 649 at K = 7: the cluster counts of BASELINE configs 2 and 3) -- integer parity, no sampling."""
+    lib = cuda_shim.load_library()
+    s, sh, nf, nfh, slots = geometry(lib, K)
+    out = np.zeros(46, dtype=np.int32)
+    po = out.ctypes.data_as(ctypes.c_void_p)
+    hist = {}
+    for i in range(K ** (K - 1)):
+        tree = orc.decode_tree(K, i)
+        par = np.asarray(tree, dtype=np.int8)
+        assert lib.bamse_debug_program(K, par.ctypes.data_as(ctypes.c_void_p), None, K, s, sh, po) == 0
+        w = orc.canon_weight(tree)[1]
+        assert int(out[4]) == w, (K, i, tree)
+        hist[w] = hist.get(w, 0) + 1
+    assert sum(hist.values()) == K ** (K - 1) and hist.get(1, 0) > 0
