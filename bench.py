@@ -2,7 +2,13 @@
 """bench.py -- tree-likelihood evals/sec of the BAMSE hot path on B200 (contract in the task
 statement, section 4 of the tier framing).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--config c2] [--impl ours|reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--config c3] [--impl ours|reference]
+
+Default workload: BASELINE.json configs[2] (c3: 20 samples, 2000 mutations, -nc 8 -n 100), the configuration
+the baseline quotes for 1/2/4/8 B200 and the largest one whose every leg (resident, enumeration-only, early-exit,
+end to end, CPU sample) fits a few minutes; the same workload at every N, so the per-N values are one strong-scaling
+curve.  `--config c2` is the round-1 default (a 4 ms step since the pair path: launch-bound beyond 2 GPUs);
+lines of every configuration from one build are in profiles/scale/.
 
 One "step" = one pass of the hot path over the configuration's whole work list: every labeled
 rooted tree (K^(K-1)) of every candidate clustering (x every (e,s) pair for c5), thresholded
@@ -287,12 +293,15 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--config", default="c2", choices=["c1", "c2", "c3", "c4", "c5"])
+    ap.add_argument("--config", default="c3", choices=["c1", "c2", "c3", "c4", "c5"])
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="fp32", choices=["fp32", "fp64"])
     ap.add_argument("--topk", type=int, default=5)
     ap.add_argument("--ref-items", type=int, default=16, help="work items per step of the reference arm")
-    ap.add_argument("--cpu-items", type=int, default=200, help="sample size of the cpu_baseline leg (SURVEY 8d: >= 200 items; ~30 s on 16 cores)")
+    ap.add_argument("--cpu-items", type=int, default=0,
+                    help="sample size of the cpu_baseline leg; default: 200 items (SURVEY 8d) where an item costs a few "
+                         "core-seconds (c1, c2, c5), 96 on c3 (~14 core-seconds per item: 20 samples, 7 clusters), 32 on c4 "
+                         "-- about a minute of wall time on 16 cores")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--search-only", action="store_true",
                     help="not a bench line: run ONE pass of the early-exit search (for configurations whose full\n"
@@ -304,6 +313,8 @@ def main():
                     help="debug: one GPU scores only shard 0 of W (what each rank of a W-GPU run does)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
+    if args.cpu_items <= 0:
+        args.cpu_items = {"c3": 96, "c4": 32}.get(args.config, 200)
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -489,6 +500,11 @@ def main():
     step_resident()
     barrier()
     stats = ctx.kernel_stats(reset=True)
+    # ... and of the enumeration alone (one more untimed step over the tables just built): the difference is the
+    #     table builders' share, so each kernel group gets its own executed XU-pipe fraction
+    step_resident(tables=False)
+    barrier()
+    stats_enum = ctx.kernel_stats(reset=True)
     ctx.set_option(cuda_shim.OPT_STATS, 0)
     ctx.kernel_time(reset=True)
     ctx.table_time(reset=True)
@@ -606,7 +622,17 @@ def main():
             bound, achieved, peak, unit = "xu (MUFU ex2/lg2)", xu / kernel_s / 1e12, peaks["xu_tops"], "Tops/s"
             kname = "table builders (k_forest_level, k_ctx_level) + k_enumerate_pairs / k_enumerate_fast"
             ex = stats["mufu_ops"] / kernel_s / 1e12     # this rank's executed MUFU ops of one step per second
-            executed = {"xu_tops": ex, "xu_pipe_frac": ex / peaks["xu_tops"],
+            mufu_enum = min(stats_enum["mufu_ops"], stats["mufu_ops"])
+            mufu_tab = stats["mufu_ops"] - mufu_enum
+            groups = {
+                "table_builders": {"kernels": "k_tables_fast, k_forest_level, k_ctx_level", "ms_per_step": tab_ms_max,
+                                   "mufu_ops_per_step": mufu_tab, "share_of_kernel_time": tab_ms_max / (1e3 * kernel_s),
+                                   "xu_pipe_frac": (mufu_tab / (tab_ms_max / 1e3) / 1e12 / peaks["xu_tops"]) if tab_ms_max > 0 else None},
+                "enumeration": {"kernels": "k_enumerate_pairs, k_enumerate_fast", "ms_per_step": kern_ms_max,
+                                "mufu_ops_per_step": mufu_enum, "share_of_kernel_time": kern_ms_max / (1e3 * kernel_s),
+                                "xu_pipe_frac": (mufu_enum / (kern_ms_max / 1e3) / 1e12 / peaks["xu_tops"]) if kern_ms_max > 0 else None,
+                                "bound": "L1 wavefronts of the windowed table reads (profiles/r02_k_enumerate_pairs_*.txt), not the XU pipe"}}
+            executed = {"xu_tops": ex, "xu_pipe_frac": ex / peaks["xu_tops"], "by_kernel_group": groups,
                         "mufu_ops_per_step": stats["mufu_ops"], "convolutions_per_step": stats["convs"],
                         "conv_terms_executed_per_step": stats["conv_terms"],
                         "conv_terms_algorithmic_per_step": terms,
@@ -618,19 +644,24 @@ def main():
                                 "of what actually executed (table builders + enumeration kernels, event-timed)"}
         # DRAM traffic of the step's table-building kernels (1 launch of each per step), from the committed
         # ncu --set full capture of this configuration (profiles/r02_traffic.json); null for other configurations
-        traffic, traffic_detail = None, None
-        try:
-            with open(os.path.join(ROOT, "profiles", "r02_traffic.json")) as f:
-                tj = json.load(f)
+        traffic, traffic_detail, traffic_s = None, None, kernel_s
+        for tname in ("r02_traffic_%s.json" % args.config, "r02_traffic.json"):
+            try:
+                with open(os.path.join(ROOT, "profiles", tname)) as f:
+                    tj = json.load(f)
+            except Exception:
+                continue
             if args.config == tj.get("config") and world == tj.get("n_gpus", 1) and args.precision == "fp32":
                 traffic = int(tj["dram_bytes_read"] + tj["dram_bytes_write"])
-                traffic_detail = {"dominant_kernel": tj["dominant_kernel"], "per_kernel": tj["kernels"], "source": tj["source"]}
-        except Exception:
-            pass
+                traffic_detail = {"dominant_kernel": tj["dominant_kernel"], "per_kernel": tj["kernels"], "source": tj["source"],
+                                  "scope": tj.get("scope", "every kernel of one step")}
+                if tj.get("kernel_time") == "table_build" and tab_ms_max > 0:
+                    traffic_s = tab_ms_max / 1e3       # the capture covers the table builders only
+                break
         roofline = {"bound": bound, "achieved": achieved, "peak": peak, "unit": unit, "frac": achieved / peak,
                     "traffic": traffic, "peak_source": peaks["source"], "kernel": kname,
                     "kernel_ms_per_launch": 1e3 * kernel_s, "executed": executed,
-                    "hbm": hbm_evidence(int(h2d), traffic, kernel_s), "traffic_detail": traffic_detail}
+                    "hbm": hbm_evidence(int(h2d), traffic, traffic_s), "traffic_detail": traffic_detail}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "f32" if prec == cuda_shim.FP32 else "f64",

@@ -5,6 +5,7 @@ import ctypes
 import math
 import os
 import re
+import sys
 
 import numpy as np
 import pytest
@@ -358,6 +359,46 @@ def test_committed_bench_lines_follow_the_contract():
         assert set(("bound", "achieved", "peak", "unit", "frac", "traffic")) <= set(d["roofline"])
         assert d["gpu_launches"] > 0 and d["value"] > 0 and d["e2e"]["value"] > 0
         assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+
+
+def test_bench_script_executes_end_to_end_with_stand_ins(built_library):
+    """bench.py's own arm, every leg, on stand-ins for the CUDA runtime and the library context (tests/bench_dryrun.py):
+    the driver-facing script parses its arguments, runs its legs in order and assembles a line with every key of the
+    contract.  Shape only -- the numbers of a dry run mean nothing."""
+    import json
+    import subprocess
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "bench_dryrun.py"), "--config", "c1", "--steps", "3",
+                          "--warmup", "3", "--no-cpu-baseline"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline"):
+        assert k in d, k
+    assert d["steps"] == 3 and d["warmup"] == 3 and d["n_gpus"] == 1 and d["config"]["evals_per_step"] == 523
+    assert set(("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step", "cold_single_shot_ms")) <= set(d["e2e"])
+    assert set(("bound", "achieved", "peak", "unit", "frac", "traffic", "executed")) <= set(d["roofline"])
+    groups = d["roofline"]["executed"]["by_kernel_group"]
+    # the stand-in counts 900 builder ops with the counters on and 100 per enumeration: the split is by difference
+    assert groups["table_builders"]["mufu_ops_per_step"] == 900 and groups["enumeration"]["mufu_ops_per_step"] == 100
+    assert abs(groups["table_builders"]["share_of_kernel_time"] + groups["enumeration"]["share_of_kernel_time"] - 1) < 1e-12
+
+
+def test_default_workload_of_the_bench_is_config_3():
+    """no flags = BASELINE.json configs[2] at every N (one strong-scaling curve), with its own DRAM-traffic summary."""
+    import json
+    import subprocess
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--help"], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0
+    import re
+    assert re.search(r"--config\s*\{c1,c2,c3,c4,c5\}", out.stdout)
+    src = open(os.path.join(ROOT, "bench.py")).read()
+    assert 'add_argument("--config", default="c3"' in src
+    tj = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic_c3.json")))
+    assert tj["config"] == "c3" and tj["n_gpus"] == 1
+    assert tj["dram_bytes_read"] == sum(k["dram_bytes_read"] for k in tj["kernels"].values())
+    assert tj["dram_bytes_write"] == sum(k["dram_bytes_write"] for k in tj["kernels"].values())
 
 
 def test_the_binding_printed_in_integration_md_matches_the_library(built_library):

@@ -76,6 +76,7 @@ def test_pairs_reproduce_the_oracle(built_library, K, s, r):
     T = K ** (K - 1)
     idx = range(T) if T <= 700 else list(range(0, T, max(1, T // 200))) + [T - 1]
     n_reg = 0
+    memo = {}                        # the oracle's sub-tree messages for THIS D (pure-function cache, oracle/bamse_oracle.py)
     for i in idx:
         tree = orc.decode_tree(K, i)
         reg, fg, t = classify(lib, tree, s, r)
@@ -83,7 +84,7 @@ def test_pairs_reproduce_the_oracle(built_library, K, s, r):
             continue
         n_reg += 1
         assert 0 <= fg < nf and 0 <= t < nt
-        want = orc.tree_score_samples(tree, D[:, None, :], p0)[0]
+        want = orc.tree_score_samples(tree, D[:, None, :], p0, memo)[0]
         got = logsumexp(tab.FG[fg] + ctxs.row(t))
         assert got == pytest.approx(want, rel=1e-9), (K, s, r, i, tree, fg, t)
     if (K, s, r) in ((2, 1, 1), (3, 2, 1), (4, 2, 2), (5, 3, 3), (6, 4, 3), (6, 3, 4), (7, 4, 4)):
@@ -171,13 +172,14 @@ def test_pairs_at_the_default_geometry_of_large_k_reproduce_the_oracle(built_lib
     trees += [[-1] + list(range(K - 1)), [-1] + [0] * (K - 1), [-1, 0] + [1] * (K - 2), [-1] + [i // 2 for i in range(K - 1)],
               [K - 1] + [-1] + [1] * (K - 3) + [K - 2]]
     n_reg = 0
+    memo = {}
     for tree in trees:
         reg, fg, t = classify(lib, tree, s, r)
         if not reg:
             continue
         n_reg += 1
         assert 0 <= fg < nf and 0 <= t < nt
-        want = orc.tree_score_samples(tree, D[:, None, :], p0)[0]
+        want = orc.tree_score_samples(tree, D[:, None, :], p0, memo)[0]
         got = logsumexp(tab.FG[fg] + ctxs.row(t))
         assert got == pytest.approx(want, rel=1e-9), (K, s, r, tree, fg, t)
     assert n_reg >= len(trees) - (4 if K == 10 else 0)
