@@ -250,7 +250,7 @@ def run_reference_arm(args, rank, world):
     from bamse_b200 import workloads
     work = workloads.build(args.config)
     cores = os.cpu_count() or 1
-    per_step = max(cores, args.ref_items)
+    per_step = args.ref_items if args.ref_items > 0 else cores
     rates = []
     for _ in range(args.warmup):
         cpu_reference_rate(work, max(1, cores), cores, seed=99)
@@ -297,7 +297,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="fp32", choices=["fp32", "fp64"])
     ap.add_argument("--topk", type=int, default=5)
-    ap.add_argument("--ref-items", type=int, default=16, help="work items per step of the reference arm")
+    ap.add_argument("--ref-items", type=int, default=0,
+                    help="work items per step of the reference arm (default: one per host core, so a step lasts one item -- "
+                         "about 3 s on c2 and 14 s on c3 -- whatever the core count)")
     ap.add_argument("--cpu-items", type=int, default=0,
                     help="sample size of the cpu_baseline leg; default: 200 items (SURVEY 8d) where an item costs a few "
                          "core-seconds (c1, c2, c5), 96 on c3 (~14 core-seconds per item: 20 samples, 7 clusters), 32 on c4 "
