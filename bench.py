@@ -273,6 +273,31 @@ def run_reference_arm(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def run_other_config(name, args):
+    """A second configuration through this same script in a child process (one GPU, same build, same box, seconds
+    later), summarised under `also_measured`: with c3 as the default workload the line still carries c2, the default
+    of round 1.  Never fatal: a failing child is reported as an error string."""
+    try:
+        cmd = [sys.executable, os.path.abspath(__file__), "--gpus", "1", "--config", name, "--steps", str(args.steps),
+               "--warmup", str(args.warmup), "--precision", args.precision, "--topk", str(args.topk),
+               "--no-cpu-baseline", "--also", ""]
+        out = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+        lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+        if out.returncode != 0 or not lines:
+            return {"config": name, "error": ("rc %d: " % out.returncode) + out.stderr.strip()[-300:]}
+        d = json.loads(lines[-1])
+        ex = (d.get("roofline") or {}).get("executed") or {}
+        return {"config": d["config"]["workload"], "evals_per_step": d["config"]["evals_per_step"], "value": d["value"],
+                "unit": d["unit"], "ms_per_step": d["ms_per_step"], "steps": d["steps"], "warmup": d["warmup"],
+                "e2e": {k: d["e2e"].get(k) for k in ("value", "ms_per_step", "h2d_bytes_per_step", "d2h_bytes_per_step",
+                                                     "cold_single_shot_ms")},
+                "gpu_launches": d.get("gpu_launches"), "table_build_ms": ex.get("table_build_ms"),
+                "enumeration_ms": ex.get("enumeration_ms"), "xu_pipe_frac": ex.get("xu_pipe_frac"),
+                "clocks": d.get("clocks"), "note": "not the headline: `python bench.py --config %s` in a child process" % name}
+    except Exception as e:                                   # noqa: BLE001 -- an extra must never cost the headline
+        return {"config": name, "error": "%s: %s" % (type(e).__name__, str(e)[:300])}
+
+
 def config_dict(args, work, world):
     import collections
     ks = collections.Counter(int(c.As.shape[0]) for c in work["clusts"])
@@ -305,6 +330,9 @@ def main():
                          "core-seconds (c1, c2, c5), 96 on c3 (~14 core-seconds per item: 20 samples, 7 clusters), 32 on c4 "
                          "-- about a minute of wall time on 16 cores")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--also", default=None, choices=["", "c1", "c2", "c3", "c5"],
+                    help="one more configuration, measured by a child process after the headline and summarised under "
+                         "`also_measured` (one GPU only); default: c2 when the workload is c3, none otherwise; '' = none")
     ap.add_argument("--search-only", action="store_true",
                     help="not a bench line: run ONE pass of the early-exit search (for configurations whose full\n"
                          "scoring pass is too long, e.g. c4 = 3e9 trees) and print its own JSON")
@@ -315,6 +343,8 @@ def main():
                     help="debug: one GPU scores only shard 0 of W (what each rank of a W-GPU run does)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
+    if args.also is None:
+        args.also = "c2" if args.config == "c3" else ""
     if args.cpu_items <= 0:
         args.cpu_items = {"c3": 96, "c4": 32}.get(args.config, 200)
 
@@ -677,8 +707,11 @@ def main():
                          "tree": int(final["tree"][0, 0])}}
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_reference_rate(work, args.cpu_items, os.cpu_count() or 1)
-        print(json.dumps(line), flush=True)
     ctx.close()
+    if rank == 0:
+        if world == 1 and args.also and args.also != args.config and not args.lean:
+            line["also_measured"] = run_other_config(args.also, args)
+        print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

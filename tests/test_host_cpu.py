@@ -368,7 +368,7 @@ def test_bench_script_executes_end_to_end_with_stand_ins(built_library):
     import json
     import subprocess
     out = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "bench_dryrun.py"), "--config", "c1", "--steps", "3",
-                          "--warmup", "3", "--no-cpu-baseline"], capture_output=True, text=True, timeout=600)
+                          "--warmup", "3", "--no-cpu-baseline", "--also", "c2"], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stderr[-2000:]
     lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
     assert len(lines) == 1
@@ -379,6 +379,10 @@ def test_bench_script_executes_end_to_end_with_stand_ins(built_library):
     assert d["steps"] == 3 and d["warmup"] == 3 and d["n_gpus"] == 1 and d["config"]["evals_per_step"] == 523
     assert set(("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step", "cold_single_shot_ms")) <= set(d["e2e"])
     assert set(("bound", "achieved", "peak", "unit", "frac", "traffic", "executed")) <= set(d["roofline"])
+    # the second configuration runs the REAL script in a child process: without a GPU it must fail there (no CPU
+    # fallback) and leave the headline intact
+    if not has_cuda():
+        assert d["also_measured"]["config"] == "c2" and "no CUDA device" in d["also_measured"]["error"]
     groups = d["roofline"]["executed"]["by_kernel_group"]
     # the stand-in counts 900 builder ops with the counters on and 100 per enumeration: the split is by difference
     assert groups["table_builders"]["mufu_ops_per_step"] == 900 and groups["enumeration"]["mufu_ops_per_step"] == 100
