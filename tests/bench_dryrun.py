@@ -138,6 +138,10 @@ def main():
     torch.Tensor.pin_memory = lambda self, *a, **k: self
     torch.device = lambda *a, **k: _real_device("cpu")
     cuda_shim.Context = _Context
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:           # under torchrun: gloo stands in for NCCL
+        import torch.distributed as dist
+        real_init = dist.init_process_group
+        dist.init_process_group = lambda backend=None, **k: real_init("gloo")
     sys.argv = [os.path.join(ROOT, "bench.py")] + sys.argv[1:]
     print("DRY RUN (stand-ins for the CUDA runtime and the library context; numbers are meaningless)", file=sys.stderr)
     runpy.run_path(os.path.join(ROOT, "bench.py"), run_name="__main__")

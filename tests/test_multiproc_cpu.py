@@ -108,3 +108,26 @@ def test_two_rank_allgather_topk_equals_single_rank():
         merged = np.frombuffer(got[r], dtype=RECORD_DTYPE).reshape(P, topk)
         for f in ("total", "score", "clust", "tree"):
             np.testing.assert_array_equal(merged[f], want[f])
+
+
+@pytest.mark.timeout(300)
+def test_bench_script_under_torchrun_with_two_ranks_and_stand_ins():
+    """bench.py as the driver launches it for N > 1 (torch.distributed.run, one rank per GPU), on the stand-ins of
+    tests/bench_dryrun.py with gloo in place of NCCL: both ranks walk the same legs (every collective is matched, nobody
+    hangs), rank 0 alone prints the one line, and the line says n_gpus = 2.  Shape only."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", str(_free_port()), os.path.join(root, "tests", "bench_dryrun.py"), "--gpus", "2", "--config", "c1",
+           "--steps", "2", "--warmup", "3"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=280)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["n_gpus"] == 2 and d["steps"] == 2 and d["warmup"] == 3 and d["scaling"] == "strong"
+    assert "cpu_baseline" not in d and "also_measured" not in d          # rank 0 at N = 1 only
+    assert d["config"]["parallelism"].startswith("x2:")
+    assert d["gpu_launches"] > 0 and d["e2e"]["h2d_bytes_per_step"] > 0
