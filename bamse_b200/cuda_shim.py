@@ -297,6 +297,49 @@ class Context(object):
                           "ranking below the ties is best effort" % (self.last_topk_preselected, topk))
         return rec, par, cnt
 
+    def score_list_topk(self, item_clust, item_parent, item_nodes, clust_const, threshold=None, topk=1,
+                        precision=FP64):
+        """Explicit-list counterpart of score_topk (SURVEY 8b's `K_enum_mode = 0`): the top-`topk` of a GIVEN list of
+        full trees (nodes 0..K-1 in order: `scre` depends on the labels) instead of an index range.  The scores come from the GPU (bamse_score_list); `log scre`
+        (tree_tools.canonizeF, integer), the constants, the threshold rule (`score >= thr - 1e-12 |thr|`) and the
+        order (total desc, clustering asc, position in the list asc) are the ones of bamse_score_topk, in host fp64.
+        Returns (records [P][topk] -- `tree` holds the item's position in the list --, counts [P])."""
+        from .tree_tools import canonizeF
+        clust = np.ascontiguousarray(item_clust, dtype=np.int32)
+        par = np.ascontiguousarray(item_parent, dtype=np.int8)
+        n = len(clust)
+        if n and (clust.min() < 0 or clust.max() >= self.C):
+            raise ValueError("score_list_topk: clustering index out of range")
+        cc = np.ascontiguousarray(clust_const, dtype=np.float64).reshape(self.P, self.C)
+        th = None if threshold is None else np.ascontiguousarray(threshold, dtype=np.float64).reshape(self.P, self.C)
+        raw = self.score_list(clust, par, item_nodes, precision) if n else np.empty((self.P, 0))
+        logscre = np.empty(n)
+        for i in range(n):
+            K = int(self.K_of_c[clust[i]])
+            tree = [int(x) for x in par[i, :K]]
+            if [int(x) for x in np.asarray(item_nodes)[i][:K]] != list(range(K)) or (K < par.shape[1] and par[i, K] != -2):
+                raise ValueError("score_list_topk: item %d is not a full tree of its clustering" % i)
+            logscre[i] = np.log(canonizeF(tree)['scre'])
+        rec = np.zeros((self.P, topk), dtype=RECORD_DTYPE)
+        rec["clust"], rec["total"], rec["score"] = -1, -np.inf, -np.inf
+        cnt = np.zeros(self.P, dtype=np.int32)
+        for p in range(self.P):
+            rec["param"][p] = p
+            score = raw[p] + logscre
+            keep = ~np.isnan(score)
+            if th is not None:
+                t = th[p, clust]
+                keep &= score >= t - 1e-12 * np.abs(t)
+            idx = np.nonzero(keep)[0]
+            total = score[idx] + cc[p, clust[idx]]
+            order = idx[np.lexsort((idx, clust[idx], -total))][:topk]
+            cnt[p] = len(order)
+            rec["total"][p, :len(order)] = score[order] + cc[p, clust[order]]
+            rec["score"][p, :len(order)] = score[order]
+            rec["clust"][p, :len(order)] = clust[order]
+            rec["tree"][p, :len(order)] = order
+        return rec, cnt
+
     @property
     def last_topk_verified(self):
         """True when the last score_topk proved its preselection cut safe (identical to a full fp64 ranking)."""

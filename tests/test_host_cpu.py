@@ -503,3 +503,40 @@ def test_writers_are_byte_compatible_on_a_spread_of_trees(tmp_path):
         assert open(a).read() == g["subclones"], (K, M)
         assert open(b).read() == g["samples"], (K, M)
         assert open(c).read() == g["text"], (K, M)
+
+
+def test_explicit_list_topk_ranks_like_the_enumeration_rule():
+    """Context.score_list_topk (K_enum_mode = 0) with the GPU call replaced by the oracle's scores: constants,
+    `log scre`, threshold rule and tie order are host work and must reproduce a brute-force ranking of the same list."""
+    import bamse_oracle as orc
+    from bamse_b200.clustering import _pack_items
+    rng = np.random.default_rng(5)
+    K_of_c = [3, 4, 3]
+    tables = [np.array([[orc.distrib(int(a), int(b), 0.002)] for a, b in zip(rng.integers(5, 300, K), rng.integers(5, 300, K))])
+              for K in K_of_c]
+    tables[2] = tables[0]                                    # a duplicated clustering: exact ties, broken by the clustering index
+    ctx = object.__new__(cuda_shim.Context)
+    ctx.P, ctx.C, ctx.Kmax, ctx.K_of_c = 2, 3, 4, np.array(K_of_c, dtype=np.int32)
+    items = [(c, orc.decode_tree(K, i), list(range(K))) for c, K in enumerate(K_of_c) for i in range(K ** (K - 1))]
+    raw = np.array([orc.tree_score_samples(t, tables[c], orc.prior_const(len(t))).sum() for c, t, _ in items])
+    ctx.score_list = lambda clust, par, nod, precision: np.stack([raw, raw - 0.25 * np.asarray(clust)])
+    const = np.array([[0.0, 1.5, 0.0], [0.3, 0.0, 0.3]])
+    thr = np.array([[-np.inf, np.median(raw[9:]), -np.inf], [-np.inf, -np.inf, 1e9]])
+    rec, cnt = ctx.score_list_topk(*_pack_items(4, items), const, thr, topk=7)
+    for p in range(2):
+        rows = []
+        for i, (c, t, _) in enumerate(items):
+            s = (raw[i] if p == 0 else raw[i] - 0.25 * c) + math.log(orc.canon_weight(t)[1])
+            if s >= thr[p, c] - 1e-12 * abs(thr[p, c]):
+                rows.append((-(s + const[p, c]), c, i, s))
+        rows.sort()
+        assert cnt[p] == min(7, len(rows))
+        assert [(int(r["clust"]), int(r["tree"])) for r in rec[p, :cnt[p]]] == [(c, i) for _, c, i, _ in rows[:7]]
+        np.testing.assert_allclose(rec["score"][p, :cnt[p]], [s for _, _, _, s in rows[:7]], rtol=0, atol=0)
+    assert (rec["clust"][1] != 2).all()                      # an unreachable threshold removes a clustering
+    # clusterings 0 and 2 are the same tables with the same constant: their trees tie exactly, the lower clustering first
+    r0 = rec[0, :cnt[0]]
+    tied = [j for j in range(len(r0) - 1) if r0["total"][j] == r0["total"][j + 1]]
+    assert tied and all((int(r0["clust"][j]), int(r0["clust"][j + 1])) == (0, 2) for j in tied)
+    with pytest.raises(ValueError):
+        ctx.score_list_topk(*_pack_items(4, [(0, [-1, 0], [0, 1])]), const, None, topk=1)      # not a full tree
